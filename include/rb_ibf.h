@@ -1,0 +1,196 @@
+/*
+ * rb_ibf.h -- C ABI of the B200-native Interleaved Bloom Filter (IBF) engine.
+ *
+ * This is the drop-in boundary for ReadBouncer's IBF hot path.  The reference
+ * has no FFI layer: src/IBF (interleave::IBF, interleave::Read) calls seven
+ * entry points of an external SeqAn-2 `BinningDirectory<InterleavedBloomFilter>`
+ * directly.  Each function below names the reference interface it replaces
+ * (paths relative to the ReadBouncer tree).  The C++ shim that re-creates the
+ * interleave:: classes on top of this ABI is include/rb_interleave.hpp; the
+ * binding a ReadBouncer maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no exceptions cross the boundary; every
+ *    call returns an rb_status (0 = ok) or reports one through `status`.
+ *  - rb_last_error() returns a thread-local message for the last failure.
+ *  - "host" entry points take host buffers and include the H2D/D2H copies;
+ *    "_dev" entry points take device pointers (same device as the handle) and
+ *    only enqueue work on `stream` (a cudaStream_t passed as void*; NULL = the
+ *    legacy default stream).  Nothing here falls back to the CPU: without a
+ *    CUDA device the calls fail with RB_ERR_NO_DEVICE.
+ *  - handles are immutable after load/insert, so count calls on one handle may
+ *    run concurrently from several host threads on different streams.
+ *  - reads are ASCII (A/C/G/T/U any case, everything else = N), concatenated in
+ *    `bases`; read i is bases[read_off[i] .. read_off[i+1]).
+ */
+#ifndef RB_IBF_H_
+#define RB_IBF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RB_API __declspec(dllexport)
+#else
+#define RB_API __attribute__((visibility("default")))
+#endif
+
+typedef struct rb_ibf rb_ibf;      /* opaque device-resident filter            */
+typedef void *rb_stream;           /* cudaStream_t                              */
+
+/* Status codes; 1..8 map 1:1 onto the reference's exception classes
+ * (src/IBF/IBFExceptions.hpp). */
+typedef enum rb_status {
+    RB_OK = 0,
+    RB_ERR_NULL_FILTER = 1,       /* NullFilterException      :178 */
+    RB_ERR_SHORT_READ = 2,        /* ShortReadException       :96  */
+    RB_ERR_COUNT_KMER = 3,        /* CountKmerException       :123 */
+    RB_ERR_PARSE_IBF_FILE = 4,    /* ParseIBFFileException    :344 */
+    RB_ERR_MISSING_IBF_FILE = 5,  /* MissingIBFFileException  :317 */
+    RB_ERR_STORE_FILTER = 6,      /* StoreFilterException     :234 */
+    RB_ERR_INSERT_SEQUENCE = 7,   /* InsertSequenceException  :206 */
+    RB_ERR_INVALID_CONFIG = 8,    /* InvalidConfigException   :150 */
+    RB_ERR_ALLOC = 9,
+    RB_ERR_CUDA = 10,
+    RB_ERR_NO_DEVICE = 11,
+    RB_ERR_INVALID_ARG = 12
+} rb_status;
+
+RB_API const char *rb_status_string(int status);
+RB_API const char *rb_last_error(void);
+RB_API int rb_device_count(void);
+
+/* ---- filter metadata ----------------------------------------------------- */
+typedef struct rb_ibf_info_t {
+    uint64_t n_bins;        /* noOfBins (global)                                */
+    uint64_t n_hash;        /* noOfHashFunc                                     */
+    uint64_t kmer_size;     /* kmerSize                                         */
+    uint64_t n_bits;        /* payload bits (file bit length - 256)             */
+    uint64_t bin_width;     /* 64-bit words per row (global) = ceil(bins/64)    */
+    uint64_t n_blocks;      /* rows = n_bits / (64*bin_width)                   */
+    uint64_t col_begin;     /* first row word held by this handle (bin shard)   */
+    uint64_t col_words;     /* row words held by this handle                    */
+    uint64_t bin_begin;     /* first global bin held  = 64*col_begin            */
+    uint64_t n_bins_local;  /* bins held by this handle                         */
+    uint64_t device_bytes;  /* bytes of HBM used by the bit matrix              */
+    int32_t device;
+    int32_t shard, n_shards;
+} rb_ibf_info_t;
+
+/* ---- host-side scalar helpers (FP64, bit-exact with the reference) ------- */
+/* IBF::calculate_filter_size_bits, src/IBF/IBFBuild.cpp:404-413 */
+RB_API uint64_t rb_ibf_size_bits(uint64_t fragment_length, uint32_t kmer_size, uint32_t n_hash,
+                                 double max_fp, uint64_t n_bins);
+/* interleave::calculateCI, src/IBF/IBF.hpp:320-338 */
+RB_API int rb_calculate_ci(double error_rate, uint32_t kmer_size, uint32_t readlen, double significance,
+                           uint16_t *low, uint16_t *high);
+/* threshold of Read::find_matches / count_matches incl. the int16 -> uint16 wrap,
+ * src/IBF/IBFClassify.cpp:102-109,154-159; lut[len] for len in [0, 65536) */
+RB_API int rb_threshold_lut(double error_rate, double significance, uint32_t kmer_size,
+                            uint16_t *lut65536);
+/* IBF::cutOutNNNs + concatenation, src/IBF/IBFBuild.cpp:81-88,112-132.
+ * `out` needs `len` bytes; returns the new length. */
+RB_API uint64_t rb_cut_out_nnns(const char *seq, uint64_t len, char *out);
+/* fragment loop of add_sequences_to_filter, src/IBF/IBFBuild.cpp:165-202.
+ * Returns the number of fragments (= bin ids consumed); fills at most `cap`. */
+RB_API uint64_t rb_fragment_schedule(uint64_t seqlen, uint64_t fragment_length, uint32_t kmer_size,
+                                     uint64_t *begin, uint64_t *end, uint64_t cap);
+
+/* ---- filter life cycle ---------------------------------------------------- */
+/* TIbf(bins, hashes, k, bits) ctor, src/IBF/IBFBuild.cpp:465: zero-filled matrix in HBM */
+RB_API rb_ibf *rb_ibf_create(uint64_t n_bins, uint32_t n_hash, uint32_t kmer_size, uint64_t n_bits,
+                             int device, int *status);
+/* seqan::retrieve, src/IBF/IBFBuild.cpp:343,360 and src/config/configReader.cpp:216.
+ * Validates the sdsl header and metadata tail; a FASTA or truncated file fails
+ * with RB_ERR_PARSE_IBF_FILE, a missing one with RB_ERR_MISSING_IBF_FILE. */
+RB_API rb_ibf *rb_ibf_load(const char *path, int device, int *status);
+/* Bin-sharded load: this handle keeps only row words
+ * [shard*W/n_shards, (shard+1)*W/n_shards) of every row (W = bin_width). */
+RB_API rb_ibf *rb_ibf_load_shard(const char *path, int device, int shard, int n_shards, int *status);
+/* Upload from host memory: `words` = the n_bits/64 payload words in file order. */
+RB_API rb_ibf *rb_ibf_from_words(const uint64_t *words, uint64_t n_bins, uint32_t n_hash,
+                                 uint32_t kmer_size, uint64_t n_bits, int device, int shard,
+                                 int n_shards, int *status);
+/* seqan::store, src/IBF/IBFBuild.cpp:307,505: byte-identical sdsl bit_vector file (unsharded handles) */
+RB_API int rb_ibf_store(const rb_ibf *f, const char *path);
+/* D2H copy of the local payload words (n_blocks*col_words for a shard, n_bits/64 otherwise) */
+RB_API int rb_ibf_download(const rb_ibf *f, uint64_t *words, uint64_t n_words);
+RB_API void rb_ibf_free(rb_ibf *f);
+/* seqan::getNumberOfBins / getKmerSize, src/IBF/IBFBuild.cpp:380-381,466 */
+RB_API int rb_ibf_info(const rb_ibf *f, rb_ibf_info_t *out);
+/* Raw device pointer of the bit matrix (for zero-copy interop, e.g. torch.from_blob) */
+RB_API uint64_t *rb_ibf_device_words(const rb_ibf *f);
+
+/* ---- build: seqan::insertKmer(filter, fragment, bin), src/IBF/IBFBuild.cpp:189-190 ---- */
+/* For every fragment i: every k-mer of bases[frag_begin[i] .. frag_end[i]) sets bit
+ * (row(h_j(kmer)), frag_bin[i]) for all hash functions j.  Fragments shorter than k
+ * insert nothing; a bin outside this handle's bin range is skipped (bin shards) and a
+ * bin >= n_bins is reported as RB_ERR_INSERT_SEQUENCE. */
+RB_API int rb_ibf_insert_batch(rb_ibf *f, const char *bases, uint64_t n_bases,
+                               const uint64_t *frag_begin, const uint64_t *frag_end,
+                               const uint64_t *frag_bin, uint64_t n_frags, rb_stream stream);
+/* device-pointer variant; max_frag_len is a launch-shape hint (0 = unknown) */
+RB_API int rb_ibf_insert_batch_dev(rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_frag_begin,
+                                   const uint64_t *d_frag_end, const uint64_t *d_frag_bin,
+                                   uint64_t n_frags, uint64_t max_frag_len, rb_stream stream);
+
+/* ---- classify: seqan::count x2 + threshold + select/max_matches -------------------------
+ * Replaces, per read, Read::count_matches / find_matches (src/IBF/IBFClassify.cpp:81-171):
+ *   counts_fwd = seqan::count(filter, read), counts_rev = seqan::count(filter, revcomp(read)),
+ *   thr = lut[len], hit = select_matches(...), max_count = max_matches(...).
+ * n_lut thresholds tables (1 or 2; each uint16[65536]) are evaluated in the same pass so the
+ * error_rate-0.02 retry of check_unblock / classify_deplete_target needs no second launch.
+ *
+ * Outputs (any may be NULL): counts_* [n_reads][n_bins_local] dense per-bin counts;
+ * max_count/hit/argmax_bin [n_lut][n_reads]; argmax_bin = lowest global bin attaining
+ * max_count among bins passing the threshold, 0xFFFFFFFF if none;
+ * read_flag [n_reads]: 0 ok, 1 = shorter than k (ShortReadException), 2 = longer than 65535
+ * bases (not representable in the reference's uint16 readlen; not classified). */
+RB_API int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_off,
+                              uint64_t n_reads, const uint16_t *thr_lut, uint32_t n_lut,
+                              uint16_t *counts_fwd, uint16_t *counts_rev, uint16_t *max_count,
+                              uint8_t *hit, uint32_t *argmax_bin, uint8_t *read_flag,
+                              rb_stream stream);
+
+/* Packed per-read summary key used by the device API and the bin-sharded combine:
+ *   bit 63      hit (some bin passes the threshold)
+ *   bits 47..32 max_count
+ *   bits 31..0  ~argmax_bin   (so that a 64-bit MAX picks the lowest bin on ties)
+ * key == 0 means no bin passed.  The elementwise MAX of the keys of all bin shards is the key of
+ * the whole filter, which is what the NCCL combine of the bin-sharded mode reduces. */
+#define RB_KEY_HIT(key) ((uint8_t)((key) >> 63))
+#define RB_KEY_MAX_COUNT(key) ((uint16_t)(((key) >> 32) & 0xFFFFu))
+#define RB_KEY_ARGMAX_BIN(key) ((key) ? ~(uint32_t)((key) & 0xFFFFFFFFu) : 0xFFFFFFFFu)
+
+/* Device-pointer variant.  d_keys [n_lut][n_reads] (required) receives the packed summaries;
+ * d_counts_* and d_read_flag may be NULL.  max_read_len (>= every read length, 0 = assume
+ * 65535) only selects kernel variants.  Work is enqueued on `stream`; no host sync. */
+RB_API int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_read_off,
+                                  uint64_t n_reads, uint32_t max_read_len, const uint16_t *d_thr_lut,
+                                  uint32_t n_lut, uint64_t *d_keys, uint16_t *d_counts_fwd,
+                                  uint16_t *d_counts_rev, uint8_t *d_read_flag, rb_stream stream);
+/* Unpack keys on the device into max_count / hit / argmax_bin arrays (any may be NULL). */
+RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_max_count, uint8_t *d_hit,
+                              uint32_t *d_argmax_bin, int device, rb_stream stream);
+
+/* Kernel selection override for tests/benchmarks: 0 auto, 1 warp-per-read tile kernel,
+ * 2 CTA-per-read streaming kernel. */
+RB_API int rb_set_count_kernel(int which);
+/* Number of kernels this library launched since load (all threads); evidence for gpu_launches. */
+RB_API uint64_t rb_kernel_launches(void);
+
+/* Measurement aid (not on the product path): uniformly random row-aligned loads of row_bytes
+ * (8, 16 or 32) over d_buf[n_rows*row_bytes]; n_blocks CTAs of 256 threads, probes_per_thread
+ * loads each (8 in flight).  Establishes the random-sector roofline of SURVEY.md section 8d. */
+RB_API int rb_microbench_gather(const void *d_buf, uint64_t n_rows, uint32_t row_bytes,
+                                uint64_t probes_per_thread, uint32_t n_blocks, uint64_t *d_sink,
+                                rb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RB_IBF_H_ */

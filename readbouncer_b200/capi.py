@@ -1,0 +1,295 @@
+"""ctypes binding of librb_ibf.so (the C ABI in include/rb_ibf.h).
+
+Fails loudly when the library is missing or no CUDA device is usable: there is no
+CPU or PyTorch fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIB = os.path.join(_HERE, "lib", "librb_ibf.so")
+_lib = None
+
+RB_OK = 0
+STATUS = {0: "ok", 1: "NullFilterException", 2: "ShortReadException", 3: "CountKmerException",
+          4: "ParseIBFFileException", 5: "MissingIBFFileException", 6: "StoreFilterException",
+          7: "InsertSequenceException", 8: "InvalidConfigException", 9: "out of memory", 10: "CUDA error",
+          11: "no CUDA device", 12: "invalid argument"}
+MAX_LUT = 4
+LUT_SIZE = 65536
+
+EXPORTS = [
+    "rb_status_string", "rb_last_error", "rb_device_count", "rb_ibf_size_bits", "rb_calculate_ci",
+    "rb_threshold_lut", "rb_cut_out_nnns", "rb_fragment_schedule", "rb_ibf_create", "rb_ibf_load",
+    "rb_ibf_load_shard", "rb_ibf_from_words", "rb_ibf_store", "rb_ibf_download", "rb_ibf_free", "rb_ibf_info",
+    "rb_ibf_device_words", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
+    "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_kernel_launches",
+    "rb_microbench_gather",
+]
+
+
+class RBError(RuntimeError):
+    def __init__(self, status, message=""):
+        super().__init__("%s (%d)%s" % (STATUS.get(status, "?"), status, ": " + message if message else ""))
+        self.status = status
+
+
+class _Info(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_bins", "n_hash", "kmer_size", "n_bits", "bin_width", "n_blocks",
+                                          "col_begin", "col_words", "bin_begin", "n_bins_local", "device_bytes")] + \
+               [("device", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32)]
+
+
+def lib_path():
+    return _LIB
+
+
+def build_library(force=False):
+    """Compile librb_ibf.so in-tree with nvcc for sm_100a (see csrc/Makefile)."""
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "rb_ibf.h"))
+    stale = not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    if force or stale:
+        cmd = ["make", "-C", _CSRC, "-j4"] + (["-B"] if force else [])
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise RuntimeError("librb_ibf.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `make -C readbouncer_b200/csrc`.  There is no CPU fallback." % _LIB)
+    L = C.CDLL(_LIB)
+    vp, u64, u32, i32, dbl = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
+    ip = C.POINTER(C.c_int)
+    sig = {
+        "rb_status_string": (C.c_char_p, [i32]),
+        "rb_last_error": (C.c_char_p, []),
+        "rb_device_count": (i32, []),
+        "rb_ibf_size_bits": (u64, [u64, u32, u32, dbl, u64]),
+        "rb_calculate_ci": (i32, [dbl, u32, u32, dbl, vp, vp]),
+        "rb_threshold_lut": (i32, [dbl, dbl, u32, vp]),
+        "rb_cut_out_nnns": (u64, [C.c_char_p, u64, C.c_char_p]),
+        "rb_fragment_schedule": (u64, [u64, u64, u32, vp, vp, u64]),
+        "rb_ibf_create": (vp, [u64, u32, u32, u64, i32, ip]),
+        "rb_ibf_load": (vp, [C.c_char_p, i32, ip]),
+        "rb_ibf_load_shard": (vp, [C.c_char_p, i32, i32, i32, ip]),
+        "rb_ibf_from_words": (vp, [vp, u64, u32, u32, u64, i32, i32, i32, ip]),
+        "rb_ibf_store": (i32, [vp, C.c_char_p]),
+        "rb_ibf_download": (i32, [vp, vp, u64]),
+        "rb_ibf_free": (None, [vp]),
+        "rb_ibf_info": (i32, [vp, C.POINTER(_Info)]),
+        "rb_ibf_device_words": (vp, [vp]),
+        "rb_ibf_insert_batch": (i32, [vp, vp, u64, vp, vp, vp, u64, vp]),
+        "rb_ibf_insert_batch_dev": (i32, [vp, vp, vp, vp, vp, u64, u64, vp]),
+        "rb_ibf_count_batch": (i32, [vp, vp, vp, u64, vp, u32, vp, vp, vp, vp, vp, vp, vp]),
+        "rb_ibf_count_batch_dev": (i32, [vp, vp, vp, u64, u32, vp, u32, vp, vp, vp, vp, vp]),
+        "rb_keys_decode_dev": (i32, [vp, u64, vp, vp, vp, i32, vp]),
+        "rb_set_count_kernel": (i32, [i32]),
+        "rb_kernel_launches": (u64, []),
+        "rb_microbench_gather": (i32, [vp, u64, u32, u64, u32, vp, vp]),
+    }
+    assert sorted(sig) == sorted(EXPORTS)
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _check(status):
+    if status != RB_OK:
+        raise RBError(status, lib().rb_last_error().decode(errors="replace"))
+
+
+def _np_ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _dev_ptr(t):
+    """Device pointer of a torch CUDA tensor (or an int / None passed through)."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    assert t.is_cuda and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(stream.cuda_stream)      # torch.cuda.Stream
+
+
+# ---- scalar helpers -------------------------------------------------------------------------------
+def device_count():
+    return int(lib().rb_device_count())
+
+
+def kernel_launches():
+    return int(lib().rb_kernel_launches())
+
+
+def set_count_kernel(which):
+    _check(lib().rb_set_count_kernel(int(which)))
+
+
+def microbench_gather(d_buf, n_rows, row_bytes, probes_per_thread, n_blocks, d_sink, stream=None):
+    _check(lib().rb_microbench_gather(_dev_ptr(d_buf), n_rows, row_bytes, probes_per_thread, n_blocks,
+                                      _dev_ptr(d_sink), _stream_ptr(stream)))
+
+
+def ibf_size_bits(fragment_length, kmer_size=13, n_hash=3, max_fp=0.01, n_bins=1):
+    return int(lib().rb_ibf_size_bits(fragment_length, kmer_size, n_hash, max_fp, n_bins))
+
+
+def calculate_ci(error_rate, kmer_size, readlen, significance=0.95):
+    lo, hi = C.c_uint16(), C.c_uint16()
+    _check(lib().rb_calculate_ci(error_rate, kmer_size, readlen, significance, C.addressof(lo), C.addressof(hi)))
+    return lo.value, hi.value
+
+
+def threshold_lut(error_rate, kmer_size, significance=0.95):
+    out = np.zeros(LUT_SIZE, np.uint16)
+    _check(lib().rb_threshold_lut(error_rate, significance, kmer_size, _np_ptr(out)))
+    return out
+
+
+def cut_out_nnns(seq):
+    s = seq if isinstance(seq, (bytes, bytearray)) else seq.encode()
+    out = C.create_string_buffer(len(s) + 1)
+    n = lib().rb_cut_out_nnns(s, len(s), out)
+    return out.raw[:n]
+
+
+def fragment_schedule(seqlen, fragment_length, kmer_size):
+    n = int(lib().rb_fragment_schedule(seqlen, fragment_length, kmer_size, None, None, 0))
+    b = np.zeros(max(n, 1), np.uint64)
+    e = np.zeros(max(n, 1), np.uint64)
+    lib().rb_fragment_schedule(seqlen, fragment_length, kmer_size, _np_ptr(b), _np_ptr(e), n)
+    return b[:n], e[:n]
+
+
+def keys_decode(keys):
+    """numpy decode of packed summary keys (see RB_KEY_* in rb_ibf.h)."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    hit = (keys >> np.uint64(63)).astype(np.uint8)
+    mx = ((keys >> np.uint64(32)) & np.uint64(0xFFFF)).astype(np.uint16)
+    am = np.where(keys != 0, ~(keys & np.uint64(0xFFFFFFFF)) & np.uint64(0xFFFFFFFF), np.uint64(0xFFFFFFFF))
+    return mx, hit, am.astype(np.uint32)
+
+
+# ---- filter handle ------------------------------------------------------------------------------------
+class IBF:
+    """Device-resident Interleaved Bloom Filter (wraps an rb_ibf*)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        info = _Info()
+        _check(lib().rb_ibf_info(self._h, C.byref(info)))
+        for name, _ in _Info._fields_:
+            setattr(self, name, int(getattr(info, name)))
+        self.k = self.kmer_size
+        self.n_local_words = self.device_bytes // 8
+
+    @staticmethod
+    def _wrap(h, st):
+        if not h:
+            raise RBError(st.value, lib().rb_last_error().decode(errors="replace"))
+        return IBF(h)
+
+    @classmethod
+    def create(cls, n_bins, n_hash, kmer_size, n_bits, device=0):
+        st = C.c_int(0)
+        return cls._wrap(lib().rb_ibf_create(n_bins, n_hash, kmer_size, n_bits, device, C.byref(st)), st)
+
+    @classmethod
+    def load(cls, path, device=0, shard=0, n_shards=1):
+        st = C.c_int(0)
+        return cls._wrap(lib().rb_ibf_load_shard(str(path).encode(), device, shard, n_shards, C.byref(st)), st)
+
+    @classmethod
+    def from_words(cls, words, n_bins, n_hash, kmer_size, n_bits, device=0, shard=0, n_shards=1):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        assert words.size >= n_bits // 64
+        st = C.c_int(0)
+        return cls._wrap(lib().rb_ibf_from_words(_np_ptr(words), n_bins, n_hash, kmer_size, n_bits, device, shard,
+                                                 n_shards, C.byref(st)), st)
+
+    def store(self, path):
+        _check(lib().rb_ibf_store(self._h, str(path).encode()))
+
+    def download(self):
+        out = np.zeros(self.n_local_words, np.uint64)
+        _check(lib().rb_ibf_download(self._h, _np_ptr(out), out.size))
+        return out
+
+    def device_words_ptr(self):
+        return int(lib().rb_ibf_device_words(self._h) or 0)
+
+    # ---- build -----------------------------------------------------------------------------------
+    def insert_batch(self, bases, frag_begin, frag_end, frag_bin, stream=None):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        fb = np.ascontiguousarray(frag_begin, dtype=np.uint64)
+        fe = np.ascontiguousarray(frag_end, dtype=np.uint64)
+        fbin = np.ascontiguousarray(frag_bin, dtype=np.uint64)
+        assert fb.size == fe.size == fbin.size
+        _check(lib().rb_ibf_insert_batch(self._h, _np_ptr(bases), bases.size, _np_ptr(fb), _np_ptr(fe), _np_ptr(fbin),
+                                         fb.size, _stream_ptr(stream)))
+
+    def insert_batch_dev(self, d_bases, d_frag_begin, d_frag_end, d_frag_bin, n_frags, max_frag_len=0, stream=None):
+        _check(lib().rb_ibf_insert_batch_dev(self._h, _dev_ptr(d_bases), _dev_ptr(d_frag_begin), _dev_ptr(d_frag_end),
+                                             _dev_ptr(d_frag_bin), n_frags, max_frag_len, _stream_ptr(stream)))
+
+    # ---- classify --------------------------------------------------------------------------------
+    def count_batch(self, bases, read_off, thr_lut, dense=False, stream=None):
+        """Host-buffer classify call.  thr_lut: uint16 [n_lut, 65536] (or [65536]).
+        Returns dict with max_count/hit/argmax_bin of shape [n_lut, n] (squeezed when n_lut == 1),
+        read_flag [n] and, with dense=True, counts_fwd/counts_rev [n, n_bins_local]."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+        lut = np.ascontiguousarray(thr_lut, dtype=np.uint16).reshape(-1, LUT_SIZE)
+        n, n_lut = read_off.size - 1, lut.shape[0]
+        res = {
+            "max_count": np.zeros((n_lut, n), np.uint16), "hit": np.zeros((n_lut, n), np.uint8),
+            "argmax_bin": np.zeros((n_lut, n), np.uint32), "read_flag": np.zeros(n, np.uint8),
+            "counts_fwd": np.zeros((n, self.n_bins_local), np.uint16) if dense else None,
+            "counts_rev": np.zeros((n, self.n_bins_local), np.uint16) if dense else None,
+        }
+        _check(lib().rb_ibf_count_batch(self._h, _np_ptr(bases), _np_ptr(read_off), n, _np_ptr(lut), n_lut,
+                                        _np_ptr(res["counts_fwd"]), _np_ptr(res["counts_rev"]),
+                                        _np_ptr(res["max_count"]), _np_ptr(res["hit"]), _np_ptr(res["argmax_bin"]),
+                                        _np_ptr(res["read_flag"]), _stream_ptr(stream)))
+        if n_lut == 1:
+            for key in ("max_count", "hit", "argmax_bin"):
+                res[key] = res[key][0]
+        return res
+
+    def count_batch_dev(self, d_bases, d_read_off, n_reads, d_thr_lut, n_lut, d_keys, max_read_len=0,
+                        d_counts_fwd=None, d_counts_rev=None, d_read_flag=None, stream=None):
+        """Device-pointer classify call: enqueues on `stream`, no host synchronisation."""
+        _check(lib().rb_ibf_count_batch_dev(self._h, _dev_ptr(d_bases), _dev_ptr(d_read_off), n_reads, max_read_len,
+                                            _dev_ptr(d_thr_lut), n_lut, _dev_ptr(d_keys), _dev_ptr(d_counts_fwd),
+                                            _dev_ptr(d_counts_rev), _dev_ptr(d_read_flag), _stream_ptr(stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rb_ibf_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

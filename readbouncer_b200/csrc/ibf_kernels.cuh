@@ -1,0 +1,49 @@
+// ibf_kernels.cuh -- launch interfaces of the sm_100a kernels (internal to the library).
+#pragma once
+
+#include "ibf_common.cuh"
+
+namespace rb {
+
+// View of one handle's slice of the bit matrix, as the kernels see it.
+struct FilterView {
+    const uint64_t *words;   // row r starts at words + r * stride
+    uint64_t stride;         // local row width in 64-bit words (col_words)
+    uint64_t bin_begin;      // global bin index of local bit 0
+    uint64_t n_bins_local;   // valid local bins (the last word may be partial)
+    HashParams hp;
+};
+
+struct CountArgs {
+    FilterView fv;
+    const uint8_t *bases;       // ASCII
+    const uint64_t *read_off;   // [n_reads + 1]
+    uint64_t n_reads;
+    const uint16_t *lut;        // [n_lut][65536], already cast to uint16
+    uint32_t n_lut;
+    uint64_t *keys;             // [n_lut][n_reads]
+    uint16_t *counts_fwd;       // [n_reads][n_bins_local] or null
+    uint16_t *counts_rev;
+    uint8_t *read_flag;         // [n_reads] or null
+};
+
+struct InsertArgs {
+    uint64_t *words;
+    uint64_t stride;
+    uint64_t bin_begin;      // first global bin held by this handle
+    uint64_t bin_end;        // one past the last global bin held
+    uint64_t n_bins;         // global bin count (bins >= this are an error)
+    HashParams hp;
+    const uint8_t *bases;
+    const uint64_t *frag_begin, *frag_end, *frag_bin;
+    uint64_t n_frags;
+    unsigned int *error_flag;  // set to 1 when a fragment names a bin >= n_bins
+};
+
+// which: 0 auto, 1 tile kernel, 2 streaming kernel.  Returns number of kernel launches or <0.
+int launch_count(const CountArgs &a, uint32_t max_read_len, int which, int sm_count, cudaStream_t st);
+int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cudaStream_t st);
+int launch_keys_decode(const uint64_t *keys, uint64_t n, uint16_t *max_count, uint8_t *hit,
+                       uint32_t *argmax_bin, cudaStream_t st);
+
+}  // namespace rb

@@ -1,0 +1,62 @@
+// ibf_microbench.cu -- random-sector gather microbenchmark.
+//
+// Establishes the measured ceiling for the tile kernel's access pattern (SURVEY.md section 8d:
+// "a random-32B-gather microbenchmark must be added to establish the random-sector ceilings"):
+// every thread issues independent, uniformly random, row-aligned loads of ROWB bytes over a
+// buffer, 8 in flight per thread, and XOR-folds them into a sink so nothing is optimised away.
+#include "../../include/rb_ibf.h"
+#include "ibf_common.cuh"
+
+namespace rb {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+template <int ROWB>
+__global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__ buf, uint64_t n_rows, uint64_t magic,
+                                                     uint64_t probes_per_thread, uint64_t *sink)
+{
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t acc = 0;
+    for (uint64_t it = 0; it < probes_per_thread; it += 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            uint64_t row = fast_mod(mix64(tid * 0x100000001B3ULL + it + u), n_rows, magic);
+            const uint8_t *p = buf + row * ROWB;
+            if constexpr (ROWB == 8) v[u] = __ldg(reinterpret_cast<const uint64_t *>(p));
+            else if constexpr (ROWB == 16) { ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(p)); v[u] = t.x ^ t.y; }
+            else {
+                ulonglong2 t0 = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+                ulonglong2 t1 = __ldg(reinterpret_cast<const ulonglong2 *>(p) + 1);
+                v[u] = t0.x ^ t0.y ^ t1.x ^ t1.y;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc ^= v[u];
+    }
+    if (acc == 0x123456789ABCDEFULL) sink[0] = acc;   // practically never; keeps the loads live
+}
+
+}  // namespace rb
+
+extern "C" RB_API int rb_microbench_gather(const void *d_buf, uint64_t n_rows, uint32_t row_bytes,
+                                           uint64_t probes_per_thread, uint32_t n_blocks, uint64_t *d_sink,
+                                           rb_stream stream)
+{
+    if (!d_buf || !d_sink || n_rows == 0 || n_blocks == 0) return RB_ERR_INVALID_ARG;
+    const uint64_t magic = rb::mod_magic(n_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    probes_per_thread = (probes_per_thread + 7) / 8 * 8;
+    const uint8_t *b = static_cast<const uint8_t *>(d_buf);
+    if (row_bytes == 8) rb::gather_kernel<8><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
+    else if (row_bytes == 16) rb::gather_kernel<16><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
+    else if (row_bytes == 32) rb::gather_kernel<32><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
+    else return RB_ERR_INVALID_ARG;
+    return cudaGetLastError() == cudaSuccess ? RB_OK : RB_ERR_CUDA;
+}

@@ -1,0 +1,708 @@
+// rb_ibf_api.cu -- the C ABI declared in include/rb_ibf.h.
+//
+// Host side of the drop-in boundary: filter life cycle (sdsl/SeqAn file format, HBM
+// residency, optional bin sharding and L2 persistence), the FP64 scalar helpers that must
+// agree bit for bit with the reference (thresholds, sizing), and the batch entry points
+// that enqueue the kernels of ibf_count.cu / ibf_insert.cu.  There is no CPU fallback:
+// every compute entry point fails with RB_ERR_NO_DEVICE when no CUDA device is usable.
+#include "../../include/rb_ibf.h"
+#include "ibf_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_count_kernel{0};
+
+int fail(int status, const std::string &msg)
+{
+    g_last_error = msg;
+    return status;
+}
+
+#define RB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? RB_ERR_ALLOC : RB_ERR_CUDA,             \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                      \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+struct rb_ibf {
+    int device = 0, shard = 0, n_shards = 1, sm_count = 148;
+    uint64_t n_bins = 0, n_hash = 0, k = 0, n_bits = 0, bin_width = 0, n_blocks = 0;
+    uint64_t col_begin = 0, col_words = 0, n_bins_local = 0;
+    uint64_t n_local_words = 0;   // words allocated in HBM
+    uint64_t *d_words = nullptr;
+    unsigned int *d_err = nullptr;
+    bool l2_persist = false;
+    rb::HashParams hp{};
+};
+
+namespace {
+
+// ---- host FP64 helpers ---------------------------------------------------------------------
+// RationalApproximation / NormalCDFInverse, src/IBF/IBF.hpp:268-308
+double rational_approx(double t)
+{
+    const double c0 = 2.515517, c1 = 0.802853, c2 = 0.010328;
+    const double d0 = 1.432788, d1 = 0.189269, d2 = 0.001308;
+    return t - ((c2 * t + c1) * t + c0) / (((d2 * t + d1) * t + d0) * t + 1.0);
+}
+
+double normal_cdf_inverse(double p)
+{
+    return p < 0.5 ? -rational_approx(std::sqrt(-2.0 * std::log(p)))
+                   : rational_approx(std::sqrt(-2.0 * std::log(1.0 - p)));
+}
+
+uint16_t cast_u16(double x) { return (uint16_t)(int64_t)x; }
+
+// calculateCI, src/IBF/IBF.hpp:320-338 (kmer_size arrives as uint8_t there)
+void calculate_ci(double r, uint32_t kmer_size, uint32_t readlen, double confidence, uint16_t *lo, uint16_t *hi)
+{
+    const double k = (double)(uint8_t)kmer_size;
+    const double q = 1.0 - std::pow(1.0 - r, k);
+    const double L = ((double)readlen - k + 1.0);
+    const double varN = L * (1.0 - q) * (q * (2.0 * k + (2.0 / r) - 1.0) - 2.0 * k)
+                        + k * (k - 1.0) * std::pow((1.0 - q), 2.0)
+                        + (2.0 * (1.0 - q) / (std::pow(r, 2.0))) * ((1.0 + (k - 1.0) * (1.0 - q)) * r - q);
+    const double alpha = 1 - confidence;
+    const double z = normal_cdf_inverse(1.0 - alpha / 2.0);
+    if (lo) *lo = cast_u16(std::floor(L * q - z * std::sqrt(varN)));
+    if (hi) *hi = cast_u16(std::ceil(L * q + z * std::sqrt(varN)));
+}
+
+int check_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(RB_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(RB_ERR_INVALID_ARG, "device index out of range");
+    return RB_OK;
+}
+
+int derive_geometry(rb_ibf *f, int shard, int n_shards)
+{
+    if (f->n_bins == 0 || f->n_hash == 0 || f->n_hash > (uint64_t)rb::kMaxHash || f->k == 0 || f->k > 32)
+        return fail(RB_ERR_INVALID_CONFIG, "bins/hash functions/k-mer size out of range");
+    if (f->n_bits == 0 || (f->n_bits % 64) != 0) return fail(RB_ERR_INVALID_CONFIG, "filter size must be a positive multiple of 64 bits");
+    f->bin_width = (f->n_bins + 63) / 64;
+    f->n_blocks = f->n_bits / (64 * f->bin_width);
+    if (f->n_blocks == 0) return fail(RB_ERR_INVALID_CONFIG, "filter smaller than one row");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(RB_ERR_INVALID_ARG, "bad shard index");
+    f->shard = shard;
+    f->n_shards = n_shards;
+    f->col_begin = f->bin_width * (uint64_t)shard / (uint64_t)n_shards;
+    const uint64_t col_end = f->bin_width * (uint64_t)(shard + 1) / (uint64_t)n_shards;
+    f->col_words = col_end - f->col_begin;
+    if (f->col_words == 0) return fail(RB_ERR_INVALID_ARG, "more shards than row words");
+    const uint64_t bin_end = std::min<uint64_t>(f->n_bins, 64 * col_end);
+    f->n_bins_local = bin_end - 64 * f->col_begin;
+    f->n_local_words = n_shards == 1 ? f->n_bits / 64 : f->n_blocks * f->col_words;
+    f->hp = rb::make_hash_params(f->n_blocks, (uint32_t)f->k, (uint32_t)f->n_hash);
+    return RB_OK;
+}
+
+int alloc_device(rb_ibf *f, bool zero)
+{
+    RB_CUDA(cudaSetDevice(f->device));
+    cudaDeviceProp prop{};
+    RB_CUDA(cudaGetDeviceProperties(&prop, f->device));
+    f->sm_count = prop.multiProcessorCount;
+    RB_CUDA(cudaMalloc(&f->d_words, f->n_local_words * 8));
+    RB_CUDA(cudaMalloc(&f->d_err, sizeof(unsigned int)));
+    RB_CUDA(cudaMemset(f->d_err, 0, sizeof(unsigned int)));
+    if (zero) RB_CUDA(cudaMemset(f->d_words, 0, f->n_local_words * 8));
+    // a filter that fits the persisting-L2 carve-out is pinned there for count launches
+    const size_t bytes = f->n_local_words * 8;
+    if (prop.persistingL2CacheMaxSize > 0 && bytes <= (size_t)prop.persistingL2CacheMaxSize &&
+        bytes <= (size_t)prop.accessPolicyMaxWindowSize) {
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) == cudaSuccess) f->l2_persist = true;
+        else cudaGetLastError();
+    }
+    return RB_OK;
+}
+
+void destroy(rb_ibf *f)
+{
+    if (!f) return;
+    if (f->d_words || f->d_err) {
+        DeviceGuard g(f->device);
+        if (f->d_words) cudaFree(f->d_words);
+        if (f->d_err) cudaFree(f->d_err);
+    }
+    delete f;
+}
+
+// copy `rows` rows of the host matrix (row pitch = bin_width words) into the local slice
+int upload_rows(rb_ibf *f, const uint64_t *host_rows, uint64_t row0, uint64_t rows, cudaStream_t st)
+{
+    RB_CUDA(cudaMemcpy2DAsync(f->d_words + row0 * f->col_words, f->col_words * 8, host_rows + f->col_begin,
+                              f->bin_width * 8, f->col_words * 8, rows, cudaMemcpyHostToDevice, st));
+    return RB_OK;
+}
+
+struct PinnedPair {
+    uint64_t *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    size_t words = 0;
+    int init(size_t w)
+    {
+        words = w;
+        RB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            RB_CUDA(cudaMallocHost(&buf[i], w * 8));
+            RB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        return RB_OK;
+    }
+    ~PinnedPair()
+    {
+        for (int i = 0; i < 2; ++i) {
+            if (buf[i]) cudaFreeHost(buf[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+        }
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+constexpr size_t kStageBytes = 64u << 20;
+
+int sticky_insert_error(const rb_ibf *f)
+{
+    unsigned int flag = 0;
+    RB_CUDA(cudaMemcpy(&flag, f->d_err, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(f->d_err, 0, sizeof(flag));
+        return fail(RB_ERR_INSERT_SEQUENCE, "a fragment named a bin >= number of bins (not inserted)");
+    }
+    return RB_OK;
+}
+
+rb::FilterView view_of(const rb_ibf *f)
+{
+    rb::FilterView v{};
+    v.words = f->d_words;
+    v.stride = f->col_words;
+    v.bin_begin = 64 * f->col_begin;
+    v.n_bins_local = f->n_bins_local;
+    v.hp = f->hp;
+    return v;
+}
+
+// RAII for the L2 access-policy window around count launches
+struct L2Window {
+    cudaStream_t st;
+    bool active = false;
+    L2Window(const rb_ibf *f, cudaStream_t s) : st(s)
+    {
+        if (!f->l2_persist) return;
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = f->d_words;
+        attr.accessPolicyWindow.num_bytes = f->n_local_words * 8;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) active = true;
+        else cudaGetLastError();
+    }
+    ~L2Window()
+    {
+        if (!active) return;
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
+};
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char *rb_status_string(int status)
+{
+    switch (status) {
+    case RB_OK: return "ok";
+    case RB_ERR_NULL_FILTER: return "NullFilterException";
+    case RB_ERR_SHORT_READ: return "ShortReadException";
+    case RB_ERR_COUNT_KMER: return "CountKmerException";
+    case RB_ERR_PARSE_IBF_FILE: return "ParseIBFFileException";
+    case RB_ERR_MISSING_IBF_FILE: return "MissingIBFFileException";
+    case RB_ERR_STORE_FILTER: return "StoreFilterException";
+    case RB_ERR_INSERT_SEQUENCE: return "InsertSequenceException";
+    case RB_ERR_INVALID_CONFIG: return "InvalidConfigException";
+    case RB_ERR_ALLOC: return "out of memory";
+    case RB_ERR_CUDA: return "CUDA error";
+    case RB_ERR_NO_DEVICE: return "no CUDA device";
+    case RB_ERR_INVALID_ARG: return "invalid argument";
+    default: return "unknown status";
+    }
+}
+
+const char *rb_last_error(void) { return g_last_error.c_str(); }
+
+int rb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+uint64_t rb_kernel_launches(void) { return g_launches.load(); }
+
+int rb_set_count_kernel(int which)
+{
+    if (which < 0 || which > 2) return fail(RB_ERR_INVALID_ARG, "kernel selector must be 0, 1 or 2");
+    g_count_kernel.store(which);
+    return RB_OK;
+}
+
+// ---- scalar helpers ----------------------------------------------------------------------------
+uint64_t rb_ibf_size_bits(uint64_t fragment_length, uint32_t kmer_size, uint32_t n_hash, double max_fp,
+                          uint64_t n_bins)
+{
+    // IBF::calculate_filter_size_bits, src/IBF/IBFBuild.cpp:404-413
+    const uint64_t max_kmer_count = fragment_length - kmer_size + 1;
+    const uint64_t optimal_bins = (uint64_t)(std::floor(((double)n_bins / 64.0) + 1) * 64);
+    const uint64_t bin_size_bits = (uint64_t)std::ceil(
+        -1 / (std::pow(1 - std::pow(max_fp, 1.0 / (double)n_hash), 1.0 / ((double)(n_hash * max_kmer_count))) - 1));
+    return bin_size_bits * optimal_bins;
+}
+
+int rb_calculate_ci(double error_rate, uint32_t kmer_size, uint32_t readlen, double significance, uint16_t *low,
+                    uint16_t *high)
+{
+    if (!(error_rate > 0.0 && error_rate < 1.0) || !(significance > 0.0 && significance < 1.0))
+        return fail(RB_ERR_INVALID_CONFIG, "error rate and significance must be in (0, 1)");
+    calculate_ci(error_rate, kmer_size, readlen, significance, low, high);
+    return RB_OK;
+}
+
+int rb_threshold_lut(double error_rate, double significance, uint32_t kmer_size, uint16_t *lut65536)
+{
+    if (!lut65536) return fail(RB_ERR_INVALID_ARG, "null lut");
+    if (!(error_rate > 0.0 && error_rate < 1.0) || !(significance > 0.0 && significance < 1.0))
+        return fail(RB_ERR_INVALID_CONFIG, "error rate and significance must be in (0, 1)");
+    for (uint32_t len = 0; len < 65536; ++len) {
+        // src/IBF/IBFClassify.cpp:154-159: uint16 readlen, int16 threshold, used as uint16
+        uint16_t hi = 0;
+        calculate_ci(error_rate, kmer_size, len, significance, nullptr, &hi);
+        const int16_t thr = (int16_t)((int)(uint16_t)len - (int)kmer_size + 1 - (int)hi);
+        lut65536[len] = (uint16_t)thr;
+    }
+    return RB_OK;
+}
+
+uint64_t rb_cut_out_nnns(const char *seq, uint64_t len, char *out)
+{
+    // IBF::cutOutNNNs, src/IBF/IBFBuild.cpp:112-132: pieces between runs of 'N' are kept; the
+    // last piece loses its final base when the sequence does not end in 'N'.
+    uint64_t n = 0, pos = 0;
+    while (pos < len) {
+        while (pos < len && seq[pos] == 'N') ++pos;
+        if (pos >= len) break;
+        uint64_t stop = pos;
+        while (stop < len && seq[stop] != 'N') ++stop;
+        uint64_t take = stop < len ? stop - pos : len - pos - 1;
+        std::memcpy(out + n, seq + pos, take);
+        n += take;
+        pos = stop;
+    }
+    return n;
+}
+
+uint64_t rb_fragment_schedule(uint64_t seqlen, uint64_t fragment_length, uint32_t kmer_size, uint64_t *begin,
+                              uint64_t *end, uint64_t cap)
+{
+    // src/IBF/IBFBuild.cpp:165-202
+    uint64_t n = 0;
+    int64_t start = 0;
+    for (int64_t idx = 0; start < (int64_t)seqlen - 1; ++idx) {
+        uint64_t stop = std::min<uint64_t>((uint64_t)(idx + 1) * fragment_length, seqlen);
+        if (n < cap) {
+            if (begin) begin[n] = (uint64_t)start;
+            if (end) end[n] = stop;
+        }
+        ++n;
+        start = (idx + 1) * (int64_t)fragment_length - (int64_t)kmer_size + 1;
+    }
+    return n;
+}
+
+// ---- life cycle --------------------------------------------------------------------------------
+rb_ibf *rb_ibf_create(uint64_t n_bins, uint32_t n_hash, uint32_t kmer_size, uint64_t n_bits, int device, int *status)
+{
+    int st = check_device(device);
+    rb_ibf *f = nullptr;
+    if (st == RB_OK) {
+        f = new rb_ibf();
+        f->device = device;
+        f->n_bins = n_bins; f->n_hash = n_hash; f->k = kmer_size; f->n_bits = n_bits;
+        DeviceGuard g(device);
+        st = derive_geometry(f, 0, 1);
+        if (st == RB_OK) st = alloc_device(f, true);
+        if (st != RB_OK) { destroy(f); f = nullptr; }
+    }
+    if (status) *status = st;
+    return f;
+}
+
+rb_ibf *rb_ibf_from_words(const uint64_t *words, uint64_t n_bins, uint32_t n_hash, uint32_t kmer_size, uint64_t n_bits,
+                          int device, int shard, int n_shards, int *status)
+{
+    int st = words ? check_device(device) : fail(RB_ERR_INVALID_ARG, "null words");
+    rb_ibf *f = nullptr;
+    if (st == RB_OK) {
+        f = new rb_ibf();
+        f->device = device;
+        f->n_bins = n_bins; f->n_hash = n_hash; f->k = kmer_size; f->n_bits = n_bits;
+        DeviceGuard g(device);
+        st = derive_geometry(f, shard, n_shards);
+        if (st == RB_OK) st = alloc_device(f, false);
+        if (st == RB_OK) {
+            auto body = [&]() -> int {
+                if (n_shards == 1) RB_CUDA(cudaMemcpy(f->d_words, words, f->n_local_words * 8, cudaMemcpyHostToDevice));
+                else {
+                    int s2 = upload_rows(f, words, 0, f->n_blocks, nullptr);
+                    if (s2 != RB_OK) return s2;
+                    RB_CUDA(cudaStreamSynchronize(nullptr));
+                }
+                return RB_OK;
+            };
+            st = body();
+        }
+        if (st != RB_OK) { destroy(f); f = nullptr; }
+    }
+    if (status) *status = st;
+    return f;
+}
+
+rb_ibf *rb_ibf_load_shard(const char *path, int device, int shard, int n_shards, int *status)
+{
+    rb_ibf *f = nullptr;
+    FILE *fp = nullptr;
+    auto body = [&]() -> int {
+        if (!path || !*path) return fail(RB_ERR_MISSING_IBF_FILE, "either update_filter_file or input_filter_file has to be specified");
+        struct stat sb;
+        if (stat(path, &sb) != 0 || !S_ISREG(sb.st_mode)) return fail(RB_ERR_MISSING_IBF_FILE, std::string("cannot open IBF file ") + path);
+        fp = std::fopen(path, "rb");
+        if (!fp) return fail(RB_ERR_MISSING_IBF_FILE, std::string("cannot open IBF file ") + path);
+        // sdsl bit_vector::serialize: u64 bit length, then ceil(len/64) words
+        uint64_t bit_len = 0;
+        const uint64_t fsize = (uint64_t)sb.st_size;
+        if (fsize < 8 + 32 + 8 || std::fread(&bit_len, 8, 1, fp) != 1) return fail(RB_ERR_PARSE_IBF_FILE, "file too small for an IBF");
+        if (bit_len < 256 + 64 || (bit_len % 64) != 0 || fsize != 8 + bit_len / 8)
+            return fail(RB_ERR_PARSE_IBF_FILE, "sdsl bit_vector header does not match the file size");
+        const uint64_t n_bits = bit_len - 256;
+        uint64_t tail[4];
+        if (fseeko(fp, (off_t)(8 + n_bits / 8), SEEK_SET) != 0 || std::fread(tail, 8, 4, fp) != 4)
+            return fail(RB_ERR_PARSE_IBF_FILE, "cannot read the metadata tail");
+        if (tail[0] == 0 || tail[1] == 0 || tail[1] > (uint64_t)rb::kMaxHash || tail[2] == 0 || tail[2] > 32 || tail[3] != tail[2])
+            return fail(RB_ERR_PARSE_IBF_FILE, "metadata tail is not [bins, hash functions, k, k]");
+        int st = check_device(device);
+        if (st != RB_OK) return st;
+        f = new rb_ibf();
+        f->device = device;
+        f->n_bins = tail[0]; f->n_hash = tail[1]; f->k = tail[2]; f->n_bits = n_bits;
+        st = derive_geometry(f, shard, n_shards);
+        if (st == RB_ERR_INVALID_CONFIG) return fail(RB_ERR_PARSE_IBF_FILE, std::string(g_last_error));
+        if (st != RB_OK) return st;
+        st = alloc_device(f, false);
+        if (st != RB_OK) return st;
+        if (fseeko(fp, 8, SEEK_SET) != 0) return fail(RB_ERR_PARSE_IBF_FILE, "seek failed");
+        // stream the payload through two pinned staging buffers so disk reads overlap the H2D copies
+        const uint64_t row_words = f->bin_width;
+        uint64_t rows_per_stage = std::max<uint64_t>(1, kStageBytes / 8 / row_words);
+        PinnedPair pp;
+        st = pp.init((size_t)(n_shards == 1 ? kStageBytes / 8 : rows_per_stage * row_words));
+        if (st != RB_OK) return st;
+        int cur = 0;
+        if (n_shards == 1) {
+            const uint64_t total = n_bits / 64;
+            for (uint64_t w0 = 0; w0 < total; w0 += pp.words, cur ^= 1) {
+                const uint64_t nw = std::min<uint64_t>(pp.words, total - w0);
+                RB_CUDA(cudaEventSynchronize(pp.ev[cur]));
+                if (std::fread(pp.buf[cur], 8, nw, fp) != nw) return fail(RB_ERR_PARSE_IBF_FILE, "short read of the bit matrix");
+                RB_CUDA(cudaMemcpyAsync(f->d_words + w0, pp.buf[cur], nw * 8, cudaMemcpyHostToDevice, pp.st));
+                RB_CUDA(cudaEventRecord(pp.ev[cur], pp.st));
+            }
+        } else {
+            for (uint64_t r0 = 0; r0 < f->n_blocks; r0 += rows_per_stage, cur ^= 1) {
+                const uint64_t nr = std::min<uint64_t>(rows_per_stage, f->n_blocks - r0);
+                RB_CUDA(cudaEventSynchronize(pp.ev[cur]));
+                if (std::fread(pp.buf[cur], 8, nr * row_words, fp) != nr * row_words) return fail(RB_ERR_PARSE_IBF_FILE, "short read of the bit matrix");
+                st = upload_rows(f, pp.buf[cur], r0, nr, pp.st);
+                if (st != RB_OK) return st;
+                RB_CUDA(cudaEventRecord(pp.ev[cur], pp.st));
+            }
+        }
+        RB_CUDA(cudaStreamSynchronize(pp.st));
+        return RB_OK;
+    };
+    int prev = -1;
+    cudaGetDevice(&prev);
+    int st = body();
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+    if (fp) std::fclose(fp);
+    if (st != RB_OK) { destroy(f); f = nullptr; }
+    if (status) *status = st;
+    return f;
+}
+
+rb_ibf *rb_ibf_load(const char *path, int device, int *status) { return rb_ibf_load_shard(path, device, 0, 1, status); }
+
+int rb_ibf_download(const rb_ibf *f, uint64_t *words, uint64_t n_words)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "null filter");
+    if (!words || n_words != f->n_local_words) return fail(RB_ERR_INVALID_ARG, "word count does not match the local matrix");
+    DeviceGuard g(f->device);
+    RB_CUDA(cudaDeviceSynchronize());
+    int st = sticky_insert_error(f);
+    if (st != RB_OK) return st;
+    RB_CUDA(cudaMemcpy(words, f->d_words, n_words * 8, cudaMemcpyDeviceToHost));
+    return RB_OK;
+}
+
+int rb_ibf_store(const rb_ibf *f, const char *path)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "null filter");
+    if (f->n_shards != 1) return fail(RB_ERR_STORE_FILTER, "a bin shard cannot be stored as a whole filter");
+    if (!path || !*path) return fail(RB_ERR_STORE_FILTER, "no output filter file given");
+    DeviceGuard g(f->device);
+    RB_CUDA(cudaDeviceSynchronize());
+    int st = sticky_insert_error(f);
+    if (st != RB_OK) return st;
+    FILE *fp = std::fopen(path, "wb");
+    if (!fp) return fail(RB_ERR_STORE_FILTER, std::string("could not store IBF to ") + path);
+    auto body = [&]() -> int {
+        const uint64_t bit_len = f->n_bits + 256;
+        if (std::fwrite(&bit_len, 8, 1, fp) != 1) return fail(RB_ERR_STORE_FILTER, "write failed");
+        PinnedPair pp;
+        int s2 = pp.init(kStageBytes / 8);
+        if (s2 != RB_OK) return s2;
+        const uint64_t total = f->n_bits / 64;
+        // D2H of stage i+1 overlaps the fwrite of stage i
+        uint64_t issued = 0, written = 0;
+        int cur = 0;
+        uint64_t pending[2] = {0, 0};
+        auto issue = [&](int b) -> int {
+            const uint64_t nw = std::min<uint64_t>(pp.words, total - issued);
+            RB_CUDA(cudaMemcpyAsync(pp.buf[b], f->d_words + issued, nw * 8, cudaMemcpyDeviceToHost, pp.st));
+            RB_CUDA(cudaEventRecord(pp.ev[b], pp.st));
+            pending[b] = nw;
+            issued += nw;
+            return RB_OK;
+        };
+        if (total) { s2 = issue(0); if (s2 != RB_OK) return s2; }
+        while (written < total) {
+            if (issued < total) { s2 = issue(cur ^ 1); if (s2 != RB_OK) return s2; }
+            RB_CUDA(cudaEventSynchronize(pp.ev[cur]));
+            if (std::fwrite(pp.buf[cur], 8, pending[cur], fp) != pending[cur]) return fail(RB_ERR_STORE_FILTER, "write failed");
+            written += pending[cur];
+            cur ^= 1;
+        }
+        const uint64_t tail[4] = {f->n_bins, f->n_hash, f->k, f->k};
+        if (std::fwrite(tail, 8, 4, fp) != 4) return fail(RB_ERR_STORE_FILTER, "write failed");
+        return RB_OK;
+    };
+    st = body();
+    if (std::fclose(fp) != 0 && st == RB_OK) st = fail(RB_ERR_STORE_FILTER, "close failed");
+    return st;
+}
+
+void rb_ibf_free(rb_ibf *f) { destroy(f); }
+
+int rb_ibf_info(const rb_ibf *f, rb_ibf_info_t *out)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "null filter");
+    if (!out) return fail(RB_ERR_INVALID_ARG, "null out");
+    out->n_bins = f->n_bins; out->n_hash = f->n_hash; out->kmer_size = f->k; out->n_bits = f->n_bits;
+    out->bin_width = f->bin_width; out->n_blocks = f->n_blocks; out->col_begin = f->col_begin;
+    out->col_words = f->col_words; out->bin_begin = 64 * f->col_begin; out->n_bins_local = f->n_bins_local;
+    out->device_bytes = f->n_local_words * 8; out->device = f->device; out->shard = f->shard; out->n_shards = f->n_shards;
+    return RB_OK;
+}
+
+uint64_t *rb_ibf_device_words(const rb_ibf *f) { return f ? f->d_words : nullptr; }
+
+// ---- build ---------------------------------------------------------------------------------------
+int rb_ibf_insert_batch_dev(rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_frag_begin, const uint64_t *d_frag_end,
+                            const uint64_t *d_frag_bin, uint64_t n_frags, uint64_t max_frag_len, rb_stream stream)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "null filter");
+    if (n_frags == 0) return RB_OK;
+    if (!d_bases || !d_frag_begin || !d_frag_end || !d_frag_bin) return fail(RB_ERR_INVALID_ARG, "null device pointer");
+    DeviceGuard g(f->device);
+    rb::InsertArgs a{};
+    a.words = f->d_words; a.stride = f->col_words;
+    a.bin_begin = 64 * f->col_begin; a.bin_end = a.bin_begin + f->n_bins_local; a.n_bins = f->n_bins;
+    a.hp = f->hp; a.bases = d_bases; a.frag_begin = d_frag_begin; a.frag_end = d_frag_end; a.frag_bin = d_frag_bin;
+    a.n_frags = n_frags; a.error_flag = f->d_err;
+    int n = rb::launch_insert(a, max_frag_len, f->sm_count, (cudaStream_t)stream);
+    if (n < 0) return fail(RB_ERR_CUDA, std::string("insert launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    g_launches += (uint64_t)n;
+    return RB_OK;
+}
+
+int rb_ibf_insert_batch(rb_ibf *f, const char *bases, uint64_t n_bases, const uint64_t *frag_begin,
+                        const uint64_t *frag_end, const uint64_t *frag_bin, uint64_t n_frags, rb_stream stream)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "null filter");
+    if (n_frags == 0) return RB_OK;
+    if (!bases || !frag_begin || !frag_end || !frag_bin) return fail(RB_ERR_INVALID_ARG, "null pointer");
+    uint64_t max_len = 0;
+    for (uint64_t i = 0; i < n_frags; ++i) {
+        if (frag_end[i] < frag_begin[i] || frag_end[i] > n_bases) return fail(RB_ERR_INSERT_SEQUENCE, "fragment outside the sequence buffer");
+        max_len = std::max(max_len, frag_end[i] - frag_begin[i]);
+    }
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *d_bases = nullptr;
+    uint64_t *d_frag = nullptr;
+    auto body = [&]() -> int {
+        RB_CUDA(cudaMallocAsync(&d_bases, n_bases ? n_bases : 1, st));
+        RB_CUDA(cudaMallocAsync(&d_frag, 3 * n_frags * 8, st));
+        RB_CUDA(cudaMemcpyAsync(d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(d_frag, frag_begin, n_frags * 8, cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(d_frag + n_frags, frag_end, n_frags * 8, cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(d_frag + 2 * n_frags, frag_bin, n_frags * 8, cudaMemcpyHostToDevice, st));
+        int s2 = rb_ibf_insert_batch_dev(f, d_bases, d_frag, d_frag + n_frags, d_frag + 2 * n_frags, n_frags, max_len, stream);
+        if (s2 != RB_OK) return s2;
+        RB_CUDA(cudaStreamSynchronize(st));
+        return sticky_insert_error(f);
+    };
+    int s = body();
+    if (d_bases) cudaFreeAsync(d_bases, st);
+    if (d_frag) cudaFreeAsync(d_frag, st);
+    cudaStreamSynchronize(st);
+    return s;
+}
+
+// ---- classify --------------------------------------------------------------------------------------
+int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                           uint32_t max_read_len, const uint16_t *d_thr_lut, uint32_t n_lut, uint64_t *d_keys,
+                           uint16_t *d_counts_fwd, uint16_t *d_counts_rev, uint8_t *d_read_flag, rb_stream stream)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "No IBF provided to classify the read!");
+    if (n_reads == 0) return RB_OK;
+    if (!d_bases || !d_read_off || !d_thr_lut || !d_keys) return fail(RB_ERR_INVALID_ARG, "null device pointer");
+    if (n_lut == 0 || n_lut > (uint32_t)rb::kMaxLut) return fail(RB_ERR_INVALID_ARG, "n_lut must be 1..4");
+    if (n_reads > 0x7FFFFFFFull) return fail(RB_ERR_INVALID_ARG, "more than 2^31-1 reads in one batch");
+    DeviceGuard g(f->device);
+    rb::CountArgs a{};
+    a.fv = view_of(f);
+    a.bases = d_bases; a.read_off = d_read_off; a.n_reads = n_reads; a.lut = d_thr_lut; a.n_lut = n_lut;
+    a.keys = d_keys; a.counts_fwd = d_counts_fwd; a.counts_rev = d_counts_rev; a.read_flag = d_read_flag;
+    L2Window win(f, (cudaStream_t)stream);
+    int n = rb::launch_count(a, max_read_len, g_count_kernel.load(), f->sm_count, (cudaStream_t)stream);
+    if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    g_launches += (uint64_t)n;
+    return RB_OK;
+}
+
+int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_max_count, uint8_t *d_hit, uint32_t *d_argmax_bin,
+                       int device, rb_stream stream)
+{
+    if (n == 0) return RB_OK;
+    if (!d_keys) return fail(RB_ERR_INVALID_ARG, "null keys");
+    DeviceGuard g(device);
+    int k = rb::launch_keys_decode(d_keys, n, d_max_count, d_hit, d_argmax_bin, (cudaStream_t)stream);
+    if (k < 0) return fail(RB_ERR_CUDA, "decode launch failed");
+    g_launches += (uint64_t)k;
+    return RB_OK;
+}
+
+int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_off, uint64_t n_reads,
+                       const uint16_t *thr_lut, uint32_t n_lut, uint16_t *counts_fwd, uint16_t *counts_rev,
+                       uint16_t *max_count, uint8_t *hit, uint32_t *argmax_bin, uint8_t *read_flag, rb_stream stream)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "No IBF provided to classify the read!");
+    if (n_reads == 0) return RB_OK;
+    if (!bases || !read_off || !thr_lut) return fail(RB_ERR_INVALID_ARG, "null pointer");
+    if (n_lut == 0 || n_lut > (uint32_t)rb::kMaxLut) return fail(RB_ERR_INVALID_ARG, "n_lut must be 1..4");
+    uint64_t max_len = 0;
+    for (uint64_t i = 0; i < n_reads; ++i) {
+        if (read_off[i + 1] < read_off[i]) return fail(RB_ERR_INVALID_ARG, "read offsets must be non-decreasing");
+        max_len = std::max(max_len, read_off[i + 1] - read_off[i]);
+    }
+    const uint64_t n_bases = read_off[n_reads] - read_off[0];
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t nk = (uint64_t)n_lut * n_reads;
+    const uint64_t dense = n_reads * f->n_bins_local;
+    uint8_t *d_bases = nullptr, *d_small = nullptr;
+    uint64_t *d_off = nullptr, *d_keys = nullptr;
+    uint16_t *d_lut = nullptr, *d_cf = nullptr, *d_cr = nullptr;
+    std::vector<uint64_t> rel;
+    auto body = [&]() -> int {
+        RB_CUDA(cudaMallocAsync(&d_bases, n_bases ? n_bases : 1, st));
+        RB_CUDA(cudaMallocAsync(&d_off, (n_reads + 1) * 8, st));
+        RB_CUDA(cudaMallocAsync(&d_lut, (size_t)n_lut * rb::kLutSize * 2, st));
+        RB_CUDA(cudaMallocAsync(&d_keys, nk * 8, st));
+        // max_count (2 B) | argmax (4 B) | hit (1 B) per key, then read_flag
+        RB_CUDA(cudaMallocAsync(&d_small, nk * 7 + n_reads + 16, st));
+        if (counts_fwd) RB_CUDA(cudaMallocAsync(&d_cf, dense * 2, st));
+        if (counts_rev) RB_CUDA(cudaMallocAsync(&d_cr, dense * 2, st));
+        const uint64_t *off_src = read_off;
+        if (read_off[0] != 0) {   // make offsets relative to the uploaded slice
+            rel.resize(n_reads + 1);
+            for (uint64_t i = 0; i <= n_reads; ++i) rel[i] = read_off[i] - read_off[0];
+            off_src = rel.data();
+        }
+        RB_CUDA(cudaMemcpyAsync(d_bases, bases + read_off[0], n_bases, cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(d_off, off_src, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(d_lut, thr_lut, (size_t)n_lut * rb::kLutSize * 2, cudaMemcpyHostToDevice, st));
+        uint32_t *d_amax = reinterpret_cast<uint32_t *>(d_small);            // 4-byte aligned first
+        uint16_t *d_max = reinterpret_cast<uint16_t *>(d_small + nk * 4);
+        uint8_t *d_hit = d_small + nk * 6;
+        uint8_t *d_flag = d_small + nk * 7;
+        int s2 = rb_ibf_count_batch_dev(f, d_bases, d_off, n_reads, (uint32_t)std::min<uint64_t>(max_len, 0xFFFFFFFFu), d_lut,
+                                        n_lut, d_keys, d_cf, d_cr, d_flag, stream);
+        if (s2 != RB_OK) return s2;
+        s2 = rb_keys_decode_dev(d_keys, nk, d_max, d_hit, d_amax, f->device, stream);
+        if (s2 != RB_OK) return s2;
+        if (max_count) RB_CUDA(cudaMemcpyAsync(max_count, d_max, nk * 2, cudaMemcpyDeviceToHost, st));
+        if (hit) RB_CUDA(cudaMemcpyAsync(hit, d_hit, nk, cudaMemcpyDeviceToHost, st));
+        if (argmax_bin) RB_CUDA(cudaMemcpyAsync(argmax_bin, d_amax, nk * 4, cudaMemcpyDeviceToHost, st));
+        if (read_flag) RB_CUDA(cudaMemcpyAsync(read_flag, d_flag, n_reads, cudaMemcpyDeviceToHost, st));
+        if (counts_fwd) RB_CUDA(cudaMemcpyAsync(counts_fwd, d_cf, dense * 2, cudaMemcpyDeviceToHost, st));
+        if (counts_rev) RB_CUDA(cudaMemcpyAsync(counts_rev, d_cr, dense * 2, cudaMemcpyDeviceToHost, st));
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(RB_ERR_COUNT_KMER, std::string("Error counting kmers in IBF bins: ") + cudaGetErrorString(e));
+        return RB_OK;
+    };
+    int s = body();
+    void *bufs[] = {d_bases, d_off, d_lut, d_keys, d_small, d_cf, d_cr};
+    for (void *p : bufs) if (p) cudaFreeAsync(p, st);
+    cudaStreamSynchronize(st);
+    return s;
+}
+
+}  // extern "C"

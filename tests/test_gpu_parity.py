@@ -1,0 +1,274 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> librb_ibf.so), against
+the CPU oracle on the same inputs and against the reference's golden fixtures.  Bit-exact."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+import readbouncer_b200 as rb
+from readbouncer_b200 import synth
+from conftest import data_path, golden_words, read_fasta
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = {"auto": 0, "tile": 1, "stream": 2}
+
+
+@pytest.fixture(autouse=True)
+def _reset_kernel_choice():
+    yield
+    rb.set_count_kernel(0)
+
+
+def make_filter_pair(n_seqs, seq_len, fragment_length, k=13, seed=100, n_hash=3):
+    """Same synthetic reference inserted by the oracle (CPU) and by the GPU library."""
+    ref = [synth.random_bases(seq_len, seed + i) for i in range(n_seqs)]
+    plan = synth.build_plan(ref, fragment_length, k, n_hash=n_hash)
+    of = oracle.OracleIBF.create(plan["n_bins"], n_hash, k, plan["n_bits"])
+    of.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"], n_threads=4)
+    gf = rb.IBF.create(plan["n_bins"], n_hash, k, plan["n_bits"])
+    gf.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+    return plan, of, gf
+
+
+def assert_same_results(got, exp, dense=True):
+    assert np.array_equal(got["read_flag"], exp["short_read"])
+    if dense:
+        assert np.array_equal(got["counts_fwd"], exp["counts_fwd"])
+        assert np.array_equal(got["counts_rev"], exp["counts_rev"])
+    assert np.array_equal(got["max_count"], exp["max_count"])
+    assert np.array_equal(got["hit"], exp["hit"])
+    assert np.array_equal(got["argmax_bin"], exp["argmax_bin"])
+
+
+# ---- golden fixtures ----------------------------------------------------------------------------------
+def test_golden_load_info_store(known, golden_ibf_paths, tmp_path):
+    exp = {"lib_test": (2, 3, 13, 79121216), "lib_test1": (4, 3, 13, 79121216), "classify_test": (2, 3, 15, 79119680)}
+    for name, path in golden_ibf_paths.items():
+        f = rb.IBF.load(path)
+        assert (f.n_bins, f.n_hash, f.kmer_size, f.n_bits) == exp[name]
+        assert f.bin_width == 1 and f.n_blocks == f.n_bits // 64 and f.n_shards == 1
+        out = tmp_path / (name + ".gpu.ibf")
+        f.store(out)
+        assert hashlib.md5(out.read_bytes()).hexdigest() == known["ibf"][name]["md5"]
+
+
+def test_golden_load_rejects_non_ibf(tmp_path):
+    with pytest.raises(rb.RBError) as e:
+        rb.IBF.load(data_path("lib_test.fasta"))
+    assert e.value.status == 4                      # ParseIBFFileException (FASTA sniffing, configReader.cpp:210-224)
+    with pytest.raises(rb.RBError) as e:
+        rb.IBF.load(tmp_path / "nope.ibf")
+    assert e.value.status == 5                      # MissingIBFFileException
+
+
+@pytest.mark.parametrize("name,fasta,k", [("lib_test", "lib_test.fasta", 13), ("lib_test1", "lib_test1.fasta", 13),
+                                          ("classify_test", "classify_test.fasta", 15)])
+def test_golden_rebuild_on_gpu(known, golden_sparse, name, fasta, k):
+    """GPU insert kernel + host build plan reproduce the reference's .ibf files bit for bit
+    (the fixtures were written by a test build that queued every sequence twice)."""
+    seqs = [s for _, s in read_fasta(data_path(fasta))]
+    plan = synth.build_plan(seqs + seqs, 100000, k)
+    meta, words = golden_words(known, golden_sparse, name)
+    assert plan["n_bits"] + 256 == meta["bit_length"] and plan["n_bins"] == meta["tail"][0]
+    f = rb.IBF.create(plan["n_bins"], 3, k, plan["n_bits"])
+    f.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+    assert np.array_equal(f.download(), words[:plan["n_bits"] // 64])
+
+
+@pytest.mark.parametrize("kernel", ["tile", "stream"])
+def test_golden_known_answers(known, golden_ibf_paths, kernel):
+    rb.set_count_kernel(KERNELS[kernel])
+    ka = known["known"]
+    f0 = rb.IBF.load(golden_ibf_paths["lib_test"])
+    f1 = rb.IBF.load(golden_ibf_paths["lib_test1"])
+    reads = [ka["read35"]["seq"].encode(), ka["read35_revcomp"]["seq"].encode(), ka["read354"]["seq"].encode()]
+    off = np.cumsum([0] + [len(r) for r in reads]).astype(np.uint64)
+    bases = np.frombuffer(b"".join(reads), np.uint8)
+    lut = rb.threshold_lut(0.1, 13)
+    assert lut[35] == 65529 and lut[354] == 36
+    r0 = f0.count_batch(bases, off, lut, dense=True)
+    r1 = f1.count_batch(bases, off, lut, dense=True)
+    assert r0["counts_fwd"][0].tolist() == [23, 23] and r0["counts_rev"][0].tolist() == [0, 0]    # read.hpp:139-140
+    assert r0["counts_fwd"][1].tolist() == [0, 0] and r0["counts_rev"][1].tolist() == [23, 23]    # read.hpp:286-327
+    assert r0["max_count"].tolist() == [0, 0, 282] and r1["max_count"].tolist() == [0, 0, 182]    # read.hpp:221-229
+    assert r0["hit"].tolist() == [0, 0, 1] and r0["argmax_bin"].tolist() == [0xFFFFFFFF, 0xFFFFFFFF, 0]
+    # a zero threshold table reproduces the int-compare of CountMatchesTest: max 23 (read.hpp:327)
+    rz = f0.count_batch(bases, off, np.zeros(65536, np.uint16))
+    assert rz["max_count"].tolist()[:2] == [23, 23] and rz["hit"].tolist() == [1, 1, 1]
+
+
+def test_golden_classify_fastq(golden_ibf_paths):
+    """classifyTests: 3/3 reads found in <= 4 chunks of 360, all in chunk 0 at 250."""
+    f = rb.IBF.load(golden_ibf_paths["classify_test"])
+    of = oracle.OracleIBF.load(golden_ibf_paths["classify_test"])
+    reads = [s for _, s in read_fasta(data_path("classify_test.fastq"))]
+    for cl, expect in [(250, [0, 0, 0]), (360, [0, 0, 3])]:
+        chunks, owner = [], []
+        for ri, s in enumerate(reads):
+            for i in range(5):
+                chunks.append(s[i * cl:min((i + 1) * cl, len(s))])
+                owner.append((ri, i))
+        off = np.cumsum([0] + [len(c) for c in chunks]).astype(np.uint64)
+        bases = np.frombuffer(b"".join(chunks), np.uint8)
+        lut = rb.threshold_lut(0.1, 15)
+        got = f.count_batch(bases, off, lut, dense=True)
+        exp = of.count_batch(bases, off, oracle.threshold_lut(0.1, 15))
+        assert_same_results(got, exp)
+        first = [min(i for (r, i), m in zip(owner, got["max_count"]) if r == ri and m > 0) for ri in range(3)]
+        assert first == expect
+
+
+# ---- synthetic differential tests ---------------------------------------------------------------------
+RAGGED = [250] * 40 + [0, 1, 12, 13, 14, 31, 32, 33, 64, 100, 249, 251, 360, 500, 1023, 1024, 1036, 1037, 1500, 2100, 5000]
+
+
+@pytest.mark.parametrize("kernel", ["tile", "stream"])
+@pytest.mark.parametrize("n_seqs,seq_len,frag,k", [
+    (1, 500000, 100000, 13),     # 6 bins,  W=1   (config #1 shape)
+    (100, 20000, 21000, 13),     # 100 bins, W=2  (config #2 shape)
+    (130, 3000, 4000, 15),       # 130 bins, W=3
+    (200, 3000, 4000, 13),       # 200 bins, W=4
+    (1, 700 * 2000 + 7, 2000, 13),   # 701 bins, W=11 (odd stride -> 8-byte loads, tiles 4+4+3)
+    (1100, 1500, 2000, 11),      # 1100 bins, W=18 (even stride -> 16-byte loads)
+])
+def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
+    rb.set_count_kernel(KERNELS[kernel])
+    plan, of, gf = make_filter_pair(n_seqs, seq_len, frag, k)
+    assert np.array_equal(gf.download(), of.words()[:plan["n_bits"] // 64])
+    bases, off = synth.ragged_reads(plan["bases"], RAGGED, seed=7, frac_from_ref=0.7, n_frac=0.003, lower_frac=0.1)
+    lut = rb.threshold_lut(0.1, k)
+    assert np.array_equal(lut, oracle.threshold_lut(0.1, k))
+    got = gf.count_batch(bases, off, lut, dense=True)
+    exp = of.count_batch(bases, off, lut, n_threads=4)
+    assert_same_results(got, exp)
+    assert exp["hit"].sum() > 10 and (exp["short_read"] == 1).sum() >= 2
+
+
+def test_two_threshold_tables_in_one_pass():
+    plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
+    bases, off, _ = synth.sample_reads(plan["bases"], 3000, 250, seed=5, error_rate=0.12)
+    luts = np.stack([rb.threshold_lut(0.1, 13), rb.threshold_lut(0.08, 13)])
+    got = gf.count_batch(bases, off, luts)
+    for t in range(2):
+        exp = of.count_batch(bases, off, luts[t], dense=False, n_threads=4)
+        assert np.array_equal(got["max_count"][t], exp["max_count"])
+        assert np.array_equal(got["hit"][t], exp["hit"])
+        assert np.array_equal(got["argmax_bin"][t], exp["argmax_bin"])
+    assert (got["hit"][0] != got["hit"][1]).any()
+
+
+def test_long_read_too_long_flag():
+    plan, of, gf = make_filter_pair(1, 300000, 100000, 13)
+    bases, off = synth.ragged_reads(plan["bases"], [70000, 65535, 300], seed=3, frac_from_ref=1.0)
+    lut = rb.threshold_lut(0.1, 13)
+    got = gf.count_batch(bases, off, lut, dense=True)
+    exp = of.count_batch(bases, off, lut)
+    assert got["read_flag"].tolist() == [2, 0, 0]
+    assert_same_results(got, exp)
+
+
+@pytest.mark.parametrize("kernel", ["tile", "stream"])
+@pytest.mark.parametrize("n_shards", [2, 3])
+def test_bin_sharded_counts_and_key_combine(kernel, n_shards):
+    """Column-sliced handles: dense counts equal the oracle's bin range; MAX over shard keys equals the whole filter."""
+    rb.set_count_kernel(KERNELS[kernel])
+    plan, of, gf = make_filter_pair(1, 700 * 2000 + 7, 2000, 13)
+    words = gf.download()
+    bases, off = synth.ragged_reads(plan["bases"], [250] * 60 + [13, 5, 1200], seed=11, frac_from_ref=0.8)
+    lut = rb.threshold_lut(0.1, 13)
+    exp = of.count_batch(bases, off, lut)
+    keys = np.zeros(len(off) - 1, np.uint64)
+    for s in range(n_shards):
+        sh = rb.IBF.from_words(words, plan["n_bins"], 3, 13, plan["n_bits"], shard=s, n_shards=n_shards)
+        assert sh.col_begin == gf.bin_width * s // n_shards
+        got = sh.count_batch(bases, off, lut, dense=True)
+        lo, hi = sh.bin_begin, sh.bin_begin + sh.n_bins_local
+        assert np.array_equal(got["counts_fwd"], exp["counts_fwd"][:, lo:hi])
+        assert np.array_equal(got["counts_rev"], exp["counts_rev"][:, lo:hi])
+        k_s = (got["hit"].astype(np.uint64) << np.uint64(63)) | (got["max_count"].astype(np.uint64) << np.uint64(32)) | \
+              np.where(got["hit"] > 0, (~got["argmax_bin"]).astype(np.uint64) & np.uint64(0xFFFFFFFF), np.uint64(0))
+        keys = np.maximum(keys, k_s)
+    mx, hit, am = rb.keys_decode(keys)
+    assert np.array_equal(mx, exp["max_count"]) and np.array_equal(hit, exp["hit"]) and np.array_equal(am, exp["argmax_bin"])
+
+
+def test_sharded_load_from_file(tmp_path):
+    plan, of, gf = make_filter_pair(1, 300 * 2000 + 7, 2000, 13)
+    p = tmp_path / "wide.ibf"
+    gf.store(p)
+    assert oracle.OracleIBF.load(p).n_bins == plan["n_bins"]
+    full = gf.download().reshape(-1)[:gf.n_blocks * gf.bin_width].reshape(gf.n_blocks, gf.bin_width)
+    for s in range(2):
+        sh = rb.IBF.load(p, shard=s, n_shards=2)
+        loc = sh.download().reshape(sh.n_blocks, sh.col_words)
+        assert np.array_equal(loc, full[:, sh.col_begin:sh.col_begin + sh.col_words])
+
+
+def test_generic_hash_count_path():
+    """n_hash != 3 takes the runtime-n_hash tile path (file format allows it; the reference fixes 3)."""
+    plan, of, gf = make_filter_pair(20, 5000, 6000, 13, n_hash=2)
+    bases, off = synth.ragged_reads(plan["bases"], [250] * 30 + [40, 9], seed=2, frac_from_ref=0.8)
+    lut = rb.threshold_lut(0.1, 13)
+    assert_same_results(gf.count_batch(bases, off, lut, dense=True), of.count_batch(bases, off, lut))
+
+
+# ---- insert ---------------------------------------------------------------------------------------------
+def test_insert_reports_out_of_range_bin():
+    """Quirk Q3: a sequence with len mod F in (F-k+2, F-1] consumes one bin id too many."""
+    ref = [synth.random_bases(199991, 1), synth.random_bases(50001, 2)]     # post-N-cut: 199990, 50000
+    plan = synth.build_plan(ref, 100000, 13)
+    assert plan["bin_ids_consumed"] == plan["n_bins"] + 1
+    gf = rb.IBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    with pytest.raises(rb.RBError) as e:
+        gf.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+    assert e.value.status == 7
+    of = oracle.OracleIBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    of.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+    assert np.array_equal(gf.download(), of.words()[:plan["n_bits"] // 64])     # in-range fragments still inserted
+
+
+def test_insert_is_idempotent_and_order_free():
+    plan, of, gf = make_filter_pair(3, 250000, 100000, 13)
+    before = gf.download()
+    perm = np.random.default_rng(0).permutation(len(plan["frag_bin"]))
+    gf.insert_batch(plan["bases"], plan["frag_begin"][perm], plan["frag_end"][perm], plan["frag_bin"][perm])
+    assert np.array_equal(gf.download(), before)
+
+
+# ---- BASELINE config #2 at full size: size-independent properties + sampled oracle check ----------------
+def test_config2_full_size_properties():
+    ref = [synth.random_bases(4_000_000, 2 + i) for i in range(100)]
+    plan = synth.build_plan(ref, 4_200_000, 13)
+    assert plan["n_bins"] == 100
+    gf = rb.IBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    gf.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+    n = 1_000_000
+    bases, off, from_ref = synth.sample_reads(plan["bases"], n, 250, seed=1234)
+    lut = rb.threshold_lut(0.1, 13)
+    assert lut[250] == 18
+    res = gf.count_batch(bases, off, lut)
+    # (1) reverse-complementing every read swaps the strands: identical summaries
+    rc = synth._COMP[bases.reshape(n, 250)[:, ::-1]].reshape(-1)
+    res_rc = gf.count_batch(rc, off, lut)
+    for key in ("max_count", "hit", "argmax_bin"):
+        assert np.array_equal(res[key], res_rc[key])
+    # (2) both kernels agree on the whole batch
+    rb.set_count_kernel(2)
+    res_s = gf.count_batch(bases, off, lut)
+    rb.set_count_kernel(0)
+    for key in ("max_count", "hit", "argmax_bin", "read_flag"):
+        assert np.array_equal(res[key], res_s[key])
+    # (3) sanity of the classifier on the synthetic mix
+    assert res["hit"][from_ref].mean() > 0.97 and res["hit"][~from_ref].mean() < 0.01
+    # (4) oracle on a random sample of the full-size batch, against the downloaded filter
+    of = oracle.OracleIBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    of.words()[:plan["n_bits"] // 64] = gf.download()
+    pick = np.random.default_rng(9).choice(n, 3000, replace=False)
+    sb = bases.reshape(n, 250)[pick].reshape(-1)
+    so = np.arange(len(pick) + 1, dtype=np.uint64) * np.uint64(250)
+    exp = of.count_batch(sb, so, lut, dense=False, n_threads=8)
+    assert np.array_equal(res["max_count"][pick], exp["max_count"])
+    assert np.array_equal(res["hit"][pick], exp["hit"])
+    assert np.array_equal(res["argmax_bin"][pick], exp["argmax_bin"])
