@@ -157,12 +157,13 @@ RB_API int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t
                               rb_stream stream);
 
 /* Packed per-read summary key used by the device API and the bin-sharded combine:
- *   bit 63      hit (some bin passes the threshold)
+ *   bit 48      hit (some bin passes the threshold)
  *   bits 47..32 max_count
  *   bits 31..0  ~argmax_bin   (so that a 64-bit MAX picks the lowest bin on ties)
- * key == 0 means no bin passed.  The elementwise MAX of the keys of all bin shards is the key of
- * the whole filter, which is what the NCCL combine of the bin-sharded mode reduces. */
-#define RB_KEY_HIT(key) ((uint8_t)((key) >> 63))
+ * key == 0 means no bin passed; keys are < 2^49, so signed and unsigned 64-bit MAX agree.  The
+ * elementwise MAX of the keys of all bin shards is the key of the whole filter, which is what the
+ * NCCL combine of the bin-sharded mode reduces. */
+#define RB_KEY_HIT(key) ((uint8_t)(((key) >> 48) & 1u))
 #define RB_KEY_MAX_COUNT(key) ((uint16_t)(((key) >> 32) & 0xFFFFu))
 #define RB_KEY_ARGMAX_BIN(key) ((key) ? ~(uint32_t)((key) & 0xFFFFFFFFu) : 0xFFFFFFFFu)
 

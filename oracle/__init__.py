@@ -83,7 +83,11 @@ def lib():
 
 
 def _b(s):
-    return s if isinstance(s, (bytes, bytearray)) else s.encode()
+    if isinstance(s, (bytes, bytearray)):
+        return s
+    if isinstance(s, np.ndarray):
+        return s.tobytes()
+    return s.encode()
 
 
 def _ptr(a):

@@ -184,7 +184,7 @@ def fragment_schedule(seqlen, fragment_length, kmer_size):
 def keys_decode(keys):
     """numpy decode of packed summary keys (see RB_KEY_* in rb_ibf.h)."""
     keys = np.asarray(keys, dtype=np.uint64)
-    hit = (keys >> np.uint64(63)).astype(np.uint8)
+    hit = ((keys >> np.uint64(48)) & np.uint64(1)).astype(np.uint8)
     mx = ((keys >> np.uint64(32)) & np.uint64(0xFFFF)).astype(np.uint16)
     am = np.where(keys != 0, ~(keys & np.uint64(0xFFFFFFFF)) & np.uint64(0xFFFFFFFF), np.uint64(0xFFFFFFFF))
     return mx, hit, am.astype(np.uint32)

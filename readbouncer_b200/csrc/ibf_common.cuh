@@ -89,7 +89,7 @@ RB_HD uint32_t comp5(uint32_t d) { return d < 4u ? 3u - d : 4u; }
 // packed per-read summary (see rb_ibf.h)
 RB_HD uint64_t pack_key(uint32_t count, uint32_t global_bin)
 {
-    return (1ULL << 63) | ((uint64_t)(count & 0xFFFFu) << 32) | (uint64_t)(~global_bin);
+    return (1ULL << 48) | ((uint64_t)(count & 0xFFFFu) << 32) | (uint64_t)(~global_bin);
 }
 
 }  // namespace rb

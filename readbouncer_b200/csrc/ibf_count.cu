@@ -425,7 +425,7 @@ __global__ void keys_decode_kernel(const uint64_t *__restrict__ keys, uint64_t n
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t key = keys[i];
         if (max_count) max_count[i] = (uint16_t)((key >> 32) & 0xFFFFu);
-        if (hit) hit[i] = (uint8_t)(key >> 63);
+        if (hit) hit[i] = (uint8_t)((key >> 48) & 1u);
         if (argmax_bin) argmax_bin[i] = key ? ~(uint32_t)(key & 0xFFFFFFFFu) : 0xFFFFFFFFu;
     }
 }

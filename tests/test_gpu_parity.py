@@ -187,7 +187,7 @@ def test_bin_sharded_counts_and_key_combine(kernel, n_shards):
         lo, hi = sh.bin_begin, sh.bin_begin + sh.n_bins_local
         assert np.array_equal(got["counts_fwd"], exp["counts_fwd"][:, lo:hi])
         assert np.array_equal(got["counts_rev"], exp["counts_rev"][:, lo:hi])
-        k_s = (got["hit"].astype(np.uint64) << np.uint64(63)) | (got["max_count"].astype(np.uint64) << np.uint64(32)) | \
+        k_s = (got["hit"].astype(np.uint64) << np.uint64(48)) | (got["max_count"].astype(np.uint64) << np.uint64(32)) | \
               np.where(got["hit"] > 0, (~got["argmax_bin"]).astype(np.uint64) & np.uint64(0xFFFFFFFF), np.uint64(0))
         keys = np.maximum(keys, k_s)
     mx, hit, am = rb.keys_decode(keys)
