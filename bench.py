@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=0, help="chunks per GPU per step (0 = workload default)")
     ap.add_argument("--mode", default="read_sharded", choices=["read_sharded", "bin_sharded"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 tile, 2 stream")
+    ap.add_argument("--l2-gran", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -182,6 +183,8 @@ def run_ours(args, w, n_reads):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rb.set_count_kernel(args.kernel)
+    if args.l2_gran:
+        rb.set_l2_fetch_granularity(args.l2_gran, device=local)
     stream = torch.cuda.current_stream()
     bin_sharded = args.mode == "bin_sharded" and world > 1
 
@@ -374,7 +377,7 @@ def run_ours(args, w, n_reads):
         "config": {"workload": args.workload, "mode": args.mode if world > 1 else "single_gpu",
                    "chunks_per_gpu_per_step": n_reads, "chunk_length": w["chunk"], "kmer_size": w["k"],
                    "bins": plan["n_bins"], "row_bytes": int(gf.bin_width * 8), "filter_bytes": plan["n_bits"] // 8,
-                   "thresholds_per_pass": n_lut, "error_rate": ERROR_RATE, "read_mix": "50% reference-derived @10% errors, 50% iid",
+                   "thresholds_per_pass": n_lut, "l2_fetch_granularity": rb.get_l2_fetch_granularity(local), "error_rate": ERROR_RATE, "read_mix": "50% reference-derived @10% errors, 50% iid",
                    "l2": "no flush: inputs (%.0f MB reads + %.0f MB filter) exceed the 126 MB L2" % (
                        bases_np.nbytes / 1e6, plan["n_bits"] / 8e6),
                    "hit_fraction": hits_dev / n_reads, "ibf_build_ms_gpu": build_ms,

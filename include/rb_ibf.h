@@ -184,6 +184,12 @@ RB_API int rb_set_count_kernel(int which);
 /* Number of kernels this library launched since load (all threads); evidence for gpu_launches. */
 RB_API uint64_t rb_kernel_launches(void);
 
+/* L2 fetch granularity of the device (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes).  Random
+ * probes of narrow rows touch one 32-byte sector each; with the default granularity the L2 pulls
+ * whole 128-byte lines from HBM and DRAM traffic is ~4x the useful bytes.  Device-wide setting. */
+RB_API int rb_set_l2_fetch_granularity(int device, uint32_t bytes);
+RB_API int rb_get_l2_fetch_granularity(int device, uint32_t *bytes);
+
 /* Measurement aid (not on the product path): uniformly random row-aligned loads of row_bytes
  * (8, 16 or 32) over d_buf[n_rows*row_bytes]; n_blocks CTAs of 256 threads, probes_per_thread
  * loads each (8 in flight).  Establishes the random-sector roofline of SURVEY.md section 8d. */

@@ -28,7 +28,7 @@ EXPORTS = [
     "rb_ibf_load_shard", "rb_ibf_from_words", "rb_ibf_store", "rb_ibf_download", "rb_ibf_free", "rb_ibf_info",
     "rb_ibf_device_words", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_kernel_launches",
-    "rb_microbench_gather",
+    "rb_microbench_gather", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
 ]
 
 
@@ -95,6 +95,8 @@ def lib():
         "rb_set_count_kernel": (i32, [i32]),
         "rb_kernel_launches": (u64, []),
         "rb_microbench_gather": (i32, [vp, u64, u32, u64, u32, vp, vp]),
+        "rb_set_l2_fetch_granularity": (i32, [i32, u32]),
+        "rb_get_l2_fetch_granularity": (i32, [i32, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -148,6 +150,16 @@ def set_count_kernel(which):
 def microbench_gather(d_buf, n_rows, row_bytes, probes_per_thread, n_blocks, d_sink, stream=None):
     _check(lib().rb_microbench_gather(_dev_ptr(d_buf), n_rows, row_bytes, probes_per_thread, n_blocks,
                                       _dev_ptr(d_sink), _stream_ptr(stream)))
+
+
+def set_l2_fetch_granularity(nbytes, device=0):
+    _check(lib().rb_set_l2_fetch_granularity(device, nbytes))
+
+
+def get_l2_fetch_granularity(device=0):
+    v = C.c_uint32(0)
+    _check(lib().rb_get_l2_fetch_granularity(device, C.addressof(v)))
+    return int(v.value)
 
 
 def ibf_size_bits(fragment_length, kmer_size=13, n_hash=3, max_fp=0.01, n_bins=1):

@@ -276,6 +276,27 @@ int rb_device_count(void)
 
 uint64_t rb_kernel_launches(void) { return g_launches.load(); }
 
+int rb_set_l2_fetch_granularity(int device, uint32_t bytes)
+{
+    if (bytes != 32 && bytes != 64 && bytes != 128) return fail(RB_ERR_INVALID_ARG, "granularity must be 32, 64 or 128");
+    int st = check_device(device);
+    if (st != RB_OK) return st;
+    DeviceGuard g(device);
+    RB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, bytes));
+    return RB_OK;
+}
+
+int rb_get_l2_fetch_granularity(int device, uint32_t *bytes)
+{
+    int st = check_device(device);
+    if (st != RB_OK) return st;
+    DeviceGuard g(device);
+    size_t v = 0;
+    RB_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+    if (bytes) *bytes = (uint32_t)v;
+    return RB_OK;
+}
+
 int rb_set_count_kernel(int which)
 {
     if (which < 0 || which > 2) return fail(RB_ERR_INVALID_ARG, "kernel selector must be 0, 1 or 2");

@@ -261,7 +261,10 @@ def test_config2_full_size_properties():
     for key in ("max_count", "hit", "argmax_bin", "read_flag"):
         assert np.array_equal(res[key], res_s[key])
     # (3) sanity of the classifier on the synthetic mix
-    assert res["hit"][from_ref].mean() > 0.97 and res["hit"][~from_ref].mean() < 0.01
+    # (k=13 has only 4^13 = 67 M k-mers, so 4 Mb bins also contain ~6 % of any random read's k-mers and
+    #  iid reads pass thr 18 too -- a property of the configuration, reproduced by the oracle below)
+    assert res["hit"][from_ref].mean() > 0.97
+    assert res["max_count"][from_ref].mean() > res["max_count"][~from_ref].mean() + 20
     # (4) oracle on a random sample of the full-size batch, against the downloaded filter
     of = oracle.OracleIBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
     of.words()[:plan["n_bits"] // 64] = gf.download()

@@ -1,0 +1,51 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (raw page) into a small JSON: one entry per profiled launch with the
+metrics DESIGN.md / bench.py quote.  Usage: tools/ncu_summary.py prof.ncu-rep > profiles/x.json"""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "sm__cycles_elapsed.max",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_atom.sum",
+    "lts__t_sectors_op_atom.sum", "lts__t_sectors_op_red.sum",
+]
+
+
+def main():
+    rep = sys.argv[1]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    out = []
+    for vals in rows[2:]:
+        d = {"kernel": vals[hdr.index("Kernel Name")], "grid": vals[hdr.index("Grid Size")],
+             "block": vals[hdr.index("Block Size")]}
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                try:
+                    d[k] = {"value": float(vals[i].replace(",", "")), "unit": units[i]}
+                except ValueError:
+                    d[k] = {"value": vals[i], "unit": units[i]}
+        out.append(d)
+    json.dump(out, sys.stdout, indent=1)
+
+
+if __name__ == "__main__":
+    main()
