@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="chunks per GPU per step (0 = workload default)")
     ap.add_argument("--mode", default="read_sharded", choices=["read_sharded", "bin_sharded"])
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 tile, 2 stream")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 tile, 2 stream, 3 k-mer table")
     ap.add_argument("--l2-gran", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -326,7 +326,8 @@ def run_ours(args, w, n_reads):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel",
+                "traffic": traffic, "kernel": ("count_table_kernel" if gf.kmer_table_bytes() else
+                           "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel"),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_chunk": bytes_per_chunk, "peak_source": peak_src,
                 "kmer_lookups_per_s": world * n_reads * lookups / (total_ms * 1e-3 / args.steps)}
     # random-sector ceiling for narrow rows (<= 32 B): measured gather microbenchmark over the same matrix
@@ -380,7 +381,7 @@ def run_ours(args, w, n_reads):
                    "thresholds_per_pass": n_lut, "l2_fetch_granularity": rb.get_l2_fetch_granularity(local), "error_rate": ERROR_RATE, "read_mix": "50% reference-derived @10% errors, 50% iid",
                    "l2": "no flush: inputs (%.0f MB reads + %.0f MB filter) exceed the 126 MB L2" % (
                        bases_np.nbytes / 1e6, plan["n_bits"] / 8e6),
-                   "hit_fraction": hits_dev / n_reads, "ibf_build_ms_gpu": build_ms,
+                   "hit_fraction": hits_dev / n_reads, "kmer_table_bytes": gf.kmer_table_bytes(), "ibf_build_ms_gpu": build_ms,
                    "ibf_build_kmers_per_s": n_kmers_ref / (build_ms * 1e-3)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

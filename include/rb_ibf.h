@@ -79,6 +79,8 @@ typedef struct rb_ibf_info_t {
     uint64_t device_bytes;  /* bytes of HBM used by the bit matrix              */
     int32_t device;
     int32_t shard, n_shards;
+    int32_t reserved_;
+    uint64_t kmer_table_bytes; /* bytes of the direct k-mer table, 0 if not built */
 } rb_ibf_info_t;
 
 /* ---- host-side scalar helpers (FP64, bit-exact with the reference) ------- */
@@ -178,8 +180,17 @@ RB_API int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const
 RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_max_count, uint8_t *d_hit,
                               uint32_t *d_argmax_bin, int device, rb_stream stream);
 
+/* Direct k-mer table for narrow filters (row <= 4 words, k <= 16): the AND of the h probed rows is a
+ * pure function of the k-mer, so it is tabulated once for all 4^k ACGT k-mers and both strands
+ * (4^k * 16 * col_words bytes of HBM; 2.1 GB for k=13, 100 bins).  Count calls then read one entry
+ * per k-mer position instead of 2*h rows; k-mers containing N still take the hashed path, so results
+ * are bit-identical.  Built automatically by the first count call when the filter exceeds the L2 and
+ * the table fits half of the free HBM (env RB_KMER_TABLE=0 disables); dropped by rb_ibf_insert_batch*.
+ * This call forces the build now with the given budget (0 = automatic budget); UINT64_MAX disables. */
+RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);
+
 /* Kernel selection override for tests/benchmarks: 0 auto, 1 warp-per-read tile kernel,
- * 2 CTA-per-read streaming kernel. */
+ * 2 CTA-per-read streaming kernel, 3 direct k-mer table kernel (fails if not applicable). */
 RB_API int rb_set_count_kernel(int which);
 /* Number of kernels this library launched since load (all threads); evidence for gpu_launches. */
 RB_API uint64_t rb_kernel_launches(void);

@@ -29,6 +29,7 @@ EXPORTS = [
     "rb_ibf_device_words", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_kernel_launches",
     "rb_microbench_gather", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
+    "rb_ibf_enable_kmer_table",
 ]
 
 
@@ -41,7 +42,8 @@ class RBError(RuntimeError):
 class _Info(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_bins", "n_hash", "kmer_size", "n_bits", "bin_width", "n_blocks",
                                           "col_begin", "col_words", "bin_begin", "n_bins_local", "device_bytes")] + \
-               [("device", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32)]
+               [("device", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32), ("reserved_", C.c_int32),
+                ("kmer_table_bytes", C.c_uint64)]
 
 
 def lib_path():
@@ -97,6 +99,7 @@ def lib():
         "rb_microbench_gather": (i32, [vp, u64, u32, u64, u32, vp, vp]),
         "rb_set_l2_fetch_granularity": (i32, [i32, u32]),
         "rb_get_l2_fetch_granularity": (i32, [i32, vp]),
+        "rb_ibf_enable_kmer_table": (i32, [vp, u64, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -211,7 +214,8 @@ class IBF:
         info = _Info()
         _check(lib().rb_ibf_info(self._h, C.byref(info)))
         for name, _ in _Info._fields_:
-            setattr(self, name, int(getattr(info, name)))
+            if name not in ("reserved_", "kmer_table_bytes"):      # the latter changes over time: see method
+                setattr(self, name, int(getattr(info, name)))
         self.k = self.kmer_size
         self.n_local_words = self.device_bytes // 8
 
@@ -246,6 +250,18 @@ class IBF:
         out = np.zeros(self.n_local_words, np.uint64)
         _check(lib().rb_ibf_download(self._h, _np_ptr(out), out.size))
         return out
+
+    def enable_kmer_table(self, max_table_bytes=0, stream=None):
+        """Build the direct k-mer table now (0 = automatic budget).  See rb_ibf.h."""
+        _check(lib().rb_ibf_enable_kmer_table(self._h, max_table_bytes, _stream_ptr(stream)))
+
+    def disable_kmer_table(self):
+        _check(lib().rb_ibf_enable_kmer_table(self._h, 0xFFFFFFFFFFFFFFFF, None))
+
+    def kmer_table_bytes(self):
+        info = _Info()
+        _check(lib().rb_ibf_info(self._h, C.byref(info)))
+        return int(info.kmer_table_bytes)
 
     def device_words_ptr(self):
         return int(lib().rb_ibf_device_words(self._h) or 0)

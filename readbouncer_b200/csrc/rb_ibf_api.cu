@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,6 +60,12 @@ struct rb_ibf {
     unsigned int *d_err = nullptr;
     bool l2_persist = false;
     rb::HashParams hp{};
+    // direct k-mer table (ibf_table.cu): built lazily by the first count call, dropped by inserts
+    mutable std::mutex table_mu;
+    mutable uint64_t *d_table = nullptr;
+    mutable uint64_t table_entries = 0;
+    mutable bool table_tried = false;
+    mutable uint64_t table_budget = 0;      // 0 = automatic
 };
 
 namespace {
@@ -150,10 +157,11 @@ int alloc_device(rb_ibf *f, bool zero)
 void destroy(rb_ibf *f)
 {
     if (!f) return;
-    if (f->d_words || f->d_err) {
+    if (f->d_words || f->d_err || f->d_table) {
         DeviceGuard g(f->device);
         if (f->d_words) cudaFree(f->d_words);
         if (f->d_err) cudaFree(f->d_err);
+        if (f->d_table) cudaFree(f->d_table);
     }
     delete f;
 }
@@ -213,6 +221,53 @@ rb::FilterView view_of(const rb_ibf *f)
     v.n_bins_local = f->n_bins_local;
     v.hp = f->hp;
     return v;
+}
+
+// ---- direct k-mer table policy -----------------------------------------------------------------
+constexpr uint64_t kTableMinFilterBytes = 64ull << 20;   // smaller filters live in L2: direct probes are as cheap
+
+uint64_t table_bytes_needed(const rb_ibf *f)
+{
+    if (f->col_words == 0 || f->col_words > 4 || f->k > 16) return 0;
+    return (1ull << (2 * f->k)) * 2 * f->col_words * 8;
+}
+
+// Builds the table on `st` if the policy allows it; returns the device pointer or null.
+// force: ignore the "filter fits L2" heuristic (tests, explicit rb_ibf_enable_kmer_table).
+const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force)
+{
+    std::lock_guard<std::mutex> lock(f->table_mu);
+    if (f->d_table) return f->d_table;
+    if (f->table_tried && !force) return nullptr;
+    f->table_tried = true;
+    const char *env = std::getenv("RB_KMER_TABLE");
+    if (!force && env && env[0] == '0') return nullptr;
+    const uint64_t need = table_bytes_needed(f);
+    if (need == 0) return nullptr;
+    if (!force && f->n_local_words * 8 < kTableMinFilterBytes) return nullptr;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>(free_b / 2, 48ull << 30);
+    if (need > budget || need > free_b) return nullptr;
+    uint64_t *t = nullptr;
+    if (cudaMalloc(&t, need) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    const uint64_t entries = 1ull << (2 * f->k);
+    int n = rb::launch_table_build(view_of(f), t, entries, f->sm_count, st);
+    // other host threads may use the table from their own streams right away: finish the build first
+    if (n < 0 || cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(t); cudaGetLastError(); return nullptr; }
+    g_launches += (uint64_t)n;
+    f->d_table = t;
+    f->table_entries = entries;
+    return t;
+}
+
+void drop_table(rb_ibf *f)
+{
+    std::lock_guard<std::mutex> lock(f->table_mu);
+    if (f->d_table) { cudaDeviceSynchronize(); cudaFree(f->d_table); }
+    f->d_table = nullptr;
+    f->table_entries = 0;
+    f->table_tried = false;
 }
 
 // RAII for the L2 access-policy window around count launches
@@ -299,7 +354,7 @@ int rb_get_l2_fetch_granularity(int device, uint32_t *bytes)
 
 int rb_set_count_kernel(int which)
 {
-    if (which < 0 || which > 2) return fail(RB_ERR_INVALID_ARG, "kernel selector must be 0, 1 or 2");
+    if (which < 0 || which > 3) return fail(RB_ERR_INVALID_ARG, "kernel selector must be 0..3");
     g_count_kernel.store(which);
     return RB_OK;
 }
@@ -568,6 +623,21 @@ int rb_ibf_info(const rb_ibf *f, rb_ibf_info_t *out)
     out->bin_width = f->bin_width; out->n_blocks = f->n_blocks; out->col_begin = f->col_begin;
     out->col_words = f->col_words; out->bin_begin = 64 * f->col_begin; out->n_bins_local = f->n_bins_local;
     out->device_bytes = f->n_local_words * 8; out->device = f->device; out->shard = f->shard; out->n_shards = f->n_shards;
+    {
+        std::lock_guard<std::mutex> lock(f->table_mu);
+        out->kmer_table_bytes = f->d_table ? f->table_entries * 2 * f->col_words * 8 : 0;
+    }
+    return RB_OK;
+}
+
+int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "null filter");
+    DeviceGuard g(f->device);
+    if (max_table_bytes == UINT64_MAX) { drop_table(f); f->table_tried = true; return RB_OK; }   // disable
+    f->table_budget = max_table_bytes;
+    if (!ensure_table(f, (cudaStream_t)stream, true))
+        return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable (row > 4 words, k > 16) or over the memory budget");
     return RB_OK;
 }
 
@@ -581,6 +651,7 @@ int rb_ibf_insert_batch_dev(rb_ibf *f, const uint8_t *d_bases, const uint64_t *d
     if (n_frags == 0) return RB_OK;
     if (!d_bases || !d_frag_begin || !d_frag_end || !d_frag_bin) return fail(RB_ERR_INVALID_ARG, "null device pointer");
     DeviceGuard g(f->device);
+    drop_table(f);                      // the table tabulates the old matrix
     rb::InsertArgs a{};
     a.words = f->d_words; a.stride = f->col_words;
     a.bin_begin = 64 * f->col_begin; a.bin_end = a.bin_begin + f->n_bins_local; a.n_bins = f->n_bins;
@@ -641,8 +712,18 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     a.fv = view_of(f);
     a.bases = d_bases; a.read_off = d_read_off; a.n_reads = n_reads; a.lut = d_thr_lut; a.n_lut = n_lut;
     a.keys = d_keys; a.counts_fwd = d_counts_fwd; a.counts_rev = d_counts_rev; a.read_flag = d_read_flag;
+    const int which = g_count_kernel.load();
+    const uint64_t *table = nullptr;
+    if (which == 0 || which == 3) table = ensure_table(f, (cudaStream_t)stream, which == 3);
+    if (which == 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
+    if (table) {
+        int n = rb::launch_count_table(a, table, f->sm_count, (cudaStream_t)stream);
+        if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        g_launches += (uint64_t)n;
+        return RB_OK;
+    }
     L2Window win(f, (cudaStream_t)stream);
-    int n = rb::launch_count(a, max_read_len, g_count_kernel.load(), f->sm_count, (cudaStream_t)stream);
+    int n = rb::launch_count(a, max_read_len, which, f->sm_count, (cudaStream_t)stream);
     if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     g_launches += (uint64_t)n;
     return RB_OK;

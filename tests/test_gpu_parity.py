@@ -12,7 +12,7 @@ from conftest import data_path, golden_words, read_fasta
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = {"auto": 0, "tile": 1, "stream": 2}
+KERNELS = {"auto": 0, "tile": 1, "stream": 2, "table": 3}
 
 
 @pytest.fixture(autouse=True)
@@ -124,7 +124,7 @@ def test_golden_classify_fastq(golden_ibf_paths):
 RAGGED = [250] * 40 + [0, 1, 12, 13, 14, 31, 32, 33, 64, 100, 249, 251, 360, 500, 1023, 1024, 1036, 1037, 1500, 2100, 5000]
 
 
-@pytest.mark.parametrize("kernel", ["tile", "stream"])
+@pytest.mark.parametrize("kernel", ["tile", "stream", "table"])
 @pytest.mark.parametrize("n_seqs,seq_len,frag,k", [
     (1, 500000, 100000, 13),     # 6 bins,  W=1   (config #1 shape)
     (100, 20000, 21000, 13),     # 100 bins, W=2  (config #2 shape)
@@ -136,6 +136,14 @@ RAGGED = [250] * 40 + [0, 1, 12, 13, 14, 31, 32, 33, 64, 100, 249, 251, 360, 500
 def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
     rb.set_count_kernel(KERNELS[kernel])
     plan, of, gf = make_filter_pair(n_seqs, seq_len, frag, k)
+    if kernel == "table":
+        if gf.bin_width > 4:
+            with pytest.raises(rb.RBError):
+                gf.count_batch(np.frombuffer(b"ACGTACGTACGTACGTACGT", np.uint8), np.array([0, 20], np.uint64),
+                               rb.threshold_lut(0.1, k))
+            return
+        gf.enable_kmer_table()
+        assert gf.kmer_table_bytes() == 4 ** k * 16 * gf.bin_width
     assert np.array_equal(gf.download(), of.words()[:plan["n_bits"] // 64])
     bases, off = synth.ragged_reads(plan["bases"], RAGGED, seed=7, frac_from_ref=0.7, n_frac=0.003, lower_frac=0.1)
     lut = rb.threshold_lut(0.1, k)
@@ -144,6 +152,31 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
     exp = of.count_batch(bases, off, lut, n_threads=4)
     assert_same_results(got, exp)
     assert exp["hit"].sum() > 10 and (exp["short_read"] == 1).sum() >= 2
+
+
+def test_kmer_table_handles_n_rich_reads_and_is_dropped_by_insert():
+    """Windows containing N are not in the table and must take the hashed path; inserts invalidate the table."""
+    plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
+    bases, off = synth.ragged_reads(plan["bases"], [250] * 64 + [13, 14, 40, 1200], seed=21, frac_from_ref=0.9,
+                                    n_frac=0.05, lower_frac=0.3)
+    bases[int(off[3]):int(off[4])] = ord("N")                  # an all-N read
+    bases[int(off[5])] = ord("U")                               # U counts as T
+    lut = rb.threshold_lut(0.1, 13)
+    exp = of.count_batch(bases, off, lut, n_threads=4)
+    rb.set_count_kernel(3)
+    assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+    assert gf.kmer_table_bytes() > 0
+    rb.set_count_kernel(0)
+    # insert one more fragment into bin 0: table must be rebuilt, results must follow the new matrix
+    extra = synth.random_bases(5000, 999)
+    gf.insert_batch(extra, [0], [5000], [0])
+    of.insert_batch(extra, [0], [5000], [0])
+    assert gf.kmer_table_bytes() == 0
+    b2, o2 = synth.ragged_reads(extra, [250] * 16, seed=1, frac_from_ref=1.0, error_rate=0.0)
+    rb.set_count_kernel(3)
+    got = gf.count_batch(b2, o2, lut, dense=True)
+    assert_same_results(got, of.count_batch(b2, o2, lut))
+    assert got["hit"].all() and gf.kmer_table_bytes() > 0
 
 
 def test_two_threshold_tables_in_one_pass():
@@ -254,12 +287,14 @@ def test_config2_full_size_properties():
     res_rc = gf.count_batch(rc, off, lut)
     for key in ("max_count", "hit", "argmax_bin"):
         assert np.array_equal(res[key], res_rc[key])
-    # (2) both kernels agree on the whole batch
-    rb.set_count_kernel(2)
-    res_s = gf.count_batch(bases, off, lut)
+    # (2) all three kernels agree on the whole batch (auto = direct k-mer table at this size)
+    assert gf.kmer_table_bytes() == 4 ** 13 * 32
+    for which in (1, 2):
+        rb.set_count_kernel(which)
+        res_s = gf.count_batch(bases, off, lut)
+        for key in ("max_count", "hit", "argmax_bin", "read_flag"):
+            assert np.array_equal(res[key], res_s[key]), (which, key)
     rb.set_count_kernel(0)
-    for key in ("max_count", "hit", "argmax_bin", "read_flag"):
-        assert np.array_equal(res[key], res_s[key])
     # (3) sanity of the classifier on the synthetic mix
     # (k=13 has only 4^13 = 67 M k-mers, so 4 Mb bins also contain ~6 % of any random read's k-mers and
     #  iid reads pass thr 18 too -- a property of the configuration, reproduced by the oracle below)
