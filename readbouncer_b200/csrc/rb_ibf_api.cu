@@ -144,6 +144,14 @@ int alloc_device(rb_ibf *f, bool zero)
     RB_CUDA(cudaMalloc(&f->d_err, sizeof(unsigned int)));
     RB_CUDA(cudaMemset(f->d_err, 0, sizeof(unsigned int)));
     if (zero) RB_CUDA(cudaMemset(f->d_words, 0, f->n_local_words * 8));
+    // host-buffer calls take their staging buffers from the stream-ordered pool; keep freed blocks
+    // cached instead of returning them to the driver at every synchronisation
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, f->device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     // a filter that fits the persisting-L2 carve-out is pinned there for count launches
     const size_t bytes = f->n_local_words * 8;
     if (prop.persistingL2CacheMaxSize > 0 && bytes <= (size_t)prop.persistingL2CacheMaxSize &&
@@ -749,62 +757,113 @@ int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_
     if (n_reads == 0) return RB_OK;
     if (!bases || !read_off || !thr_lut) return fail(RB_ERR_INVALID_ARG, "null pointer");
     if (n_lut == 0 || n_lut > (uint32_t)rb::kMaxLut) return fail(RB_ERR_INVALID_ARG, "n_lut must be 1..4");
-    uint64_t max_len = 0;
-    for (uint64_t i = 0; i < n_reads; ++i) {
+    if (n_reads > 0x7FFFFFFFull) return fail(RB_ERR_INVALID_ARG, "more than 2^31-1 reads in one batch");
+
+    // ---- cut the batch into pieces of ~16 MB of bases: piece i+1 is copied in while piece i is
+    //      classified and piece i-1 is copied out (three slots, three streams) ------------------------
+    const uint64_t kPieceBytes = 16ull << 20, kPieceReads = 1ull << 18;
+    const bool dense = counts_fwd || counts_rev;
+    const uint64_t nbl = f->n_bins_local;
+    const uint64_t max_piece_reads = dense ? std::max<uint64_t>(1, std::min<uint64_t>(kPieceReads, (64ull << 20) / (2 * nbl)))
+                                           : kPieceReads;
+    std::vector<uint64_t> cut{0};
+    uint64_t max_len = 0, max_piece_bases = 0, max_piece_n = 0;
+    for (uint64_t i = 0, r0 = 0; i < n_reads; ++i) {
         if (read_off[i + 1] < read_off[i]) return fail(RB_ERR_INVALID_ARG, "read offsets must be non-decreasing");
         max_len = std::max(max_len, read_off[i + 1] - read_off[i]);
-    }
-    const uint64_t n_bases = read_off[n_reads] - read_off[0];
-    DeviceGuard g(f->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const uint64_t nk = (uint64_t)n_lut * n_reads;
-    const uint64_t dense = n_reads * f->n_bins_local;
-    uint8_t *d_bases = nullptr, *d_small = nullptr;
-    uint64_t *d_off = nullptr, *d_keys = nullptr;
-    uint16_t *d_lut = nullptr, *d_cf = nullptr, *d_cr = nullptr;
-    std::vector<uint64_t> rel;
-    auto body = [&]() -> int {
-        RB_CUDA(cudaMallocAsync(&d_bases, n_bases ? n_bases : 1, st));
-        RB_CUDA(cudaMallocAsync(&d_off, (n_reads + 1) * 8, st));
-        RB_CUDA(cudaMallocAsync(&d_lut, (size_t)n_lut * rb::kLutSize * 2, st));
-        RB_CUDA(cudaMallocAsync(&d_keys, nk * 8, st));
-        // max_count (2 B) | argmax (4 B) | hit (1 B) per key, then read_flag
-        RB_CUDA(cudaMallocAsync(&d_small, nk * 7 + n_reads + 16, st));
-        if (counts_fwd) RB_CUDA(cudaMallocAsync(&d_cf, dense * 2, st));
-        if (counts_rev) RB_CUDA(cudaMallocAsync(&d_cr, dense * 2, st));
-        const uint64_t *off_src = read_off;
-        if (read_off[0] != 0) {   // make offsets relative to the uploaded slice
-            rel.resize(n_reads + 1);
-            for (uint64_t i = 0; i <= n_reads; ++i) rel[i] = read_off[i] - read_off[0];
-            off_src = rel.data();
+        const bool last = i + 1 == n_reads;
+        if (last || read_off[i + 1] - read_off[r0] >= kPieceBytes || i + 1 - r0 >= max_piece_reads) {
+            max_piece_bases = std::max(max_piece_bases, read_off[i + 1] - read_off[r0]);
+            max_piece_n = std::max(max_piece_n, i + 1 - r0);
+            cut.push_back(i + 1);
+            r0 = i + 1;
         }
-        RB_CUDA(cudaMemcpyAsync(d_bases, bases + read_off[0], n_bases, cudaMemcpyHostToDevice, st));
-        RB_CUDA(cudaMemcpyAsync(d_off, off_src, (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
-        RB_CUDA(cudaMemcpyAsync(d_lut, thr_lut, (size_t)n_lut * rb::kLutSize * 2, cudaMemcpyHostToDevice, st));
-        uint32_t *d_amax = reinterpret_cast<uint32_t *>(d_small);            // 4-byte aligned first
-        uint16_t *d_max = reinterpret_cast<uint16_t *>(d_small + nk * 4);
-        uint8_t *d_hit = d_small + nk * 6;
-        uint8_t *d_flag = d_small + nk * 7;
-        int s2 = rb_ibf_count_batch_dev(f, d_bases, d_off, n_reads, (uint32_t)std::min<uint64_t>(max_len, 0xFFFFFFFFu), d_lut,
-                                        n_lut, d_keys, d_cf, d_cr, d_flag, stream);
-        if (s2 != RB_OK) return s2;
-        s2 = rb_keys_decode_dev(d_keys, nk, d_max, d_hit, d_amax, f->device, stream);
-        if (s2 != RB_OK) return s2;
-        if (max_count) RB_CUDA(cudaMemcpyAsync(max_count, d_max, nk * 2, cudaMemcpyDeviceToHost, st));
-        if (hit) RB_CUDA(cudaMemcpyAsync(hit, d_hit, nk, cudaMemcpyDeviceToHost, st));
-        if (argmax_bin) RB_CUDA(cudaMemcpyAsync(argmax_bin, d_amax, nk * 4, cudaMemcpyDeviceToHost, st));
-        if (read_flag) RB_CUDA(cudaMemcpyAsync(read_flag, d_flag, n_reads, cudaMemcpyDeviceToHost, st));
-        if (counts_fwd) RB_CUDA(cudaMemcpyAsync(counts_fwd, d_cf, dense * 2, cudaMemcpyDeviceToHost, st));
-        if (counts_rev) RB_CUDA(cudaMemcpyAsync(counts_rev, d_cr, dense * 2, cudaMemcpyDeviceToHost, st));
-        cudaError_t e = cudaStreamSynchronize(st);
+    }
+    const size_t n_pieces = cut.size() - 1;
+    const int n_slots = (int)std::min<size_t>(3, n_pieces);
+
+    DeviceGuard g(f->device);
+    cudaStream_t user = (cudaStream_t)stream;
+    struct Slot {
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+        uint8_t *d_bases = nullptr, *d_small = nullptr;
+        uint64_t *d_off = nullptr, *d_keys = nullptr;
+        uint16_t *d_cf = nullptr, *d_cr = nullptr;
+    } slot[3];
+    uint16_t *d_lut = nullptr;
+    cudaEvent_t ev_start = nullptr;
+    const uint64_t nkp = (uint64_t)n_lut * max_piece_n;
+
+    auto body = [&]() -> int {
+        RB_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        RB_CUDA(cudaMallocAsync(&d_lut, (size_t)n_lut * rb::kLutSize * 2, user));
+        RB_CUDA(cudaMemcpyAsync(d_lut, thr_lut, (size_t)n_lut * rb::kLutSize * 2, cudaMemcpyHostToDevice, user));
+        for (int s = 0; s < n_slots; ++s) {
+            Slot &S = slot[s];
+            RB_CUDA(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+            RB_CUDA(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+            RB_CUDA(cudaMallocAsync(&S.d_bases, max_piece_bases ? max_piece_bases : 1, user));
+            RB_CUDA(cudaMallocAsync(&S.d_off, (max_piece_n + 1) * 8, user));
+            RB_CUDA(cudaMallocAsync(&S.d_keys, nkp * 8, user));
+            RB_CUDA(cudaMallocAsync(&S.d_small, nkp * 7 + max_piece_n + 16, user));   // argmax | max | hit | flag
+            if (counts_fwd) RB_CUDA(cudaMallocAsync(&S.d_cf, max_piece_n * nbl * 2, user));
+            if (counts_rev) RB_CUDA(cudaMallocAsync(&S.d_cr, max_piece_n * nbl * 2, user));
+        }
+        RB_CUDA(cudaEventRecord(ev_start, user));          // slot streams start after the caller's stream
+        for (int s = 0; s < n_slots; ++s) RB_CUDA(cudaStreamWaitEvent(slot[s].st, ev_start, 0));
+        for (size_t p = 0; p < n_pieces; ++p) {
+            Slot &S = slot[p % n_slots];
+            const uint64_t r0 = cut[p], r1 = cut[p + 1], n = r1 - r0, nk = (uint64_t)n_lut * n;
+            const uint64_t b0 = read_off[r0], nb = read_off[r1] - b0;
+            RB_CUDA(cudaMemcpyAsync(S.d_bases, bases + b0, nb, cudaMemcpyHostToDevice, S.st));
+            RB_CUDA(cudaMemcpyAsync(S.d_off, read_off + r0, (n + 1) * 8, cudaMemcpyHostToDevice, S.st));
+            uint32_t *d_amax = reinterpret_cast<uint32_t *>(S.d_small);
+            uint16_t *d_max = reinterpret_cast<uint16_t *>(S.d_small + nk * 4);
+            uint8_t *d_hit = S.d_small + nk * 6;
+            uint8_t *d_flag = S.d_small + nk * 7;
+            // offsets stay absolute: bias the base pointer instead of rewriting them
+            const uint8_t *biased = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(S.d_bases) - (uintptr_t)b0);
+            int s2 = rb_ibf_count_batch_dev(f, biased, S.d_off, n, (uint32_t)std::min<uint64_t>(max_len, 0xFFFFFFFFu),
+                                            d_lut, n_lut, S.d_keys, S.d_cf, S.d_cr, d_flag, S.st);
+            if (s2 != RB_OK) return s2;
+            s2 = rb_keys_decode_dev(S.d_keys, nk, d_max, d_hit, d_amax, f->device, S.st);
+            if (s2 != RB_OK) return s2;
+            for (uint32_t t = 0; t < n_lut; ++t) {
+                const uint64_t ho = (uint64_t)t * n_reads + r0, dofs = (uint64_t)t * n;
+                if (max_count) RB_CUDA(cudaMemcpyAsync(max_count + ho, d_max + dofs, n * 2, cudaMemcpyDeviceToHost, S.st));
+                if (hit) RB_CUDA(cudaMemcpyAsync(hit + ho, d_hit + dofs, n, cudaMemcpyDeviceToHost, S.st));
+                if (argmax_bin) RB_CUDA(cudaMemcpyAsync(argmax_bin + ho, d_amax + dofs, n * 4, cudaMemcpyDeviceToHost, S.st));
+            }
+            if (read_flag) RB_CUDA(cudaMemcpyAsync(read_flag + r0, d_flag, n, cudaMemcpyDeviceToHost, S.st));
+            if (counts_fwd) RB_CUDA(cudaMemcpyAsync(counts_fwd + r0 * nbl, S.d_cf, n * nbl * 2, cudaMemcpyDeviceToHost, S.st));
+            if (counts_rev) RB_CUDA(cudaMemcpyAsync(counts_rev + r0 * nbl, S.d_cr, n * nbl * 2, cudaMemcpyDeviceToHost, S.st));
+        }
+        for (int s = 0; s < n_slots; ++s) {
+            RB_CUDA(cudaEventRecord(slot[s].done, slot[s].st));
+            RB_CUDA(cudaStreamWaitEvent(user, slot[s].done, 0));
+        }
+        cudaError_t e = cudaStreamSynchronize(user);
         if (e != cudaSuccess) return fail(RB_ERR_COUNT_KMER, std::string("Error counting kmers in IBF bins: ") + cudaGetErrorString(e));
         return RB_OK;
     };
-    int s = body();
-    void *bufs[] = {d_bases, d_off, d_lut, d_keys, d_small, d_cf, d_cr};
-    for (void *p : bufs) if (p) cudaFreeAsync(p, st);
-    cudaStreamSynchronize(st);
-    return s;
+    int st = body();
+    if (st != RB_OK) {                       // drain whatever was enqueued before releasing buffers
+        for (int s = 0; s < n_slots; ++s) if (slot[s].st) cudaStreamSynchronize(slot[s].st);
+        cudaStreamSynchronize(user);
+        cudaGetLastError();
+    }
+    for (int s = 0; s < 3; ++s) {
+        Slot &S = slot[s];
+        void *bufs[] = {S.d_bases, S.d_off, S.d_keys, S.d_small, S.d_cf, S.d_cr};
+        for (void *p : bufs) if (p) cudaFreeAsync(p, user);
+        if (S.done) cudaEventDestroy(S.done);
+        if (S.st) cudaStreamDestroy(S.st);
+    }
+    if (d_lut) cudaFreeAsync(d_lut, user);
+    if (ev_start) cudaEventDestroy(ev_start);
+    cudaStreamSynchronize(user);
+    return st;
 }
 
 }  // extern "C"
