@@ -190,7 +190,8 @@ RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_ma
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);
 
 /* Kernel selection override for tests/benchmarks: 0 auto, 1 warp-per-read tile kernel,
- * 2 CTA-per-read streaming kernel, 3 direct k-mer table kernel (fails if not applicable). */
+ * 2 CTA-per-read streaming kernel, 3 direct k-mer table kernel (fails if not applicable; bit-sliced
+ * register counters for rows <= 2 words), 4 k-mer table kernel with shared-memory counters. */
 RB_API int rb_set_count_kernel(int which);
 /* Number of kernels this library launched since load (all threads); evidence for gpu_launches. */
 RB_API uint64_t rb_kernel_launches(void);

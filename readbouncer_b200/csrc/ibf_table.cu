@@ -167,6 +167,259 @@ count_table_kernel(const CountArgs a, const uint64_t *__restrict__ table)
 }
 
 // ------------------------------------------------------------------------------------------
+// lookup kernel with bit-sliced counting (rows of <= 2 words)
+// ------------------------------------------------------------------------------------------
+// The per-bin counters never leave registers.  Each lane adds the masks of its <= 15 k-mer positions
+// into 4 bit planes per 32-bit mask word with carry-save adders (9 logic ops per 4 positions and word),
+// so the cost does not depend on how many bits are set.  The 32 lanes are then summed by an
+// exchange-and-halve butterfly of bit-sliced full adders (shuffle distance 16, 8, 4, 2, 1): every
+// level a lane keeps one half of its span and receives its partner's copy of that half, so after five
+// levels lane l holds the 9-plane counts of NWP consecutive mask bits.  Words are ordered
+// q = 2*word32 + strand, which puts the forward and reverse counts of the same bins in lanes l and
+// l ^ (32/NWP): one more exchange and each lane evaluates select_matches / max_matches for its bins.
+constexpr int kBsSeg = 15;                  // positions per lane per chunk (4 planes hold 0..15)
+constexpr int kBsChunk = 32 * kBsSeg;       // 480 positions per warp chunk
+constexpr int kBsDig = kBsChunk + 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
+
+// fold the upper/lower half of the WORDS held by a lane pair (distance OFF); NP -> NP+1 planes
+template <int NW, int NP, int OFF>
+__device__ __forceinline__ void fold_words(const uint32_t (&in)[NP][NW], uint32_t (&out)[NP + 1][NW / 2], int lane)
+{
+    const bool upper = (lane & OFF) != 0;
+    uint32_t carry[NW / 2];
+#pragma unroll
+    for (int i = 0; i < NW / 2; ++i) carry[i] = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+#pragma unroll
+        for (int i = 0; i < NW / 2; ++i) {
+            const uint32_t lo = in[p][i], hi = in[p][NW / 2 + i];
+            const uint32_t mine = upper ? hi : lo;
+            const uint32_t recv = __shfl_xor_sync(kFull, upper ? lo : hi, OFF);
+            out[p][i] = mine ^ recv ^ carry[i];
+            carry[i] = maj3(mine, recv, carry[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NW / 2; ++i) out[NP][i] = carry[i];
+}
+
+// fold the upper/lower half of the BITS significant bits of a single word
+template <int BITS, int NP, int OFF>
+__device__ __forceinline__ void fold_bits(const uint32_t (&in)[NP], uint32_t (&out)[NP + 1], int lane)
+{
+    constexpr int H = BITS / 2;
+    constexpr uint32_t LOW = (1u << H) - 1u;
+    const bool upper = (lane & OFF) != 0;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const uint32_t lo = in[p] & LOW, hi = (in[p] >> H) & LOW;
+        const uint32_t mine = upper ? hi : lo;
+        const uint32_t recv = __shfl_xor_sync(kFull, upper ? lo : hi, OFF);
+        out[p] = mine ^ recv ^ carry;
+        carry = maj3(mine, recv, carry);
+    }
+    out[NP] = carry;
+}
+
+// 32-lane sum of 4-plane per-lane counters -> 9-plane counters of NWP bits per lane
+template <int NWP>
+__device__ __forceinline__ void warp_fold(const uint32_t (&pl)[4][NWP], uint32_t (&res)[9], int lane)
+{
+    if constexpr (NWP == 8) {
+        uint32_t a[5][4], b[6][2], c[7][1], d[7], e[8];
+        fold_words<8, 4, 16>(pl, a, lane);
+        fold_words<4, 5, 8>(a, b, lane);
+        fold_words<2, 6, 4>(b, c, lane);
+#pragma unroll
+        for (int p = 0; p < 7; ++p) d[p] = c[p][0];
+        fold_bits<32, 7, 2>(d, e, lane);
+        fold_bits<16, 8, 1>(e, res, lane);
+    } else {   // NWP == 4
+        uint32_t a[5][2], b[6][1], c[6], d[7], e[8];
+        fold_words<4, 4, 16>(pl, a, lane);
+        fold_words<2, 5, 8>(a, b, lane);
+#pragma unroll
+        for (int p = 0; p < 6; ++p) c[p] = b[p][0];
+        fold_bits<32, 6, 4>(c, d, lane);
+        fold_bits<16, 7, 2>(d, e, lane);
+        fold_bits<8, 8, 1>(e, res, lane);
+    }
+}
+
+template <int NP>
+__device__ __forceinline__ uint32_t bs_ge(const uint32_t (&pl)[NP], uint32_t thr)
+{
+    if (thr >> NP) return 0;
+    uint32_t gt = 0, eq = ~0u;
+#pragma unroll
+    for (int p = NP - 1; p >= 0; --p) {
+        const uint32_t tb = ((thr >> p) & 1u) ? ~0u : 0u;
+        gt |= eq & pl[p] & ~tb;
+        eq &= ~(pl[p] ^ tb);
+    }
+    return gt | eq;
+}
+
+template <int NP>
+__device__ __forceinline__ uint32_t bs_get(const uint32_t (&pl)[NP], int b)
+{
+    uint32_t c = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) c |= ((pl[p] >> b) & 1u) << p;
+    return c;
+}
+
+// WT: row words (1 or 2).  NPA: planes of the per-read accumulator (9 when every read is a single
+// chunk, else 16).
+template <int WT, int NPA>
+__global__ void __launch_bounds__(kTileWarps * 32)
+count_table_bs_kernel(const CountArgs a, const uint64_t *__restrict__ table)
+{
+    constexpr int NWP = 4 * WT;             // 32-bit mask words of both strands
+    constexpr int B = NWP;                  // mask bits owned by a lane after the fold
+    constexpr int LPW = 32 / B;             // lanes per mask word
+    __shared__ __align__(16) uint8_t s_dig[kTileWarps][kBsDig];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t total_warps = (uint64_t)gridDim.x * kTileWarps;
+    const uint32_t k = a.fv.hp.k;
+    const uint64_t kmask = (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    uint8_t *dig = s_dig[warp];
+    // bins this lane reports: strand = q & 1, 32-bit word ww = q >> 1 of that strand
+    const int q = lane / LPW;
+    const int strand = q & 1;
+    const uint32_t bin0 = (uint32_t)(q >> 1) * 32u + (uint32_t)B * (uint32_t)(lane % LPW);
+
+    for (uint64_t read = (uint64_t)blockIdx.x * kTileWarps + warp; read < a.n_reads; read += total_warps) {
+        const uint64_t off = a.read_off[read];
+        const uint64_t len = a.read_off[read + 1] - off;
+        const uint32_t flag = read_flag_of(len, k);
+        if (lane == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
+
+        uint32_t acc[NPA];
+#pragma unroll
+        for (int p = 0; p < NPA; ++p) acc[p] = 0;
+
+        if (flag == 0) {
+            const uint32_t npos = (uint32_t)len - k + 1;
+            for (uint32_t cs = 0; cs < npos; cs += kBsChunk) {
+                const uint32_t cn = min((uint32_t)kBsChunk, npos - cs);
+                __syncwarp();
+                for (uint32_t i = lane; i < cn + k - 1; i += 32) dig[i] = (uint8_t)dna5(a.bases[off + cs + i]);
+                __syncwarp();
+                const uint32_t seg = (cn + 31) >> 5;
+                const uint32_t j0 = lane * seg;
+                const uint32_t j1 = min(j0 + seg, cn);
+                uint32_t pl[4][NWP];
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int w = 0; w < NWP; ++w) pl[p][w] = 0;
+                if (j0 < j1) {
+                    uint64_t x = 0;
+                    uint32_t nbad = 0;
+                    for (uint32_t u = 0; u < k; ++u) {
+                        uint32_t d = dig[j0 + u];
+                        x = (x << 2) | (d & 3u);
+                        nbad += d >> 2;
+                    }
+                    x &= kmask;
+                    for (uint32_t j = j0; j < j1; j += 4) {
+                        uint64_t mf[4][WT], mr[4][WT];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                            for (int w = 0; w < WT; ++w) { mf[u][w] = 0; mr[u][w] = 0; }
+                            if (j + u < j1) {
+                                if (nbad == 0) load_entry<WT>(table + x * (2 * WT), mf[u], mr[u]);
+                                else probe_hashed<WT>(a.fv, dig, j + u, mf[u], mr[u]);
+                                if (j + u + 1 < j1) {
+                                    uint32_t dout = dig[j + u], din = dig[j + u + k];
+                                    x = ((x << 2) | (din & 3u)) & kmask;
+                                    nbad += (din >> 2) - (dout >> 2);
+                                }
+                            }
+                        }
+                        // carry-save add of the four masks into planes ones/twos/fours/eights
+#pragma unroll
+                        for (int w = 0; w < NWP; ++w) {
+                            uint32_t m[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const uint64_t v = (w & 1) ? mr[u][w >> 2] : mf[u][w >> 2];   // q = 2*word32 + strand
+                                m[u] = ((w >> 1) & 1) ? (uint32_t)(v >> 32) : (uint32_t)v;
+                            }
+                            uint32_t t1 = maj3(pl[0][w], m[0], m[1]);
+                            pl[0][w] ^= m[0] ^ m[1];
+                            uint32_t t2 = maj3(pl[0][w], m[2], m[3]);
+                            pl[0][w] ^= m[2] ^ m[3];
+                            uint32_t f4 = maj3(pl[1][w], t1, t2);
+                            pl[1][w] ^= t1 ^ t2;
+                            uint32_t c8 = pl[2][w] & f4;
+                            pl[2][w] ^= f4;
+                            pl[3][w] ^= c8;
+                        }
+                    }
+                }
+                uint32_t res[9];
+                warp_fold<NWP>(pl, res, lane);
+                // acc += res (bit-sliced ripple add, NPA planes)
+                uint32_t carry = 0;
+#pragma unroll
+                for (int p = 0; p < NPA; ++p) {
+                    const uint32_t r = p < 9 ? res[p] : 0u;
+                    const uint32_t s = acc[p] ^ r ^ carry;
+                    carry = maj3(acc[p], r, carry);
+                    acc[p] = s;
+                }
+            }
+        }
+
+        // ---- epilogue: bring the other strand's planes of my bins, then threshold / max -----------------
+        uint32_t oth[NPA];
+#pragma unroll
+        for (int p = 0; p < NPA; ++p) oth[p] = __shfl_xor_sync(kFull, acc[p], LPW);
+        const uint64_t nbl = a.fv.n_bins_local;
+        uint32_t valid = 0;
+        if (bin0 < nbl) valid = (nbl - bin0 >= (uint64_t)B) ? ((B == 32) ? ~0u : ((1u << B) - 1u)) : ((1u << (nbl - bin0)) - 1u);
+        if (a.counts_fwd || a.counts_rev) {
+            uint16_t *dst = strand == 0 ? a.counts_fwd : a.counts_rev;
+            if (dst)
+                for (int b = 0; b < B; ++b)
+                    if ((valid >> b) & 1u) dst[read * nbl + bin0 + b] = (uint16_t)bs_get<NPA>(acc, b);
+        }
+        uint64_t best[kMaxLut];
+#pragma unroll
+        for (int t = 0; t < kMaxLut; ++t) {
+            best[t] = 0;
+            if (t < (int)a.n_lut && flag == 0) {
+                const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)t * kLutSize + len);
+                uint32_t pass = (bs_ge<NPA>(acc, thr) | bs_ge<NPA>(oth, thr)) & valid;
+                while (pass) {
+                    const int b = __ffs((int)pass) - 1;
+                    pass &= pass - 1;
+                    const uint32_t m = max(bs_get<NPA>(acc, b), bs_get<NPA>(oth, b));
+                    const uint64_t key = pack_key(m, (uint32_t)(a.fv.bin_begin + bin0 + b));
+                    best[t] = key > best[t] ? key : best[t];
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kMaxLut; ++t) {
+            if (t < (int)a.n_lut) {
+                const uint64_t bk = warp_max_u64(best[t]);
+                if (lane == 0) a.keys[(size_t)t * a.n_reads + read] = bk;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
 template <int WT>
@@ -204,10 +457,33 @@ static void launch_table_wt(const CountArgs &a, const uint64_t *table, int sm_co
     count_table_kernel<WT, U><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }
 
-int launch_count_table(const CountArgs &a, const uint64_t *table, int sm_count, cudaStream_t st)
+template <int WT, int NPA>
+static void launch_table_bs(const CountArgs &a, const uint64_t *table, int sm_count, cudaStream_t st)
+{
+    static int occ = 0;
+    if (occ == 0) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, count_table_bs_kernel<WT, NPA>, kTileWarps * 32, 0);
+        occ = o > 0 ? o : 1;
+    }
+    uint64_t blocks_needed = (a.n_reads + kTileWarps - 1) / kTileWarps;
+    uint64_t max_x = (uint64_t)sm_count * occ;
+    uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
+    count_table_bs_kernel<WT, NPA><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
+}
+
+int launch_count_table(const CountArgs &a, const uint64_t *table, uint32_t max_read_len, int variant, int sm_count,
+                       cudaStream_t st)
 {
     if (a.n_reads == 0) return 0;
     if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut) return -1;
+    // variant 0: bit-sliced register counters (rows <= 2 words); 1: shared-memory atomic counters
+    if (variant == 0 && a.fv.stride <= 2) {
+        const bool single_chunk = max_read_len != 0 && max_read_len < a.fv.hp.k + (uint32_t)kBsChunk;
+        if (a.fv.stride == 1) { if (single_chunk) launch_table_bs<1, 9>(a, table, sm_count, st); else launch_table_bs<1, 16>(a, table, sm_count, st); }
+        else { if (single_chunk) launch_table_bs<2, 9>(a, table, sm_count, st); else launch_table_bs<2, 16>(a, table, sm_count, st); }
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     switch (a.fv.stride) {
     case 1: launch_table_wt<1, 2>(a, table, sm_count, st); break;
     case 2: launch_table_wt<2, 2>(a, table, sm_count, st); break;

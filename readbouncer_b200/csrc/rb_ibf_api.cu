@@ -362,7 +362,7 @@ int rb_get_l2_fetch_granularity(int device, uint32_t *bytes)
 
 int rb_set_count_kernel(int which)
 {
-    if (which < 0 || which > 3) return fail(RB_ERR_INVALID_ARG, "kernel selector must be 0..3");
+    if (which < 0 || which > 4) return fail(RB_ERR_INVALID_ARG, "kernel selector must be 0..4");
     g_count_kernel.store(which);
     return RB_OK;
 }
@@ -722,10 +722,10 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     a.keys = d_keys; a.counts_fwd = d_counts_fwd; a.counts_rev = d_counts_rev; a.read_flag = d_read_flag;
     const int which = g_count_kernel.load();
     const uint64_t *table = nullptr;
-    if (which == 0 || which == 3) table = ensure_table(f, (cudaStream_t)stream, which == 3);
-    if (which == 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
+    if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3);
+    if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
     if (table) {
-        int n = rb::launch_count_table(a, table, f->sm_count, (cudaStream_t)stream);
+        int n = rb::launch_count_table(a, table, max_read_len, which == 4 ? 1 : 0, f->sm_count, (cudaStream_t)stream);
         if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         g_launches += (uint64_t)n;
         return RB_OK;

@@ -12,7 +12,7 @@ from conftest import data_path, golden_words, read_fasta
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = {"auto": 0, "tile": 1, "stream": 2, "table": 3}
+KERNELS = {"auto": 0, "tile": 1, "stream": 2, "table": 3, "table_atomic": 4}
 
 
 @pytest.fixture(autouse=True)
@@ -124,7 +124,7 @@ def test_golden_classify_fastq(golden_ibf_paths):
 RAGGED = [250] * 40 + [0, 1, 12, 13, 14, 31, 32, 33, 64, 100, 249, 251, 360, 500, 1023, 1024, 1036, 1037, 1500, 2100, 5000]
 
 
-@pytest.mark.parametrize("kernel", ["tile", "stream", "table"])
+@pytest.mark.parametrize("kernel", ["tile", "stream", "table", "table_atomic"])
 @pytest.mark.parametrize("n_seqs,seq_len,frag,k", [
     (1, 500000, 100000, 13),     # 6 bins,  W=1   (config #1 shape)
     (100, 20000, 21000, 13),     # 100 bins, W=2  (config #2 shape)
@@ -136,7 +136,7 @@ RAGGED = [250] * 40 + [0, 1, 12, 13, 14, 31, 32, 33, 64, 100, 249, 251, 360, 500
 def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
     rb.set_count_kernel(KERNELS[kernel])
     plan, of, gf = make_filter_pair(n_seqs, seq_len, frag, k)
-    if kernel == "table":
+    if kernel.startswith("table"):
         if gf.bin_width > 4:
             with pytest.raises(rb.RBError):
                 gf.count_batch(np.frombuffer(b"ACGTACGTACGTACGTACGT", np.uint8), np.array([0, 20], np.uint64),
@@ -163,8 +163,9 @@ def test_kmer_table_handles_n_rich_reads_and_is_dropped_by_insert():
     bases[int(off[5])] = ord("U")                               # U counts as T
     lut = rb.threshold_lut(0.1, 13)
     exp = of.count_batch(bases, off, lut, n_threads=4)
-    rb.set_count_kernel(3)
-    assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+    for which in (3, 4):
+        rb.set_count_kernel(which)
+        assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
     assert gf.kmer_table_bytes() > 0
     rb.set_count_kernel(0)
     # insert one more fragment into bin 0: table must be rebuilt, results must follow the new matrix
@@ -289,7 +290,7 @@ def test_config2_full_size_properties():
         assert np.array_equal(res[key], res_rc[key])
     # (2) all three kernels agree on the whole batch (auto = direct k-mer table at this size)
     assert gf.kmer_table_bytes() == 4 ** 13 * 32
-    for which in (1, 2):
+    for which in (1, 2, 4):
         rb.set_count_kernel(which)
         res_s = gf.count_batch(bases, off, lut)
         for key in ("max_count", "hit", "argmax_bin", "read_flag"):
