@@ -208,11 +208,12 @@ def run_ours(args, w, n_reads):
     n_kmers_ref = int(np.maximum(plan["frag_end"] - plan["frag_begin"], w["k"] - 1).sum() - (w["k"] - 1) * len(plan["frag_bin"]))
     del d_ref, d_fb, d_fe, d_fbin
     gf = gf_full
+    full_keys_check = None
     if bin_sharded:
+        full_keys_check = True
         words = gf_full.download()
         gf = rb.IBF.from_words(words, plan["n_bins"], 3, w["k"], plan["n_bits"], device=local, shard=rank, n_shards=world)
         del words
-        gf_full.close()
 
     # ---- reads: host (pinned) and device copies --------------------------------------------------------
     # read-sharded: every rank classifies its own batch; bin-sharded: all ranks see the same batch
@@ -253,6 +254,15 @@ def run_ours(args, w, n_reads):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if bin_sharded:
+        # the all-reduced shard keys must equal the keys of the whole (replicated) filter
+        d_full = torch.zeros_like(d_keys)
+        gf_full.count_batch_dev(d_bases, d_off, n_reads, d_lut, n_lut, d_full, max_read_len=w["chunk"], stream=stream)
+        torch.cuda.synchronize()
+        assert torch.equal(d_full, d_keys), "bin-sharded combine differs from the whole-filter result"
+        del d_full
+        gf_full.close()
+        torch.cuda.empty_cache()
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = rb.kernel_launches()
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -329,7 +339,7 @@ def run_ours(args, w, n_reads):
                 "traffic": traffic, "kernel": ("count_table_kernel" if gf.kmer_table_bytes() else
                            "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel"),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_chunk": bytes_per_chunk, "peak_source": peak_src,
-                "kmer_lookups_per_s": world * n_reads * lookups / (total_ms * 1e-3 / args.steps)}
+                "kmer_lookups_per_s": (n_reads if bin_sharded else world * n_reads) * lookups / (total_ms * 1e-3 / args.steps)}
     # random-sector ceiling for narrow rows (<= 32 B): measured gather microbenchmark over the same matrix
     row_bytes = int(gf.col_words * 8)
     if row_bytes in (8, 16, 32):
@@ -370,7 +380,9 @@ def run_ours(args, w, n_reads):
         cpu_baseline = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "first %d chunks of the step's batch, %d threads, %.1f s; results equal the GPU's" % (sample, cores, dt)}
 
-    value = world * n_reads * args.steps / (total_ms * 1e-3)
+    # read-sharded: every rank classifies its own batch; bin-sharded: all ranks share ONE batch
+    units = n_reads if bin_sharded else world * n_reads
+    value = units * args.steps / (total_ms * 1e-3)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak" if not bin_sharded else "strong",
