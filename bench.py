@@ -35,6 +35,7 @@ WORKLOADS = {
     "cfg1_5Mb_51bins": dict(n_seqs=1, seq_len=5_000_001, fragment=100_000, k=13, chunk=250, reads=1_000_000),
     "cfg2_100x4Mb_100bins": dict(n_seqs=100, seq_len=4_000_000, fragment=4_200_000, k=13, chunk=250, reads=1_000_000),
     "cfg3_3.1Gb_31kbins": dict(n_seqs=24, seq_len=129_166_667, fragment=100_000, k=13, chunk=250, reads=65_536),
+    "w1_50x4Mb_50bins": dict(n_seqs=50, seq_len=4_000_000, fragment=4_200_000, k=13, chunk=250, reads=1_000_000),
     "mini_100x60kb_100bins": dict(n_seqs=100, seq_len=60_000, fragment=61_000, k=13, chunk=250, reads=65_536),
 }
 DEFAULT_WORKLOAD = "cfg2_100x4Mb_100bins"

@@ -79,7 +79,7 @@ typedef struct rb_ibf_info_t {
     uint64_t device_bytes;  /* bytes of HBM used by the bit matrix              */
     int32_t device;
     int32_t shard, n_shards;
-    int32_t reserved_;
+    int32_t kmer_table_span;   /* consecutive k-mers per table entry (1 or 2), 0 if not built */
     uint64_t kmer_table_bytes; /* bytes of the direct k-mer table, 0 if not built */
 } rb_ibf_info_t;
 
@@ -181,12 +181,15 @@ RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_ma
                               uint32_t *d_argmax_bin, int device, rb_stream stream);
 
 /* Direct k-mer table for narrow filters (row <= 4 words, k <= 16): the AND of the h probed rows is a
- * pure function of the k-mer, so it is tabulated once for all 4^k ACGT k-mers and both strands
- * (4^k * 16 * col_words bytes of HBM; 2.1 GB for k=13, 100 bins).  Count calls then read one entry
- * per k-mer position instead of 2*h rows; k-mers containing N still take the hashed path, so results
- * are bit-identical.  Built automatically by the first count call when the filter exceeds the L2 and
- * the table fits half of the free HBM (env RB_KMER_TABLE=0 disables); dropped by rb_ibf_insert_batch*.
- * This call forces the build now with the given budget (0 = automatic budget); UINT64_MAX disables. */
+ * pure function of the k-mer, so it is tabulated once for all ACGT k-mers and both strands.  An entry
+ * covers a window of `span` consecutive k-mers (k+span-1 bases): span 1 = 4^k * 16 * col_words bytes
+ * (2.1 GB for k=13, 100 bins), span 2 = 4^(k+1) * 32 * col_words bytes (17 GB; rows <= 2 words).
+ * Count calls then read one entry (one HBM line) per `span` k-mer positions instead of 2*h rows per
+ * position; windows containing N take the hashed path, so results are bit-identical.  Built
+ * automatically by the first count call when the filter exceeds the L2, choosing the widest span
+ * that fits min(half of the free HBM, 48 GiB) (env RB_KMER_TABLE=0 disables); dropped by
+ * rb_ibf_insert_batch*.  This call (re)builds it now under the given byte budget (0 = automatic);
+ * UINT64_MAX disables the table for this handle. */
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);
 
 /* Kernel selection override for tests/benchmarks: 0 auto, 1 warp-per-read tile kernel,

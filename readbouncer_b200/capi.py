@@ -42,7 +42,7 @@ class RBError(RuntimeError):
 class _Info(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_bins", "n_hash", "kmer_size", "n_bits", "bin_width", "n_blocks",
                                           "col_begin", "col_words", "bin_begin", "n_bins_local", "device_bytes")] + \
-               [("device", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32), ("reserved_", C.c_int32),
+               [("device", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32), ("kmer_table_span", C.c_int32),
                 ("kmer_table_bytes", C.c_uint64)]
 
 
@@ -214,7 +214,7 @@ class IBF:
         info = _Info()
         _check(lib().rb_ibf_info(self._h, C.byref(info)))
         for name, _ in _Info._fields_:
-            if name not in ("reserved_", "kmer_table_bytes"):      # the latter changes over time: see method
+            if name not in ("kmer_table_span", "kmer_table_bytes"):      # the latter changes over time: see method
                 setattr(self, name, int(getattr(info, name)))
         self.k = self.kmer_size
         self.n_local_words = self.device_bytes // 8
@@ -262,6 +262,11 @@ class IBF:
         info = _Info()
         _check(lib().rb_ibf_info(self._h, C.byref(info)))
         return int(info.kmer_table_bytes)
+
+    def kmer_table_span(self):
+        info = _Info()
+        _check(lib().rb_ibf_info(self._h, C.byref(info)))
+        return int(info.kmer_table_span)
 
     def device_words_ptr(self):
         return int(lib().rb_ibf_device_words(self._h) or 0)

@@ -43,9 +43,9 @@ struct InsertArgs {
 // which: 0 auto, 1 tile kernel, 2 streaming kernel.  Returns number of kernel launches or <0.
 int launch_count(const CountArgs &a, uint32_t max_read_len, int which, int sm_count, cudaStream_t st);
 // direct k-mer table (ibf_table.cu): build 4^k entries of 2*stride words; count through the table
-int launch_table_build(const FilterView &fv, uint64_t *table, uint64_t n_entries, int sm_count, cudaStream_t st);
-int launch_count_table(const CountArgs &a, const uint64_t *table, uint32_t max_read_len, int variant, int sm_count,
-                       cudaStream_t st);
+int launch_table_build(const FilterView &fv, uint64_t *table, uint64_t n_entries, int span, int sm_count, cudaStream_t st);
+int launch_count_table(const CountArgs &a, const uint64_t *table, int span, uint32_t max_read_len, int variant,
+                       int sm_count, cudaStream_t st);
 int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cudaStream_t st);
 int launch_keys_decode(const uint64_t *keys, uint64_t n, uint16_t *max_count, uint8_t *hit,
                        uint32_t *argmax_bin, cudaStream_t st);

@@ -32,9 +32,13 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__
             if constexpr (ROWB == 8) v[u] = __ldg(reinterpret_cast<const uint64_t *>(p));
             else if constexpr (ROWB == 16) { ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(p)); v[u] = t.x ^ t.y; }
             else {
-                ulonglong2 t0 = __ldg(reinterpret_cast<const ulonglong2 *>(p));
-                ulonglong2 t1 = __ldg(reinterpret_cast<const ulonglong2 *>(p) + 1);
-                v[u] = t0.x ^ t0.y ^ t1.x ^ t1.y;
+                uint64_t a = 0;
+#pragma unroll
+                for (int i = 0; i < ROWB / 16; ++i) {
+                    ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(p) + i);
+                    a ^= t.x ^ t.y;
+                }
+                v[u] = a;
             }
         }
 #pragma unroll
@@ -57,6 +61,8 @@ extern "C" RB_API int rb_microbench_gather(const void *d_buf, uint64_t n_rows, u
     if (row_bytes == 8) rb::gather_kernel<8><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
     else if (row_bytes == 16) rb::gather_kernel<16><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
     else if (row_bytes == 32) rb::gather_kernel<32><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
+    else if (row_bytes == 64) rb::gather_kernel<64><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
+    else if (row_bytes == 128) rb::gather_kernel<128><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
     else return RB_ERR_INVALID_ARG;
     return cudaGetLastError() == cudaSuccess ? RB_OK : RB_ERR_CUDA;
 }

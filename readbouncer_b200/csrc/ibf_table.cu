@@ -21,33 +21,38 @@ namespace rb {
 // ------------------------------------------------------------------------------------------
 // table build: one thread per k-mer value
 // ------------------------------------------------------------------------------------------
-template <int WT>
+// Entry y (a window of k+S-1 bases, 2 bits each) holds S consecutive k-mers: [t][fwd W words][rev W words].
+template <int WT, int S>
 __global__ void __launch_bounds__(256) table_build_kernel(const FilterView fv, uint64_t *__restrict__ table,
                                                           const uint64_t n_entries)
 {
     const HashParams &hp = fv.hp;
     const uint32_t k = hp.k;
-    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_entries;
-         x += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t Hf = 0, Hr = 0, pw = 1;
-        for (uint32_t j = 0; j < k; ++j) {
-            uint32_t d = (uint32_t)(x >> (2 * (k - 1 - j))) & 3u;   // j-th base of the k-mer
-            Hf = Hf * 5 + d;
-            Hr += (uint64_t)(3u - d) * pw;
-            pw *= 5;
+    const uint32_t wl = k + S - 1;                                   // window length in bases
+    for (uint64_t y = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; y < n_entries;
+         y += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t *e = table + y * (2 * WT * S);
+#pragma unroll
+        for (int t = 0; t < S; ++t) {
+            uint64_t Hf = 0, Hr = 0, pw = 1;
+            for (uint32_t j = 0; j < k; ++j) {
+                uint32_t d = (uint32_t)(y >> (2 * (wl - 1 - (t + j)))) & 3u;   // base t+j of the window
+                Hf = Hf * 5 + d;
+                Hr += (uint64_t)(3u - d) * pw;
+                pw *= 5;
+            }
+            uint64_t mf[WT], mr[WT];
+#pragma unroll
+            for (int w = 0; w < WT; ++w) { mf[w] = ~0ULL; mr[w] = ~0ULL; }
+            for (uint32_t i = 0; i < hp.n_hash; ++i) {
+                const uint64_t *pf = fv.words + hash_row(Hf, hp.pre[i], hp.n_blocks, hp.magic) * fv.stride;
+                const uint64_t *pr = fv.words + hash_row(Hr, hp.pre[i], hp.n_blocks, hp.magic) * fv.stride;
+#pragma unroll
+                for (int w = 0; w < WT; ++w) { mf[w] &= __ldg(pf + w); mr[w] &= __ldg(pr + w); }
+            }
+#pragma unroll
+            for (int w = 0; w < WT; ++w) { e[t * 2 * WT + w] = mf[w]; e[t * 2 * WT + WT + w] = mr[w]; }
         }
-        uint64_t mf[WT], mr[WT];
-#pragma unroll
-        for (int w = 0; w < WT; ++w) { mf[w] = ~0ULL; mr[w] = ~0ULL; }
-        for (uint32_t i = 0; i < hp.n_hash; ++i) {
-            const uint64_t *pf = fv.words + hash_row(Hf, hp.pre[i], hp.n_blocks, hp.magic) * fv.stride;
-            const uint64_t *pr = fv.words + hash_row(Hr, hp.pre[i], hp.n_blocks, hp.magic) * fv.stride;
-#pragma unroll
-            for (int w = 0; w < WT; ++w) { mf[w] &= __ldg(pf + w); mr[w] &= __ldg(pr + w); }
-        }
-        uint64_t *e = table + x * (2 * WT);
-#pragma unroll
-        for (int w = 0; w < WT; ++w) { e[w] = mf[w]; e[WT + w] = mr[w]; }
     }
 }
 
@@ -265,6 +270,19 @@ __device__ __forceinline__ uint32_t bs_ge(const uint32_t (&pl)[NP], uint32_t thr
     return gt | eq;
 }
 
+// max over the counters selected by `sel` (bit-sliced numbers, MSB first); `sel` shrinks to the arg-max set
+template <int NP>
+__device__ __forceinline__ uint32_t bs_max(const uint32_t (&pl)[NP], uint32_t &sel)
+{
+    uint32_t val = 0;
+#pragma unroll
+    for (int p = NP - 1; p >= 0; --p) {
+        const uint32_t t = sel & pl[p];
+        if (t) { sel = t; val |= 1u << p; }
+    }
+    return val;
+}
+
 template <int NP>
 __device__ __forceinline__ uint32_t bs_get(const uint32_t (&pl)[NP], int b)
 {
@@ -275,8 +293,8 @@ __device__ __forceinline__ uint32_t bs_get(const uint32_t (&pl)[NP], int b)
 }
 
 // WT: row words (1 or 2).  NPA: planes of the per-read accumulator (9 when every read is a single
-// chunk, else 16).
-template <int WT, int NPA>
+// chunk, else 16).  S: consecutive k-mers per table entry (window table).
+template <int WT, int NPA, int S>
 __global__ void __launch_bounds__(kTileWarps * 32)
 count_table_bs_kernel(const CountArgs a, const uint64_t *__restrict__ table)
 {
@@ -288,7 +306,8 @@ count_table_bs_kernel(const CountArgs a, const uint64_t *__restrict__ table)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t total_warps = (uint64_t)gridDim.x * kTileWarps;
     const uint32_t k = a.fv.hp.k;
-    const uint64_t kmask = (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    const uint32_t wl = k + S - 1;                                   // bases per table window
+    const uint64_t wmask = (wl >= 32) ? ~0ULL : ((1ULL << (2 * wl)) - 1);
     uint8_t *dig = s_dig[warp];
     // bins this lane reports: strand = q & 1, 32-bit word ww = q >> 1 of that strand
     const int q = lane / LPW;
@@ -321,27 +340,51 @@ count_table_bs_kernel(const CountArgs a, const uint64_t *__restrict__ table)
 #pragma unroll
                     for (int w = 0; w < NWP; ++w) pl[p][w] = 0;
                 if (j0 < j1) {
+                    // window of wl bases starting at j; bases past the end of the chunk read as 'A' (their
+                    // k-mers are never consumed) -- the digit buffer is zero-padded below
+                    const uint32_t nd = cn + k - 1;                  // valid digits in the chunk buffer
                     uint64_t x = 0;
                     uint32_t nbad = 0;
-                    for (uint32_t u = 0; u < k; ++u) {
-                        uint32_t d = dig[j0 + u];
+                    for (uint32_t u = 0; u < wl; ++u) {
+                        uint32_t d = (j0 + u < nd) ? dig[j0 + u] : 0u;
                         x = (x << 2) | (d & 3u);
                         nbad += d >> 2;
                     }
-                    x &= kmask;
+                    x &= wmask;
                     for (uint32_t j = j0; j < j1; j += 4) {
                         uint64_t mf[4][WT], mr[4][WT];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int g = 0; g < 4 / S; ++g) {
+                            const uint32_t jg = j + g * S;
 #pragma unroll
-                            for (int w = 0; w < WT; ++w) { mf[u][w] = 0; mr[u][w] = 0; }
-                            if (j + u < j1) {
-                                if (nbad == 0) load_entry<WT>(table + x * (2 * WT), mf[u], mr[u]);
-                                else probe_hashed<WT>(a.fv, dig, j + u, mf[u], mr[u]);
-                                if (j + u + 1 < j1) {
-                                    uint32_t dout = dig[j + u], din = dig[j + u + k];
-                                    x = ((x << 2) | (din & 3u)) & kmask;
-                                    nbad += (din >> 2) - (dout >> 2);
+                            for (int t = 0; t < S; ++t)
+#pragma unroll
+                                for (int w = 0; w < WT; ++w) { mf[g * S + t][w] = 0; mr[g * S + t][w] = 0; }
+                            if (jg < j1) {
+                                if (nbad == 0) {
+                                    const uint64_t *e = table + x * (2 * WT * S);
+#pragma unroll
+                                    for (int t = 0; t < S; ++t) {
+                                        uint64_t f[WT], r[WT];
+                                        load_entry<WT>(e + t * 2 * WT, f, r);
+                                        if (jg + t < j1) {
+#pragma unroll
+                                            for (int w = 0; w < WT; ++w) { mf[g * S + t][w] = f[w]; mr[g * S + t][w] = r[w]; }
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int t = 0; t < S; ++t)
+                                        if (jg + t < j1) probe_hashed<WT>(a.fv, dig, jg + t, mf[g * S + t], mr[g * S + t]);
+                                }
+                                if (jg + S < j1) {                   // slide the window by S bases
+#pragma unroll
+                                    for (int t = 0; t < S; ++t) {
+                                        const uint32_t dout = dig[jg + t];
+                                        const uint32_t din = (jg + t + wl < nd) ? dig[jg + t + wl] : 0u;
+                                        x = ((x << 2) | (din & 3u)) & wmask;
+                                        nbad += (din >> 2) - (dout >> 2);
+                                    }
                                 }
                             }
                         }
@@ -399,13 +442,15 @@ count_table_bs_kernel(const CountArgs a, const uint64_t *__restrict__ table)
             best[t] = 0;
             if (t < (int)a.n_lut && flag == 0) {
                 const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)t * kLutSize + len);
-                uint32_t pass = (bs_ge<NPA>(acc, thr) | bs_ge<NPA>(oth, thr)) & valid;
-                while (pass) {
-                    const int b = __ffs((int)pass) - 1;
-                    pass &= pass - 1;
-                    const uint32_t m = max(bs_get<NPA>(acc, b), bs_get<NPA>(oth, b));
-                    const uint64_t key = pack_key(m, (uint32_t)(a.fv.bin_begin + bin0 + b));
-                    best[t] = key > best[t] ? key : best[t];
+                const uint32_t pass = (bs_ge<NPA>(acc, thr) | bs_ge<NPA>(oth, thr)) & valid;
+                if (pass) {
+                    // max_matches over the passing bins without a per-bin loop: bit-sliced max of each strand,
+                    // then the lowest bin among those attaining the larger one
+                    uint32_t s1 = pass, s2 = pass;
+                    const uint32_t m1 = bs_max<NPA>(acc, s1), m2 = bs_max<NPA>(oth, s2);
+                    const uint32_t m = max(m1, m2);
+                    const uint32_t at = (m1 == m ? s1 : 0u) | (m2 == m ? s2 : 0u);
+                    best[t] = pack_key(m, (uint32_t)(a.fv.bin_begin + bin0 + (__ffs((int)at) - 1)));
                 }
             }
         }
@@ -422,21 +467,28 @@ count_table_bs_kernel(const CountArgs a, const uint64_t *__restrict__ table)
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-template <int WT>
+template <int WT, int S>
 static void launch_build_wt(const FilterView &fv, uint64_t *table, uint64_t n_entries, int sm_count, cudaStream_t st)
 {
     uint64_t blocks = (n_entries + 255) / 256;
     uint64_t cap = (uint64_t)sm_count * 32;
-    table_build_kernel<WT><<<(uint32_t)(blocks < cap ? blocks : cap), 256, 0, st>>>(fv, table, n_entries);
+    table_build_kernel<WT, S><<<(uint32_t)(blocks < cap ? blocks : cap), 256, 0, st>>>(fv, table, n_entries);
 }
 
-int launch_table_build(const FilterView &fv, uint64_t *table, uint64_t n_entries, int sm_count, cudaStream_t st)
+// span = k-mers per entry (1 or 2); n_entries = 4^(k + span - 1)
+int launch_table_build(const FilterView &fv, uint64_t *table, uint64_t n_entries, int span, int sm_count, cudaStream_t st)
 {
+    if (span == 2 && fv.stride <= 2) {
+        if (fv.stride == 1) launch_build_wt<1, 2>(fv, table, n_entries, sm_count, st);
+        else launch_build_wt<2, 2>(fv, table, n_entries, sm_count, st);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+    if (span != 1) return -1;
     switch (fv.stride) {
-    case 1: launch_build_wt<1>(fv, table, n_entries, sm_count, st); break;
-    case 2: launch_build_wt<2>(fv, table, n_entries, sm_count, st); break;
-    case 3: launch_build_wt<3>(fv, table, n_entries, sm_count, st); break;
-    case 4: launch_build_wt<4>(fv, table, n_entries, sm_count, st); break;
+    case 1: launch_build_wt<1, 1>(fv, table, n_entries, sm_count, st); break;
+    case 2: launch_build_wt<2, 1>(fv, table, n_entries, sm_count, st); break;
+    case 3: launch_build_wt<3, 1>(fv, table, n_entries, sm_count, st); break;
+    case 4: launch_build_wt<4, 1>(fv, table, n_entries, sm_count, st); break;
     default: return -1;
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -457,33 +509,47 @@ static void launch_table_wt(const CountArgs &a, const uint64_t *table, int sm_co
     count_table_kernel<WT, U><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }
 
-template <int WT, int NPA>
+template <int WT, int NPA, int S>
 static void launch_table_bs(const CountArgs &a, const uint64_t *table, int sm_count, cudaStream_t st)
 {
     static int occ = 0;
     if (occ == 0) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, count_table_bs_kernel<WT, NPA>, kTileWarps * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, count_table_bs_kernel<WT, NPA, S>, kTileWarps * 32, 0);
         occ = o > 0 ? o : 1;
     }
     uint64_t blocks_needed = (a.n_reads + kTileWarps - 1) / kTileWarps;
     uint64_t max_x = (uint64_t)sm_count * occ;
     uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
-    count_table_bs_kernel<WT, NPA><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
+    count_table_bs_kernel<WT, NPA, S><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }
 
-int launch_count_table(const CountArgs &a, const uint64_t *table, uint32_t max_read_len, int variant, int sm_count,
-                       cudaStream_t st)
+template <int WT, int S>
+static void launch_table_bs_np(const CountArgs &a, const uint64_t *table, bool single_chunk, int sm_count, cudaStream_t st)
+{
+    if (single_chunk) launch_table_bs<WT, 9, S>(a, table, sm_count, st);
+    else launch_table_bs<WT, 16, S>(a, table, sm_count, st);
+}
+
+// span: k-mers per table entry.  variant 0: bit-sliced register counters (rows <= 2 words);
+// 1: shared-memory atomic counters (span 1 only).
+int launch_count_table(const CountArgs &a, const uint64_t *table, int span, uint32_t max_read_len, int variant,
+                       int sm_count, cudaStream_t st)
 {
     if (a.n_reads == 0) return 0;
     if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut) return -1;
-    // variant 0: bit-sliced register counters (rows <= 2 words); 1: shared-memory atomic counters
-    if (variant == 0 && a.fv.stride <= 2) {
+    if ((variant == 0 || span == 2) && a.fv.stride <= 2) {
         const bool single_chunk = max_read_len != 0 && max_read_len < a.fv.hp.k + (uint32_t)kBsChunk;
-        if (a.fv.stride == 1) { if (single_chunk) launch_table_bs<1, 9>(a, table, sm_count, st); else launch_table_bs<1, 16>(a, table, sm_count, st); }
-        else { if (single_chunk) launch_table_bs<2, 9>(a, table, sm_count, st); else launch_table_bs<2, 16>(a, table, sm_count, st); }
+        if (a.fv.stride == 1) {
+            if (span == 2) launch_table_bs_np<1, 2>(a, table, single_chunk, sm_count, st);
+            else launch_table_bs_np<1, 1>(a, table, single_chunk, sm_count, st);
+        } else {
+            if (span == 2) launch_table_bs_np<2, 2>(a, table, single_chunk, sm_count, st);
+            else launch_table_bs_np<2, 1>(a, table, single_chunk, sm_count, st);
+        }
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
+    if (span != 1) return -1;
     switch (a.fv.stride) {
     case 1: launch_table_wt<1, 2>(a, table, sm_count, st); break;
     case 2: launch_table_wt<2, 2>(a, table, sm_count, st); break;

@@ -64,6 +64,7 @@ struct rb_ibf {
     mutable std::mutex table_mu;
     mutable uint64_t *d_table = nullptr;
     mutable uint64_t table_entries = 0;
+    mutable int table_span = 0;             // k-mers per entry (1 or 2)
     mutable bool table_tried = false;
     mutable uint64_t table_budget = 0;      // 0 = automatic
 };
@@ -234,10 +235,13 @@ rb::FilterView view_of(const rb_ibf *f)
 // ---- direct k-mer table policy -----------------------------------------------------------------
 constexpr uint64_t kTableMinFilterBytes = 64ull << 20;   // smaller filters live in L2: direct probes are as cheap
 
-uint64_t table_bytes_needed(const rb_ibf *f)
+// span = consecutive k-mers per entry: entry y is a (k+span-1)-base window, 2*span*col_words words
+uint64_t table_bytes_needed(const rb_ibf *f, int span)
 {
-    if (f->col_words == 0 || f->col_words > 4 || f->k > 16) return 0;
-    return (1ull << (2 * f->k)) * 2 * f->col_words * 8;
+    if (f->col_words == 0 || f->k + span - 1 > 16) return 0;
+    if (span == 1 && f->col_words > 4) return 0;
+    if (span == 2 && f->col_words > 2) return 0;
+    return (1ull << (2 * (f->k + span - 1))) * 2 * span * f->col_words * 8;
 }
 
 // Builds the table on `st` if the policy allows it; returns the device pointer or null.
@@ -250,22 +254,32 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force)
     f->table_tried = true;
     const char *env = std::getenv("RB_KMER_TABLE");
     if (!force && env && env[0] == '0') return nullptr;
-    const uint64_t need = table_bytes_needed(f);
-    if (need == 0) return nullptr;
     if (!force && f->n_local_words * 8 < kTableMinFilterBytes) return nullptr;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>(free_b / 2, 48ull << 30);
-    if (need > budget || need > free_b) return nullptr;
+    const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>(free_b / 2, 48ull << 30);
+    // Measured on B200 (profiles/r1_gather_sweep2.jsonl): random gathers are bound by ~42 G L2-missing
+    // 32-byte SECTOR requests/s, so a window entry only pays when two k-mer positions share one sector,
+    // i.e. for one-word rows (16 B per position).  RB_KMER_TABLE_SPAN overrides for experiments.
+    int max_span = f->col_words == 1 ? 2 : 1;
+    if (const char *sp_env = std::getenv("RB_KMER_TABLE_SPAN")) max_span = std::atoi(sp_env) >= 2 ? 2 : 1;
+    int span = 0;
+    uint64_t need = 0;
+    for (int sp = max_span; sp >= 1 && !span; --sp) {   // the widest useful window that fits the budget
+        const uint64_t b = table_bytes_needed(f, sp);
+        if (b && b <= budget && b <= free_b) { span = sp; need = b; }
+    }
+    if (!span) return nullptr;
     uint64_t *t = nullptr;
     if (cudaMalloc(&t, need) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    const uint64_t entries = 1ull << (2 * f->k);
-    int n = rb::launch_table_build(view_of(f), t, entries, f->sm_count, st);
+    const uint64_t entries = 1ull << (2 * (f->k + span - 1));
+    int n = rb::launch_table_build(view_of(f), t, entries, span, f->sm_count, st);
     // other host threads may use the table from their own streams right away: finish the build first
     if (n < 0 || cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(t); cudaGetLastError(); return nullptr; }
     g_launches += (uint64_t)n;
     f->d_table = t;
     f->table_entries = entries;
+    f->table_span = span;
     return t;
 }
 
@@ -275,6 +289,7 @@ void drop_table(rb_ibf *f)
     if (f->d_table) { cudaDeviceSynchronize(); cudaFree(f->d_table); }
     f->d_table = nullptr;
     f->table_entries = 0;
+    f->table_span = 0;
     f->table_tried = false;
 }
 
@@ -633,7 +648,8 @@ int rb_ibf_info(const rb_ibf *f, rb_ibf_info_t *out)
     out->device_bytes = f->n_local_words * 8; out->device = f->device; out->shard = f->shard; out->n_shards = f->n_shards;
     {
         std::lock_guard<std::mutex> lock(f->table_mu);
-        out->kmer_table_bytes = f->d_table ? f->table_entries * 2 * f->col_words * 8 : 0;
+        out->kmer_table_bytes = f->d_table ? f->table_entries * 2 * f->table_span * f->col_words * 8 : 0;
+        out->kmer_table_span = f->d_table ? f->table_span : 0;
     }
     return RB_OK;
 }
@@ -643,6 +659,7 @@ int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stre
     if (!f) return fail(RB_ERR_NULL_FILTER, "null filter");
     DeviceGuard g(f->device);
     if (max_table_bytes == UINT64_MAX) { drop_table(f); f->table_tried = true; return RB_OK; }   // disable
+    drop_table(f);
     f->table_budget = max_table_bytes;
     if (!ensure_table(f, (cudaStream_t)stream, true))
         return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable (row > 4 words, k > 16) or over the memory budget");
@@ -725,7 +742,7 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3);
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
     if (table) {
-        int n = rb::launch_count_table(a, table, max_read_len, which == 4 ? 1 : 0, f->sm_count, (cudaStream_t)stream);
+        int n = rb::launch_count_table(a, table, f->table_span, max_read_len, which == 4 ? 1 : 0, f->sm_count, (cudaStream_t)stream);
         if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         g_launches += (uint64_t)n;
         return RB_OK;

@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path, called through the C ABI (ctypes -> librb_ibf.so), against
 the CPU oracle on the same inputs and against the reference's golden fixtures.  Bit-exact."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -136,17 +137,28 @@ RAGGED = [250] * 40 + [0, 1, 12, 13, 14, 31, 32, 33, 64, 100, 249, 251, 360, 500
 def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
     rb.set_count_kernel(KERNELS[kernel])
     plan, of, gf = make_filter_pair(n_seqs, seq_len, frag, k)
-    if kernel.startswith("table"):
-        if gf.bin_width > 4:
-            with pytest.raises(rb.RBError):
-                gf.count_batch(np.frombuffer(b"ACGTACGTACGTACGTACGT", np.uint8), np.array([0, 20], np.uint64),
-                               rb.threshold_lut(0.1, k))
-            return
-        gf.enable_kmer_table()
-        assert gf.kmer_table_bytes() == 4 ** k * 16 * gf.bin_width
     assert np.array_equal(gf.download(), of.words()[:plan["n_bits"] // 64])
     bases, off = synth.ragged_reads(plan["bases"], RAGGED, seed=7, frac_from_ref=0.7, n_frac=0.003, lower_frac=0.1)
     lut = rb.threshold_lut(0.1, k)
+    if kernel.startswith("table"):
+        if gf.bin_width > 4:
+            with pytest.raises(rb.RBError):
+                gf.count_batch(np.frombuffer(b"ACGTACGTACGTACGTACGT", np.uint8), np.array([0, 20], np.uint64), lut)
+            return
+        exp = of.count_batch(bases, off, lut, n_threads=4)
+        span1 = 4 ** k * 16 * gf.bin_width
+        gf.enable_kmer_table(span1)                      # budget admits only one k-mer per entry
+        assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (span1, 1)
+        assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+        if gf.bin_width <= 2 and kernel == "table":      # window table: two consecutive k-mers per entry
+            os.environ["RB_KMER_TABLE_SPAN"] = "2"
+            try:
+                gf.enable_kmer_table(0)
+            finally:
+                del os.environ["RB_KMER_TABLE_SPAN"]
+            assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (4 ** (k + 1) * 32 * gf.bin_width, 2)
+            assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+        return
     assert np.array_equal(lut, oracle.threshold_lut(0.1, k))
     got = gf.count_batch(bases, off, lut, dense=True)
     exp = of.count_batch(bases, off, lut, n_threads=4)
@@ -163,10 +175,15 @@ def test_kmer_table_handles_n_rich_reads_and_is_dropped_by_insert():
     bases[int(off[5])] = ord("U")                               # U counts as T
     lut = rb.threshold_lut(0.1, 13)
     exp = of.count_batch(bases, off, lut, n_threads=4)
-    for which in (3, 4):
+    for which, span in ((3, 2), (3, 1), (4, 1)):
         rb.set_count_kernel(which)
+        os.environ["RB_KMER_TABLE_SPAN"] = str(span)
+        try:
+            gf.enable_kmer_table(0)
+        finally:
+            del os.environ["RB_KMER_TABLE_SPAN"]
+        assert gf.kmer_table_span() == span
         assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
-    assert gf.kmer_table_bytes() > 0
     rb.set_count_kernel(0)
     # insert one more fragment into bin 0: table must be rebuilt, results must follow the new matrix
     extra = synth.random_bases(5000, 999)
@@ -289,7 +306,7 @@ def test_config2_full_size_properties():
     for key in ("max_count", "hit", "argmax_bin"):
         assert np.array_equal(res[key], res_rc[key])
     # (2) all three kernels agree on the whole batch (auto = direct k-mer table at this size)
-    assert gf.kmer_table_bytes() == 4 ** 13 * 32
+    assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (4 ** 13 * 32, 1)
     for which in (1, 2, 4):
         rb.set_count_kernel(which)
         res_s = gf.count_batch(bases, off, lut)
