@@ -332,13 +332,16 @@ def run_ours(args, w, n_reads):
     lookups, bytes_per_chunk = algorithmic_bytes_per_chunk(w, gf.col_words)
     peak, peak_src = measured_peaks()
     achieved = n_reads * bytes_per_chunk / (kernel_ms * 1e-3) / 1e9
+    kernel_name = ("count_table_kernel" if gf.kmer_table_bytes() else
+                   "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
+    if os.path.exists(tp):          # measured once under ncu --set full for this workload and kernel
+        ent = json.load(open(tp)).get(args.workload, {})
+        if ent.get("kernel") == kernel_name and ent.get("chunks_per_launch") == n_reads and world == 1:
+            traffic = ent.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": ("count_table_kernel" if gf.kmer_table_bytes() else
-                           "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel"),
+                "traffic": traffic, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_chunk": bytes_per_chunk, "peak_source": peak_src,
                 "kmer_lookups_per_s": (n_reads if bin_sharded else world * n_reads) * lookups / (total_ms * 1e-3 / args.steps)}
     # random-sector ceiling for narrow rows (<= 32 B): measured gather microbenchmark over the same matrix

@@ -186,8 +186,8 @@ RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_ma
  * (2.1 GB for k=13, 100 bins), span 2 = 4^(k+1) * 32 * col_words bytes (17 GB; rows <= 2 words).
  * Count calls then read one entry (one HBM line) per `span` k-mer positions instead of 2*h rows per
  * position; windows containing N take the hashed path, so results are bit-identical.  Built
- * automatically by the first count call when the filter exceeds the L2, choosing the widest span
- * that fits min(half of the free HBM, 48 GiB) (env RB_KMER_TABLE=0 disables); dropped by
+ * automatically by the first count call with >= 1024 reads, choosing the widest useful span that
+ * fits min(half of the free HBM, 48 GiB) (env RB_KMER_TABLE=0 disables); dropped by
  * rb_ibf_insert_batch*.  This call (re)builds it now under the given byte budget (0 = automatic);
  * UINT64_MAX disables the table for this handle. */
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);

@@ -233,7 +233,7 @@ rb::FilterView view_of(const rb_ibf *f)
 }
 
 // ---- direct k-mer table policy -----------------------------------------------------------------
-constexpr uint64_t kTableMinFilterBytes = 64ull << 20;   // smaller filters live in L2: direct probes are as cheap
+constexpr uint64_t kTableMinReads = 1024;   // batches smaller than this never trigger the (GB-sized) table build
 
 // span = consecutive k-mers per entry: entry y is a (k+span-1)-base window, 2*span*col_words words
 uint64_t table_bytes_needed(const rb_ibf *f, int span)
@@ -246,15 +246,15 @@ uint64_t table_bytes_needed(const rb_ibf *f, int span)
 
 // Builds the table on `st` if the policy allows it; returns the device pointer or null.
 // force: ignore the "filter fits L2" heuristic (tests, explicit rb_ibf_enable_kmer_table).
-const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force)
+const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint64_t n_reads = ~0ull)
 {
     std::lock_guard<std::mutex> lock(f->table_mu);
     if (f->d_table) return f->d_table;
     if (f->table_tried && !force) return nullptr;
+    if (!force && n_reads < kTableMinReads) return nullptr;     // not "tried": a later large batch builds it
     f->table_tried = true;
     const char *env = std::getenv("RB_KMER_TABLE");
     if (!force && env && env[0] == '0') return nullptr;
-    if (!force && f->n_local_words * 8 < kTableMinFilterBytes) return nullptr;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>(free_b / 2, 48ull << 30);
@@ -739,7 +739,7 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     a.keys = d_keys; a.counts_fwd = d_counts_fwd; a.counts_rev = d_counts_rev; a.read_flag = d_read_flag;
     const int which = g_count_kernel.load();
     const uint64_t *table = nullptr;
-    if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3);
+    if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3, n_reads);
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
     if (table) {
         int n = rb::launch_count_table(a, table, f->table_span, max_read_len, which == 4 ? 1 : 0, f->sm_count, (cudaStream_t)stream);

@@ -288,6 +288,37 @@ def test_insert_is_idempotent_and_order_free():
     assert np.array_equal(gf.download(), before)
 
 
+# ---- BASELINE config #1: usage=classify on testData/testQueries.fasta vs an IBF of a synthetic 5 Mb reference ---
+def test_config1_testqueries_vs_5mb_reference():
+    ref = [synth.random_bases(5_000_001, 1)]                     # 5 000 000 after the N-cut quirk -> 51 bins
+    plan = synth.build_plan(ref, 100000, 13)
+    assert plan["n_bins"] == 51 and plan["n_bits"] == 79121216 and plan["bin_ids_consumed"] == 51
+    gf = rb.IBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    gf.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+    of = oracle.OracleIBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    of.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"], n_threads=8)
+    assert np.array_equal(gf.download(), of.words()[:plan["n_bits"] // 64])
+    name, query = read_fasta(data_path("testQueries.fasta"))[0]
+    assert name == "1" and len(query) == 1890
+    # the chunk schedule of classify_reads (classify.hpp:262-299): max_chunks=5 chunks of 250, plus
+    # reference-derived chunks so that the batch has hits, plus 10 000 synthetic chunks
+    chunks = [query[i * 250:(i + 1) * 250] for i in range(5)]
+    syn_b, syn_o, _ = synth.sample_reads(plan["bases"], 10000, 250, seed=1234)
+    bases = np.concatenate([np.frombuffer(b"".join(chunks), np.uint8), syn_b])
+    off = np.concatenate([np.arange(6, dtype=np.uint64) * np.uint64(250), syn_o[1:] + np.uint64(1250)])
+    luts = np.stack([rb.threshold_lut(0.1, 13), rb.threshold_lut(0.08, 13)])
+    for which in (1, 2, 3):
+        rb.set_count_kernel(which)
+        got = gf.count_batch(bases, off, luts, dense=True)
+        for t in range(2):
+            exp = of.count_batch(bases, off, luts[t], n_threads=8)
+            assert np.array_equal(got["counts_fwd"], exp["counts_fwd"]) and np.array_equal(got["counts_rev"], exp["counts_rev"])
+            for key in ("max_count", "hit", "argmax_bin"):
+                assert np.array_equal(got[key][t], exp[key]), (which, t, key)
+    assert got["hit"][0][:5].sum() == 0                          # the human-like query does not match a random reference
+    assert 0.45 < got["hit"][0][5:].mean() < 0.55                # half of the synthetic chunks come from the reference
+
+
 # ---- BASELINE config #2 at full size: size-independent properties + sampled oracle check ----------------
 def test_config2_full_size_properties():
     ref = [synth.random_bases(4_000_000, 2 + i) for i in range(100)]
