@@ -53,8 +53,12 @@ def lib_path():
 def build_library(force=False):
     """Compile librb_ibf.so in-tree with nvcc for sm_100a (see csrc/Makefile)."""
     srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", "Makefile"))]
-    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "rb_ibf.h"))
-    stale = not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+    root = os.path.dirname(_HERE)
+    srcs += [os.path.join(root, "include", f) for f in ("rb_ibf.h", "rb_interleave.hpp", "rb_drivers.hpp")]
+    srcs.append(os.path.join(root, "tools", "rb_readbouncer.cpp"))
+    exe = os.path.join(_HERE, "bin", "rb_readbouncer")
+    stale = (not os.path.exists(_LIB) or not os.path.exists(exe)
+             or any(os.path.getmtime(s) > min(os.path.getmtime(_LIB), os.path.getmtime(exe)) for s in srcs))
     if force or stale:
         cmd = ["make", "-C", _CSRC, "-j4"] + (["-B"] if force else [])
         subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
