@@ -124,5 +124,6 @@ def test_live_microbatches_equal_serial_loop(tmp_path, mode):
     assert got == expected
     assert got_pending == pending
     kinds = {a for _, a, _, _ in got}
-    assert any(g for _, _, g, _ in got)               # some reads were given up on after > 1500 bases
+    if mode != "target":                               # target-only never keeps going: no hit means unblock
+        assert any(g for _, _, g, _ in got)           # some reads were given up on after > 1500 bases
     assert (1 in kinds or mode == "target") and (2 in kinds or mode == "deplete")
