@@ -127,6 +127,11 @@ RB_API int rb_ibf_info(const rb_ibf *f, rb_ibf_info_t *out);
 /* Raw device pointer of the bit matrix (for zero-copy interop, e.g. torch.from_blob) */
 RB_API uint64_t *rb_ibf_device_words(const rb_ibf *f);
 
+/* filter.resizeBins(n) as used by IBF::update_filter (src/IBF/IBFBuild.cpp:269-279): grow the bin count; the
+ * number of rows is kept and rows are widened when n crosses a multiple of 64 (n_bits = rows * 64 * ceil(n/64)).
+ * Unsharded handles only.  (SeqAn's resizeBins is not pinned by any reference fixture.) */
+RB_API int rb_ibf_resize_bins(rb_ibf *f, uint64_t new_n_bins, rb_stream stream);
+
 /* ---- build: seqan::insertKmer(filter, fragment, bin), src/IBF/IBFBuild.cpp:189-190 ---- */
 /* For every fragment i: every k-mer of bases[frag_begin[i] .. frag_end[i]) sets bit
  * (row(h_j(kmer)), frag_bin[i]) for all hash functions j.  Fragments shorter than k

@@ -144,6 +144,15 @@ public:
             noOfBits = info.n_bits;
         }
     }
+    // re-read the metadata of the same handle (after resizeBins)
+    void refresh()
+    {
+        rb_ibf_info_t info{};
+        if (handle_ && rb_ibf_info(handle_.get(), &info) == RB_OK) {
+            noOfBins = info.n_bins; kmerSize = (uint16_t)info.kmer_size; noOfHashFunc = (uint16_t)info.n_hash;
+            noOfBits = info.n_bits;
+        }
+    }
     rb_ibf *get() const { return handle_.get(); }
     explicit operator bool() const { return (bool)handle_; }
     uint64_t noOfBins = 0;
@@ -219,31 +228,8 @@ public:
     FilterStats create_filter(IBFConfig &config)
     {
         if (!config.validate()) throw InvalidConfigException("Config not valid!");
-        if (config.reference_files.empty()) throw MissingReferenceFilesException("There were no reference files specified!");
-        if (config.fragment_length < config.kmer_size) throw InvalidConfigException("fragment_length must be >= kmer_size");
         FilterStats stats;
-        std::string bases;
-        std::vector<uint64_t> fb, fe, fbin;
-        uint64_t binid = 0;
-        for (const std::string &file : config.reference_files) {
-            for (SeqRecord &rec : read_sequence_file(file)) {
-                stats.totalSeqsFile += 1;
-                if (rec.seq.size() < config.kmer_size) { stats.invalidSeqs += 1; continue; }   // IBFBuild.cpp:70-74
-                std::string cut(rec.seq.size(), '\0');
-                cut.resize(rb_cut_out_nnns(rec.seq.data(), rec.seq.size(), cut.data()));
-                stats.totalBinsBinId += (uint32_t)(cut.size() / config.fragment_length + 1);          // IBFBuild.cpp:90
-                stats.sumSeqLen += cut.size();
-                const uint64_t n = rb_fragment_schedule(cut.size(), config.fragment_length, config.kmer_size, nullptr, nullptr, 0);
-                std::vector<uint64_t> b(n), e(n);
-                rb_fragment_schedule(cut.size(), config.fragment_length, config.kmer_size, b.data(), e.data(), n);
-                for (uint64_t i = 0; i < n; ++i) {
-                    fb.push_back(bases.size() + b[i]);
-                    fe.push_back(bases.size() + e[i]);
-                    fbin.push_back(binid++);
-                }
-                bases += cut;
-            }
-        }
+        FragmentPlan plan = parse_ref_seqs(config, stats, 0);
         if (stats.totalBinsBinId == 0) throw NullFilterException("Could not instantiate IBF Filter");
         config.filter_size_bits = rb_ibf_size_bits(config.fragment_length, config.kmer_size, config.hash_functions,
                                                    config.max_fp, stats.totalBinsBinId);
@@ -256,12 +242,34 @@ public:
         }
         filter = TIbf(h);
         stats.totalBinsFile = (uint32_t)filter.noOfBins;
-        st = rb_ibf_insert_batch(h, bases.data(), bases.size(), fb.data(), fe.data(), fbin.data(), fb.size(), nullptr);
-        if (st != RB_OK) throw_status(st, "Error inserting the sequences to the IBF");
+        add_sequences_to_filter(plan);
         if (!config.output_filter_file.empty()) {
             st = rb_ibf_store(h, config.output_filter_file.c_str());
             if (st != RB_OK) throw_status(st, "Could not store IBF to " + config.output_filter_file);
         }
+        return stats;
+    }
+
+    // update_filter, src/IBF/IBFBuild.cpp:223-321: load update_filter_file, append the bins of the new
+    // references (resizeBins), insert their fragments from bin id = old bin count, store back.
+    FilterStats update_filter(IBFConfig &config)
+    {
+        if (!config.validate()) throw InvalidConfigException("Config not valid!");
+        if (config.update_filter_file.empty())
+            throw MissingIBFFileException("Error: Either update_filter_file or input_filter_file have to be specified.");
+        FilterStats stats = load_filter(config);                 // sets config.kmer_size from the file
+        FragmentPlan plan = parse_ref_seqs(config, stats, stats.totalBinsFile);
+        const uint32_t number_new_bins = stats.totalBinsBinId + stats.totalBinsFile;
+        if (number_new_bins > stats.totalBinsFile) {
+            int st = rb_ibf_resize_bins(filter.get(), number_new_bins, nullptr);
+            if (st != RB_OK) throw_status(st, "resizeBins");
+            filter.refresh();                                    // noOfBins / noOfBits changed
+            stats.newBins = stats.totalBinsBinId;
+            stats.totalBinsBinId = number_new_bins;
+        }
+        add_sequences_to_filter(plan);
+        int st = rb_ibf_store(filter.get(), config.update_filter_file.c_str());
+        if (st != RB_OK) throw_status(st, "Could not store IBF to " + config.update_filter_file);
         return stats;
     }
 
@@ -289,6 +297,47 @@ public:
     TIbf getFilter() { return filter; }
 
 private:
+    struct FragmentPlan {
+        std::string bases;
+        std::vector<uint64_t> begin, end, bin;
+    };
+
+    // parse_ref_seqs + the fragment loop of add_sequences_to_filter (src/IBF/IBFBuild.cpp:16-104,165-202)
+    FragmentPlan parse_ref_seqs(IBFConfig &config, FilterStats &stats, uint64_t first_bin)
+    {
+        if (config.reference_files.empty()) throw MissingReferenceFilesException("There were no reference files specified!");
+        if (config.fragment_length < config.kmer_size) throw InvalidConfigException("fragment_length must be >= kmer_size");
+        FragmentPlan plan;
+        uint64_t binid = first_bin;
+        for (const std::string &file : config.reference_files) {
+            for (SeqRecord &rec : read_sequence_file(file)) {
+                stats.totalSeqsFile += 1;
+                if (rec.seq.size() < config.kmer_size) { stats.invalidSeqs += 1; continue; }   // IBFBuild.cpp:70-74
+                std::string cut(rec.seq.size(), '\0');
+                cut.resize(rb_cut_out_nnns(rec.seq.data(), rec.seq.size(), cut.data()));
+                stats.totalBinsBinId += (uint32_t)(cut.size() / config.fragment_length + 1);          // IBFBuild.cpp:90
+                stats.sumSeqLen += cut.size();
+                const uint64_t n = rb_fragment_schedule(cut.size(), config.fragment_length, config.kmer_size, nullptr, nullptr, 0);
+                std::vector<uint64_t> b(n), e(n);
+                rb_fragment_schedule(cut.size(), config.fragment_length, config.kmer_size, b.data(), e.data(), n);
+                for (uint64_t i = 0; i < n; ++i) {
+                    plan.begin.push_back(plan.bases.size() + b[i]);
+                    plan.end.push_back(plan.bases.size() + e[i]);
+                    plan.bin.push_back(binid++);
+                }
+                plan.bases += cut;
+            }
+        }
+        return plan;
+    }
+
+    void add_sequences_to_filter(const FragmentPlan &plan)
+    {
+        int st = rb_ibf_insert_batch(filter.get(), plan.bases.data(), plan.bases.size(), plan.begin.data(), plan.end.data(),
+                                     plan.bin.data(), plan.begin.size(), nullptr);
+        if (st != RB_OK) throw_status(st, "Error inserting the sequences to the IBF");
+    }
+
     TIbf filter{};
 };
 

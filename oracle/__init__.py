@@ -45,6 +45,7 @@ def lib():
         "orc_ibf_load": (vp, [C.c_char_p, C.POINTER(C.c_int)]),
         "orc_ibf_store": (C.c_int, [vp, C.c_char_p]),
         "orc_ibf_free": (None, [vp]),
+        "orc_ibf_resize_bins": (C.c_int, [vp, C.c_uint64]),
         "orc_ibf_words": (u64p, [vp]),
         "orc_ibf_info": (None, [vp, u64p, u64p, u64p, u64p, u64p]),
         "orc_kmer_hash": (C.c_uint64, [C.c_char_p, C.c_uint64]),
@@ -130,6 +131,12 @@ class OracleIBF:
         st = lib().orc_ibf_store(self._h, _b(str(path)))
         if st:
             raise OracleError(st)
+
+    def resize_bins(self, new_n_bins):
+        st = lib().orc_ibf_resize_bins(self._h, new_n_bins)
+        if st:
+            raise OracleError(st)
+        self.__init__(self._h)
 
     def words(self):
         """numpy view (no copy) of all words including the 4-word metadata tail."""

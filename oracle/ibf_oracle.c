@@ -123,6 +123,32 @@ int orc_ibf_store(const orc_ibf *f, const char *path)
     return ok ? ORC_OK : ORC_ERR_STORE;
 }
 
+/* filter.resizeBins(n) -- src/IBF/IBFBuild.cpp:274.  SeqAn keeps noOfBlocks and widens every row when
+ * ceil(n/64) grows; bit (row, bin) keeps its coordinates.  UNPINNED: no reference fixture exercises it. */
+int orc_ibf_resize_bins(orc_ibf *f, uint64_t new_n_bins)
+{
+    if (!f) return ORC_ERR_NULL_FILTER;
+    if (new_n_bins < f->n_bins) return ORC_ERR_CONFIG;
+    uint64_t new_width = (new_n_bins + 63) / 64;
+    if (new_width != f->bin_width) {
+        uint64_t n_bits = f->n_blocks * new_width * 64;
+        uint64_t n_words = (n_bits + 256 + 63) / 64;
+        uint64_t *w = (uint64_t *)calloc(n_words, sizeof(uint64_t));
+        if (!w) return ORC_ERR_ALLOC;
+        for (uint64_t r = 0; r < f->n_blocks; ++r)
+            memcpy(w + r * new_width, f->words + r * f->bin_width, f->bin_width * 8);
+        free(f->words);
+        f->words = w;
+        f->n_bits = n_bits;
+    }
+    f->n_bins = new_n_bins;
+    uint64_t rows = f->n_blocks;
+    derive(f);
+    f->n_blocks = rows;
+    write_meta(f);
+    return ORC_OK;
+}
+
 void orc_ibf_free(orc_ibf *f)
 {
     if (f) { free(f->words); free(f); }

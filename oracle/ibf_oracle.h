@@ -63,6 +63,7 @@ uint8_t orc_dna5(char c);
 orc_ibf *orc_ibf_create(uint64_t n_bins, uint64_t n_hash, uint64_t k, uint64_t n_bits);
 orc_ibf *orc_ibf_load(const char *path, int *status);
 int orc_ibf_store(const orc_ibf *f, const char *path);
+int orc_ibf_resize_bins(orc_ibf *f, uint64_t new_n_bins);
 void orc_ibf_free(orc_ibf *f);
 uint64_t *orc_ibf_words(orc_ibf *f);
 void orc_ibf_info(const orc_ibf *f, uint64_t *n_bins, uint64_t *n_hash, uint64_t *k,

@@ -29,7 +29,7 @@ EXPORTS = [
     "rb_ibf_device_words", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_kernel_launches",
     "rb_microbench_gather", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
-    "rb_ibf_enable_kmer_table",
+    "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins",
 ]
 
 
@@ -104,6 +104,7 @@ def lib():
         "rb_set_l2_fetch_granularity": (i32, [i32, u32]),
         "rb_get_l2_fetch_granularity": (i32, [i32, vp]),
         "rb_ibf_enable_kmer_table": (i32, [vp, u64, vp]),
+        "rb_ibf_resize_bins": (i32, [vp, u64, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -254,6 +255,10 @@ class IBF:
         out = np.zeros(self.n_local_words, np.uint64)
         _check(lib().rb_ibf_download(self._h, _np_ptr(out), out.size))
         return out
+
+    def resize_bins(self, new_n_bins, stream=None):
+        _check(lib().rb_ibf_resize_bins(self._h, new_n_bins, _stream_ptr(stream)))
+        self.__init__(self._h)                       # refresh the cached geometry
 
     def enable_kmer_table(self, max_table_bytes=0, stream=None):
         """Build the direct k-mer table now (0 = automatic budget).  See rb_ibf.h."""

@@ -668,6 +668,40 @@ int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stre
 
 uint64_t *rb_ibf_device_words(const rb_ibf *f) { return f ? f->d_words : nullptr; }
 
+// filter.resizeBins(n), src/IBF/IBFBuild.cpp:274 (update_filter): the number of rows stays, rows get wider
+// when the bin count crosses a multiple of 64; existing bits keep their (row, bin) coordinates.
+int rb_ibf_resize_bins(rb_ibf *f, uint64_t new_n_bins, rb_stream stream)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "null filter");
+    if (f->n_shards != 1) return fail(RB_ERR_INVALID_ARG, "cannot resize a bin shard");
+    if (new_n_bins < f->n_bins) return fail(RB_ERR_INVALID_CONFIG, "resizeBins cannot shrink the filter");
+    if (new_n_bins == f->n_bins) return RB_OK;
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    drop_table(f);
+    const uint64_t new_width = (new_n_bins + 63) / 64;
+    if (new_width != f->bin_width) {
+        uint64_t *d_new = nullptr;
+        const uint64_t new_words = f->n_blocks * new_width;
+        RB_CUDA(cudaMalloc(&d_new, new_words * 8));
+        cudaError_t e = cudaMemsetAsync(d_new, 0, new_words * 8, st);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(d_new, new_width * 8, f->d_words, f->bin_width * 8, f->bin_width * 8, f->n_blocks,
+                                  cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { cudaFree(d_new); return fail(RB_ERR_CUDA, std::string("resizeBins: ") + cudaGetErrorString(e)); }
+        cudaFree(f->d_words);
+        f->d_words = d_new;
+        f->bin_width = new_width;
+        f->col_words = new_width;
+        f->n_bits = f->n_blocks * new_width * 64;
+        f->n_local_words = new_words;
+    }
+    f->n_bins = new_n_bins;
+    f->n_bins_local = new_n_bins;
+    return RB_OK;
+}
+
 // ---- build ---------------------------------------------------------------------------------------
 int rb_ibf_insert_batch_dev(rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_frag_begin, const uint64_t *d_frag_end,
                             const uint64_t *d_frag_bin, uint64_t n_frags, uint64_t max_frag_len, rb_stream stream)

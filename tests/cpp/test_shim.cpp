@@ -132,6 +132,25 @@ int main(int argc, char **argv)
     CHECK(reload.load_filter(rc).totalBinsFile == 1);
     IBFMeta built; built.filter = reload.getFilter();
     CHECK(read.count_matches(built, config) == 282);
+    // update_filter (IBFBuild.cpp:223-321): append the same reference as a new bin of the stored filter
+    IBF updater;
+    IBFConfig uc;
+    uc.update_filter_file = bc.output_filter_file;
+    uc.reference_files.push_back(fasta);
+    uc.fragment_length = 100000;
+    FilterStats us = updater.update_filter(uc);
+    CHECK(us.totalBinsFile == 1 && us.newBins == 1 && us.totalBinsBinId == 2 && uc.kmer_size == 13);
+    IBF reload2;
+    CHECK(reload2.load_filter(rc).totalBinsFile == 2);
+    IBFMeta grown; grown.filter = reload2.getFilter();
+    CHECK(read.count_matches(grown, config) == 282);
+    {
+        const uint64_t off1[2] = {0, read354.size()};
+        std::vector<uint16_t> lut(threshold_lut(0.1, 0.95, 13));
+        std::vector<uint16_t> cf(2), cr(2);
+        CHECK(rb_ibf_count_batch(grown.filter.get(), read354.data(), off1, 1, lut.data(), 1, cf.data(), cr.data(), nullptr, nullptr, nullptr, nullptr, nullptr) == RB_OK);
+        CHECK(cf[0] == 282 && cf[1] == 282 && cr[0] == 0 && cr[1] == 0);      // both bins now hold the sequence
+    }
     IBFConfig bad;
     bad.input_filter_file = fasta;
     CHECK(throws<ParseIBFFileException>([&] { reload.load_filter(bad); }));     // configReader.cpp:210-224 sniffing

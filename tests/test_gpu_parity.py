@@ -359,3 +359,31 @@ def test_config2_full_size_properties():
     assert np.array_equal(res["max_count"][pick], exp["max_count"])
     assert np.array_equal(res["hit"][pick], exp["hit"])
     assert np.array_equal(res["argmax_bin"][pick], exp["argmax_bin"])
+
+
+# ---- update_filter / resizeBins (SeqAn's resizeBins itself is unpinned by reference fixtures) ----
+@pytest.mark.parametrize("old_seqs,new_seqs", [(3, 2), (60, 10), (64, 1), (100, 100)])
+def test_resize_bins_and_append_equals_oracle(old_seqs, new_seqs):
+    """Appending bins keeps every existing bit at its (row, bin) and widens rows when 64 is crossed."""
+    plan, of, gf = make_filter_pair(old_seqs, 3000, 4000, 13)
+    rows = gf.n_blocks
+    total = old_seqs + new_seqs
+    gf.resize_bins(total)
+    of.resize_bins(total)
+    assert (gf.n_bins, gf.n_blocks, gf.bin_width) == (total, rows, (total + 63) // 64) == (of.n_bins, of.n_blocks, of.bin_width)
+    assert gf.n_bits == of.n_bits == rows * 64 * ((total + 63) // 64)
+    assert np.array_equal(gf.download(), of.words()[:of.n_bits // 64])
+    extra = [synth.random_bases(3000, 4000 + i) for i in range(new_seqs)]
+    p2 = synth.build_plan(extra, 4000, 13)
+    bins = p2["frag_bin"] + np.uint64(old_seqs)
+    gf.insert_batch(p2["bases"], p2["frag_begin"], p2["frag_end"], bins)
+    of.insert_batch(p2["bases"], p2["frag_begin"], p2["frag_end"], bins)
+    assert np.array_equal(gf.download(), of.words()[:of.n_bits // 64])
+    both = np.concatenate([plan["bases"], p2["bases"]])
+    bases, off = synth.ragged_reads(both, [250] * 80, seed=3, frac_from_ref=0.9)
+    lut = rb.threshold_lut(0.1, 13)
+    exp = of.count_batch(bases, off, lut)
+    assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+    assert (exp["argmax_bin"][exp["hit"] > 0] >= old_seqs).any() and (exp["argmax_bin"][exp["hit"] > 0] < old_seqs).any()
+    with pytest.raises(rb.RBError):
+        gf.resize_bins(total - 1)
