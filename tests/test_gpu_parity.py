@@ -379,8 +379,9 @@ def test_resize_bins_and_append_equals_oracle(old_seqs, new_seqs):
     gf.insert_batch(p2["bases"], p2["frag_begin"], p2["frag_end"], bins)
     of.insert_batch(p2["bases"], p2["frag_begin"], p2["frag_end"], bins)
     assert np.array_equal(gf.download(), of.words()[:of.n_bits // 64])
-    both = np.concatenate([plan["bases"], p2["bases"]])
-    bases, off = synth.ragged_reads(both, [250] * 80, seed=3, frac_from_ref=0.9)
+    b_old, o_old = synth.ragged_reads(plan["bases"], [250] * 40, seed=3, frac_from_ref=1.0)
+    b_new, o_new = synth.ragged_reads(p2["bases"], [250] * 40, seed=4, frac_from_ref=1.0)
+    bases, off = np.concatenate([b_old, b_new]), np.concatenate([o_old, o_new[1:] + o_old[-1]])
     lut = rb.threshold_lut(0.1, 13)
     exp = of.count_batch(bases, off, lut)
     assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
