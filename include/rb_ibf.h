@@ -216,6 +216,11 @@ RB_API int rb_get_l2_fetch_granularity(int device, uint32_t *bytes);
 RB_API int rb_microbench_gather(const void *d_buf, uint64_t n_rows, uint32_t row_bytes,
                                 uint64_t probes_per_thread, uint32_t n_blocks, uint64_t *d_sink,
                                 rb_stream stream);
+/* Same, but row_bytes / lane_bytes adjacent lanes read one row (16..256 bytes) with ONE load
+ * instruction of lane_bytes (16 or 32) per lane: the ceiling for warp-cooperative entry loads. */
+RB_API int rb_microbench_gather_coop(const void *d_buf, uint64_t n_rows, uint32_t row_bytes, uint32_t lane_bytes,
+                                     uint64_t probes_per_group, uint32_t n_blocks, uint64_t *d_sink,
+                                     rb_stream stream);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ EXPORTS = [
     "rb_ibf_load_shard", "rb_ibf_from_words", "rb_ibf_store", "rb_ibf_download", "rb_ibf_free", "rb_ibf_info",
     "rb_ibf_device_words", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_kernel_launches",
-    "rb_microbench_gather", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
+    "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
     "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins",
 ]
 
@@ -101,6 +101,7 @@ def lib():
         "rb_set_count_kernel": (i32, [i32]),
         "rb_kernel_launches": (u64, []),
         "rb_microbench_gather": (i32, [vp, u64, u32, u64, u32, vp, vp]),
+        "rb_microbench_gather_coop": (i32, [vp, u64, u32, u32, u64, u32, vp, vp]),
         "rb_set_l2_fetch_granularity": (i32, [i32, u32]),
         "rb_get_l2_fetch_granularity": (i32, [i32, vp]),
         "rb_ibf_enable_kmer_table": (i32, [vp, u64, vp]),
@@ -158,6 +159,11 @@ def set_count_kernel(which):
 def microbench_gather(d_buf, n_rows, row_bytes, probes_per_thread, n_blocks, d_sink, stream=None):
     _check(lib().rb_microbench_gather(_dev_ptr(d_buf), n_rows, row_bytes, probes_per_thread, n_blocks,
                                       _dev_ptr(d_sink), _stream_ptr(stream)))
+
+
+def microbench_gather_coop(d_buf, n_rows, row_bytes, lane_bytes, probes_per_group, n_blocks, d_sink, stream=None):
+    _check(lib().rb_microbench_gather_coop(_dev_ptr(d_buf), n_rows, row_bytes, lane_bytes, probes_per_group, n_blocks,
+                                           _dev_ptr(d_sink), _stream_ptr(stream)))
 
 
 def set_l2_fetch_granularity(nbytes, device=0):

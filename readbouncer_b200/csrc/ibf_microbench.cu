@@ -47,6 +47,45 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint8_t *__restrict__
     if (acc == 0x123456789ABCDEFULL) sink[0] = acc;   // practically never; keeps the loads live
 }
 
+
+// Cooperative variant: G = ROWB / V adjacent lanes read ONE row with a single load instruction of V bytes
+// per lane (V = 16: LDG.128, V = 32: LDG.256), so the L1 sees one request per row that names all of its
+// sectors, instead of ROWB/16 separate requests from one thread as in gather_kernel.
+template <int V>
+__device__ __forceinline__ uint64_t load_fold(const uint8_t *p)
+{
+    if constexpr (V == 32) {
+        uint64_t a, b, c, d;
+        asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+        return a ^ b ^ c ^ d;
+    } else {
+        ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+        return t.x ^ t.y;
+    }
+}
+
+template <int ROWB, int V>
+__global__ void __launch_bounds__(256) gather_coop_kernel(const uint8_t *__restrict__ buf, uint64_t n_rows, uint64_t magic,
+                                                          uint64_t probes_per_group, uint64_t *sink)
+{
+    constexpr int G = ROWB / V;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gid = tid / G;
+    const uint32_t sub = (uint32_t)(tid % G);
+    uint64_t acc = 0;
+    for (uint64_t it = 0; it < probes_per_group; it += 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            uint64_t row = fast_mod(mix64(gid * 0x100000001B3ULL + it + u), n_rows, magic);
+            v[u] = load_fold<V>(buf + row * ROWB + sub * V);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc ^= v[u];
+    }
+    if (acc == 0x123456789ABCDEFULL) sink[0] = acc;
+}
+
 }  // namespace rb
 
 extern "C" RB_API int rb_microbench_gather(const void *d_buf, uint64_t n_rows, uint32_t row_bytes,
@@ -65,4 +104,25 @@ extern "C" RB_API int rb_microbench_gather(const void *d_buf, uint64_t n_rows, u
     else if (row_bytes == 128) rb::gather_kernel<128><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_thread, d_sink);
     else return RB_ERR_INVALID_ARG;
     return cudaGetLastError() == cudaSuccess ? RB_OK : RB_ERR_CUDA;
+}
+
+// rows of row_bytes read by row_bytes / lane_bytes adjacent lanes, one load instruction per row
+extern "C" RB_API int rb_microbench_gather_coop(const void *d_buf, uint64_t n_rows, uint32_t row_bytes, uint32_t lane_bytes,
+                                                uint64_t probes_per_group, uint32_t n_blocks, uint64_t *d_sink,
+                                                rb_stream stream)
+{
+    if (!d_buf || !d_sink || n_rows == 0 || n_blocks == 0) return RB_ERR_INVALID_ARG;
+    const uint64_t magic = rb::mod_magic(n_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    probes_per_group = (probes_per_group + 7) / 8 * 8;
+    const uint8_t *b = static_cast<const uint8_t *>(d_buf);
+#define RB_COOP(R, V)                                                                                              \
+    if (row_bytes == R && lane_bytes == V) {                                                                       \
+        rb::gather_coop_kernel<R, V><<<n_blocks, 256, 0, st>>>(b, n_rows, magic, probes_per_group, d_sink);        \
+        return cudaGetLastError() == cudaSuccess ? RB_OK : RB_ERR_CUDA;                                            \
+    }
+    RB_COOP(16, 16) RB_COOP(32, 16) RB_COOP(32, 32) RB_COOP(64, 16) RB_COOP(64, 32) RB_COOP(128, 16) RB_COOP(128, 32)
+    RB_COOP(256, 16) RB_COOP(256, 32)
+#undef RB_COOP
+    return RB_ERR_INVALID_ARG;
 }
