@@ -332,7 +332,8 @@ def run_ours(args, w, n_reads):
     lookups, bytes_per_chunk = algorithmic_bytes_per_chunk(w, gf.col_words)
     peak, peak_src = measured_peaks()
     achieved = n_reads * bytes_per_chunk / (kernel_ms * 1e-3) / 1e9
-    kernel_name = ("count_table_kernel" if gf.kmer_table_bytes() else
+    span = gf.kmer_table_span()
+    kernel_name = ("count_wtable_kernel" if span >= 2 else "count_table_kernel" if span == 1 else
                    "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -344,23 +345,53 @@ def run_ours(args, w, n_reads):
                 "traffic": traffic, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_chunk": bytes_per_chunk, "peak_source": peak_src,
                 "kmer_lookups_per_s": (n_reads if bin_sharded else world * n_reads) * lookups / (total_ms * 1e-3 / args.steps)}
-    # random-sector ceiling for narrow rows (<= 32 B): measured gather microbenchmark over the same matrix
+    # Narrow rows are bound by memory REQUESTS, not bytes: measure the box's random-gather ceiling
+    # over the very buffer the kernel reads, with the kernel's request shape, and report requests/s against it.
     row_bytes = int(gf.col_words * 8)
-    if row_bytes in (8, 16, 32):
-        sink = torch.zeros(1, dtype=torch.int64, device=dev)
-        blocks, ppt = 148 * 8, 256
+    sink = torch.zeros(1, dtype=torch.int64, device=dev)
+    blocks = 148 * 8
+
+    def time_gather(fn):
         for it in range(3):
             if it == 1:
                 torch.cuda.synchronize(); ev0.record(stream)
-            rb.microbench_gather(gf.device_words_ptr(), gf.n_blocks, row_bytes, ppt, blocks, sink, stream=stream)
+            fn()
         ev1.record(stream)
         torch.cuda.synchronize()
-        g_ms = ev0.elapsed_time(ev1) / 2
-        probes_per_s = blocks * 256 * ppt / (g_ms * 1e-3)
-        ours_probes_per_s = n_reads * lookups * 3 / (kernel_ms * 1e-3)
-        roofline["random_sector"] = {"row_bytes": row_bytes, "peak_probes_per_s": probes_per_s,
-                                     "achieved_probes_per_s": ours_probes_per_s, "frac": ours_probes_per_s / probes_per_s,
-                                     "how": "rb_microbench_gather over the same %d-row matrix" % gf.n_blocks}
+        return ev0.elapsed_time(ev1) / 2
+
+    npos = w["chunk"] - w["k"] + 1
+    if span >= 2:       # window table: one request per entry of `lanes` slots, adjacent lanes
+        lanes = 2 if span == 2 else 4
+        entry_bytes = lanes * 16 * int(gf.col_words)
+        n_rows = gf.kmer_table_bytes() // entry_bytes
+        ppg = 64 * lanes
+        g_ms = time_gather(lambda: rb.microbench_gather_coop(gf.device_kmer_table_ptr(), n_rows, entry_bytes,
+                                                              16 * int(gf.col_words), ppg, blocks, sink, stream=stream))
+        peak_req = blocks * 256 // lanes * ppg / (g_ms * 1e-3)
+        req_per_chunk = -(-npos // span)
+        roofline["requests"] = {"what": "one %d-byte table entry (%d k-mer positions, both strands) per request" % (entry_bytes, span),
+                                "per_chunk": req_per_chunk, "peak_per_s": peak_req,
+                                "achieved_per_s": n_reads * req_per_chunk / (kernel_ms * 1e-3),
+                                "how": "rb_microbench_gather_coop over the k-mer table itself (%d entries)" % n_rows}
+    elif span == 1:
+        entry_bytes = 16 * int(gf.col_words)
+        n_rows = gf.kmer_table_bytes() // entry_bytes
+        g_ms = time_gather(lambda: rb.microbench_gather(gf.device_kmer_table_ptr(), n_rows, entry_bytes, 256, blocks, sink, stream=stream)) \
+            if entry_bytes in (16, 32, 64) else None
+        if g_ms:
+            roofline["requests"] = {"what": "one %d-byte table entry (1 k-mer position, both strands) per request" % entry_bytes,
+                                    "per_chunk": npos, "peak_per_s": blocks * 256 * 256 / (g_ms * 1e-3),
+                                    "achieved_per_s": n_reads * npos / (kernel_ms * 1e-3),
+                                    "how": "rb_microbench_gather over the k-mer table itself (%d entries)" % n_rows}
+    elif row_bytes in (8, 16, 32):
+        g_ms = time_gather(lambda: rb.microbench_gather(gf.device_words_ptr(), gf.n_blocks, row_bytes, 256, blocks, sink, stream=stream))
+        roofline["requests"] = {"what": "one %d-byte row probe per request" % row_bytes, "per_chunk": lookups * 3,
+                                "peak_per_s": blocks * 256 * 256 / (g_ms * 1e-3),
+                                "achieved_per_s": n_reads * lookups * 3 / (kernel_ms * 1e-3),
+                                "how": "rb_microbench_gather over the same %d-row matrix" % gf.n_blocks}
+    if "requests" in roofline:
+        roofline["requests"]["frac"] = roofline["requests"]["achieved_per_s"] / roofline["requests"]["peak_per_s"]
 
     # ---- CPU baseline: the oracle port on this box's cores, bounded sample (N=1 only) ----------------------
     cpu_baseline = None
@@ -397,7 +428,7 @@ def run_ours(args, w, n_reads):
                    "thresholds_per_pass": n_lut, "l2_fetch_granularity": rb.get_l2_fetch_granularity(local), "error_rate": ERROR_RATE, "read_mix": "50% reference-derived @10% errors, 50% iid",
                    "l2": "no flush: inputs (%.0f MB reads + %.0f MB filter) exceed the 126 MB L2" % (
                        bases_np.nbytes / 1e6, plan["n_bits"] / 8e6),
-                   "hit_fraction": hits_dev / n_reads, "kmer_table_bytes": gf.kmer_table_bytes(), "ibf_build_ms_gpu": build_ms,
+                   "hit_fraction": hits_dev / n_reads, "kmer_table_bytes": gf.kmer_table_bytes(), "kmer_table_span": gf.kmer_table_span(), "ibf_build_ms_gpu": build_ms,
                    "ibf_build_kmers_per_s": n_kmers_ref / (build_ms * 1e-3)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

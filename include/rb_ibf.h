@@ -79,7 +79,7 @@ typedef struct rb_ibf_info_t {
     uint64_t device_bytes;  /* bytes of HBM used by the bit matrix              */
     int32_t device;
     int32_t shard, n_shards;
-    int32_t kmer_table_span;   /* consecutive k-mers per table entry (1 or 2), 0 if not built */
+    int32_t kmer_table_span;   /* consecutive k-mers per table entry (1..4), 0 if not built */
     uint64_t kmer_table_bytes; /* bytes of the direct k-mer table, 0 if not built */
 } rb_ibf_info_t;
 
@@ -126,6 +126,8 @@ RB_API void rb_ibf_free(rb_ibf *f);
 RB_API int rb_ibf_info(const rb_ibf *f, rb_ibf_info_t *out);
 /* Raw device pointer of the bit matrix (for zero-copy interop, e.g. torch.from_blob) */
 RB_API uint64_t *rb_ibf_device_words(const rb_ibf *f);
+/* Device pointer of the k-mer table (NULL if not built); measurement aid for the gather microbenchmarks. */
+RB_API const uint64_t *rb_ibf_device_kmer_table(const rb_ibf *f);
 
 /* filter.resizeBins(n) as used by IBF::update_filter (src/IBF/IBFBuild.cpp:269-279): grow the bin count; the
  * number of rows is kept and rows are widened when n crosses a multiple of 64 (n_bits = rows * 64 * ceil(n/64)).
@@ -156,7 +158,8 @@ RB_API int rb_ibf_insert_batch_dev(rb_ibf *f, const uint8_t *d_bases, const uint
  * max_count/hit/argmax_bin [n_lut][n_reads]; argmax_bin = lowest global bin attaining
  * max_count among bins passing the threshold, 0xFFFFFFFF if none;
  * read_flag [n_reads]: 0 ok, 1 = shorter than k (ShortReadException), 2 = longer than 65535
- * bases (not representable in the reference's uint16 readlen; not classified). */
+ * bases (not representable in the reference's uint16 readlen; not classified), 3 = longer than the
+ * max_read_len given to rb_ibf_count_batch_dev (not classified; never set by rb_ibf_count_batch). */
 RB_API int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_off,
                               uint64_t n_reads, const uint16_t *thr_lut, uint32_t n_lut,
                               uint16_t *counts_fwd, uint16_t *counts_rev, uint16_t *max_count,
@@ -187,19 +190,25 @@ RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_ma
 
 /* Direct k-mer table for narrow filters (row <= 4 words, k <= 16): the AND of the h probed rows is a
  * pure function of the k-mer, so it is tabulated once for all ACGT k-mers and both strands.  An entry
- * covers a window of `span` consecutive k-mers (k+span-1 bases): span 1 = 4^k * 16 * col_words bytes
- * (2.1 GB for k=13, 100 bins), span 2 = 4^(k+1) * 32 * col_words bytes (17 GB; rows <= 2 words).
- * Count calls then read one entry (one HBM line) per `span` k-mer positions instead of 2*h rows per
+ * covers a window of `span` consecutive k-mers (k+span-1 bases).  span 1: 4^k entries of 16*col_words
+ * bytes (2.1 GB for k=13, 100 bins), read by one lane each.  span 2..4 (rows <= 2 words): entries of
+ * 2 (span 2) or 4 slots of 16*col_words bytes, read by adjacent lanes in one request; when the window
+ * length is odd only the windows whose middle base is A or C are stored (a window and its reverse
+ * complement hold the same masks), e.g. k=13, span 3: 4^15/2 entries of 128 bytes = 64 GiB for 100 bins.
+ * Count calls then cost one memory request per `span` k-mer positions instead of 2*h row probes per
  * position; windows containing N take the hashed path, so results are bit-identical.  Built
- * automatically by the first count call with >= 1024 reads, choosing the widest useful span that
- * fits min(half of the free HBM, 48 GiB) (env RB_KMER_TABLE=0 disables); dropped by
- * rb_ibf_insert_batch*.  This call (re)builds it now under the given byte budget (0 = automatic);
- * UINT64_MAX disables the table for this handle. */
+ * automatically by the first count call with >= 1024 reads, choosing the widest span that fits
+ * min(60 % of the free HBM, 80 GiB) (env RB_KMER_TABLE=0 disables, RB_KMER_TABLE_MAX_GB changes the
+ * cap, RB_KMER_TABLE_SPAN the widest span tried); dropped by rb_ibf_insert_batch*.  This call
+ * (re)builds it now under the given byte budget (0 = automatic); UINT64_MAX disables the table for
+ * this handle. */
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);
 
 /* Kernel selection override for tests/benchmarks: 0 auto, 1 warp-per-read tile kernel,
  * 2 CTA-per-read streaming kernel, 3 direct k-mer table kernel (fails if not applicable; bit-sliced
- * register counters for rows <= 2 words), 4 k-mer table kernel with shared-memory counters. */
+ * register counters for rows <= 2 words), 4 k-mer table kernel with shared-memory counters,
+ * 5 k-mer table, window tables always through the warp-per-read kernel (auto uses the
+ * group-per-read kernel when every read of the launch has <= 127*span positions). */
 RB_API int rb_set_count_kernel(int which);
 /* Number of kernels this library launched since load (all threads); evidence for gpu_launches. */
 RB_API uint64_t rb_kernel_launches(void);

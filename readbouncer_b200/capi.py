@@ -26,7 +26,7 @@ EXPORTS = [
     "rb_status_string", "rb_last_error", "rb_device_count", "rb_ibf_size_bits", "rb_calculate_ci",
     "rb_threshold_lut", "rb_cut_out_nnns", "rb_fragment_schedule", "rb_ibf_create", "rb_ibf_load",
     "rb_ibf_load_shard", "rb_ibf_from_words", "rb_ibf_store", "rb_ibf_download", "rb_ibf_free", "rb_ibf_info",
-    "rb_ibf_device_words", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
+    "rb_ibf_device_words", "rb_ibf_device_kmer_table", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_kernel_launches",
     "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
     "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins",
@@ -93,6 +93,7 @@ def lib():
         "rb_ibf_free": (None, [vp]),
         "rb_ibf_info": (i32, [vp, C.POINTER(_Info)]),
         "rb_ibf_device_words": (vp, [vp]),
+        "rb_ibf_device_kmer_table": (vp, [vp]),
         "rb_ibf_insert_batch": (i32, [vp, vp, u64, vp, vp, vp, u64, vp]),
         "rb_ibf_insert_batch_dev": (i32, [vp, vp, vp, vp, vp, u64, u64, vp]),
         "rb_ibf_count_batch": (i32, [vp, vp, vp, u64, vp, u32, vp, vp, vp, vp, vp, vp, vp]),
@@ -285,6 +286,9 @@ class IBF:
 
     def device_words_ptr(self):
         return int(lib().rb_ibf_device_words(self._h) or 0)
+
+    def device_kmer_table_ptr(self):
+        return int(lib().rb_ibf_device_kmer_table(self._h) or 0)
 
     # ---- build -----------------------------------------------------------------------------------
     def insert_batch(self, bases, frag_begin, frag_end, frag_bin, stream=None):

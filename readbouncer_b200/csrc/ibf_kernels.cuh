@@ -46,6 +46,12 @@ int launch_count(const CountArgs &a, uint32_t max_read_len, int which, int sm_co
 int launch_table_build(const FilterView &fv, uint64_t *table, uint64_t n_entries, int span, int sm_count, cudaStream_t st);
 int launch_count_table(const CountArgs &a, const uint64_t *table, int span, uint32_t max_read_len, int variant,
                        int sm_count, cudaStream_t st);
+// window k-mer table with cooperative entry loads (ibf_wtable.cu): span = 2..4 k-mers per entry, rows <= 2 words
+bool wtable_geometry(uint64_t stride, uint32_t k, int span, int *lanes, int *canon, uint64_t *n_entries);
+int launch_wtable_build(const FilterView &fv, uint64_t *table, int span, int sm_count, cudaStream_t st);
+int launch_count_wtable(const CountArgs &a, const uint64_t *table, int span, uint32_t max_read_len, int sm_count,
+                        cudaStream_t st);
+void set_wtable_variant(int v);   // 0 auto (group-per-read kernel for short reads), 1 always warp-per-read
 int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cudaStream_t st);
 int launch_keys_decode(const uint64_t *keys, uint64_t n, uint16_t *max_count, uint8_t *hit,
                        uint32_t *argmax_bin, cudaStream_t st);

@@ -14,7 +14,7 @@
 // same bits the three probes would have produced.  Windows containing a non-ACGT base (Dna5
 // rank 4) are not in the table and take the hashing path of the original filter, so the output
 // stays bit-exact for every input.
-#include "ibf_device.cuh"
+#include "ibf_bitslice.cuh"
 
 namespace rb {
 
@@ -185,113 +185,6 @@ count_table_kernel(const CountArgs a, const uint64_t *__restrict__ table)
 constexpr int kBsSeg = 15;                  // positions per lane per chunk (4 planes hold 0..15)
 constexpr int kBsChunk = 32 * kBsSeg;       // 480 positions per warp chunk
 constexpr int kBsDig = kBsChunk + 32;
-constexpr unsigned kFull = 0xffffffffu;
-
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
-
-// fold the upper/lower half of the WORDS held by a lane pair (distance OFF); NP -> NP+1 planes
-template <int NW, int NP, int OFF>
-__device__ __forceinline__ void fold_words(const uint32_t (&in)[NP][NW], uint32_t (&out)[NP + 1][NW / 2], int lane)
-{
-    const bool upper = (lane & OFF) != 0;
-    uint32_t carry[NW / 2];
-#pragma unroll
-    for (int i = 0; i < NW / 2; ++i) carry[i] = 0;
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-#pragma unroll
-        for (int i = 0; i < NW / 2; ++i) {
-            const uint32_t lo = in[p][i], hi = in[p][NW / 2 + i];
-            const uint32_t mine = upper ? hi : lo;
-            const uint32_t recv = __shfl_xor_sync(kFull, upper ? lo : hi, OFF);
-            out[p][i] = mine ^ recv ^ carry[i];
-            carry[i] = maj3(mine, recv, carry[i]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NW / 2; ++i) out[NP][i] = carry[i];
-}
-
-// fold the upper/lower half of the BITS significant bits of a single word
-template <int BITS, int NP, int OFF>
-__device__ __forceinline__ void fold_bits(const uint32_t (&in)[NP], uint32_t (&out)[NP + 1], int lane)
-{
-    constexpr int H = BITS / 2;
-    constexpr uint32_t LOW = (1u << H) - 1u;
-    const bool upper = (lane & OFF) != 0;
-    uint32_t carry = 0;
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        const uint32_t lo = in[p] & LOW, hi = (in[p] >> H) & LOW;
-        const uint32_t mine = upper ? hi : lo;
-        const uint32_t recv = __shfl_xor_sync(kFull, upper ? lo : hi, OFF);
-        out[p] = mine ^ recv ^ carry;
-        carry = maj3(mine, recv, carry);
-    }
-    out[NP] = carry;
-}
-
-// 32-lane sum of 4-plane per-lane counters -> 9-plane counters of NWP bits per lane
-template <int NWP>
-__device__ __forceinline__ void warp_fold(const uint32_t (&pl)[4][NWP], uint32_t (&res)[9], int lane)
-{
-    if constexpr (NWP == 8) {
-        uint32_t a[5][4], b[6][2], c[7][1], d[7], e[8];
-        fold_words<8, 4, 16>(pl, a, lane);
-        fold_words<4, 5, 8>(a, b, lane);
-        fold_words<2, 6, 4>(b, c, lane);
-#pragma unroll
-        for (int p = 0; p < 7; ++p) d[p] = c[p][0];
-        fold_bits<32, 7, 2>(d, e, lane);
-        fold_bits<16, 8, 1>(e, res, lane);
-    } else {   // NWP == 4
-        uint32_t a[5][2], b[6][1], c[6], d[7], e[8];
-        fold_words<4, 4, 16>(pl, a, lane);
-        fold_words<2, 5, 8>(a, b, lane);
-#pragma unroll
-        for (int p = 0; p < 6; ++p) c[p] = b[p][0];
-        fold_bits<32, 6, 4>(c, d, lane);
-        fold_bits<16, 7, 2>(d, e, lane);
-        fold_bits<8, 8, 1>(e, res, lane);
-    }
-}
-
-template <int NP>
-__device__ __forceinline__ uint32_t bs_ge(const uint32_t (&pl)[NP], uint32_t thr)
-{
-    if (thr >> NP) return 0;
-    uint32_t gt = 0, eq = ~0u;
-#pragma unroll
-    for (int p = NP - 1; p >= 0; --p) {
-        const uint32_t tb = ((thr >> p) & 1u) ? ~0u : 0u;
-        gt |= eq & pl[p] & ~tb;
-        eq &= ~(pl[p] ^ tb);
-    }
-    return gt | eq;
-}
-
-// max over the counters selected by `sel` (bit-sliced numbers, MSB first); `sel` shrinks to the arg-max set
-template <int NP>
-__device__ __forceinline__ uint32_t bs_max(const uint32_t (&pl)[NP], uint32_t &sel)
-{
-    uint32_t val = 0;
-#pragma unroll
-    for (int p = NP - 1; p >= 0; --p) {
-        const uint32_t t = sel & pl[p];
-        if (t) { sel = t; val |= 1u << p; }
-    }
-    return val;
-}
-
-template <int NP>
-__device__ __forceinline__ uint32_t bs_get(const uint32_t (&pl)[NP], int b)
-{
-    uint32_t c = 0;
-#pragma unroll
-    for (int p = 0; p < NP; ++p) c |= ((pl[p] >> b) & 1u) << p;
-    return c;
-}
-
 // WT: row words (1 or 2).  NPA: planes of the per-read accumulator (9 when every read is a single
 // chunk, else 16).  S: consecutive k-mers per table entry (window table).
 template <int WT, int NPA, int S>
@@ -475,14 +368,9 @@ static void launch_build_wt(const FilterView &fv, uint64_t *table, uint64_t n_en
     table_build_kernel<WT, S><<<(uint32_t)(blocks < cap ? blocks : cap), 256, 0, st>>>(fv, table, n_entries);
 }
 
-// span = k-mers per entry (1 or 2); n_entries = 4^(k + span - 1)
+// one k-mer per entry (span 1); wider windows live in ibf_wtable.cu
 int launch_table_build(const FilterView &fv, uint64_t *table, uint64_t n_entries, int span, int sm_count, cudaStream_t st)
 {
-    if (span == 2 && fv.stride <= 2) {
-        if (fv.stride == 1) launch_build_wt<1, 2>(fv, table, n_entries, sm_count, st);
-        else launch_build_wt<2, 2>(fv, table, n_entries, sm_count, st);
-        return cudaGetLastError() == cudaSuccess ? 1 : -1;
-    }
     if (span != 1) return -1;
     switch (fv.stride) {
     case 1: launch_build_wt<1, 1>(fv, table, n_entries, sm_count, st); break;
@@ -531,25 +419,18 @@ static void launch_table_bs_np(const CountArgs &a, const uint64_t *table, bool s
     else launch_table_bs<WT, 16, S>(a, table, sm_count, st);
 }
 
-// span: k-mers per table entry.  variant 0: bit-sliced register counters (rows <= 2 words);
-// 1: shared-memory atomic counters (span 1 only).
+// variant 0: bit-sliced register counters (rows <= 2 words); 1: shared-memory atomic counters.
 int launch_count_table(const CountArgs &a, const uint64_t *table, int span, uint32_t max_read_len, int variant,
                        int sm_count, cudaStream_t st)
 {
     if (a.n_reads == 0) return 0;
-    if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut) return -1;
-    if ((variant == 0 || span == 2) && a.fv.stride <= 2) {
+    if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut || span != 1) return -1;
+    if (variant == 0 && a.fv.stride <= 2) {
         const bool single_chunk = max_read_len != 0 && max_read_len < a.fv.hp.k + (uint32_t)kBsChunk;
-        if (a.fv.stride == 1) {
-            if (span == 2) launch_table_bs_np<1, 2>(a, table, single_chunk, sm_count, st);
-            else launch_table_bs_np<1, 1>(a, table, single_chunk, sm_count, st);
-        } else {
-            if (span == 2) launch_table_bs_np<2, 2>(a, table, single_chunk, sm_count, st);
-            else launch_table_bs_np<2, 1>(a, table, single_chunk, sm_count, st);
-        }
+        if (a.fv.stride == 1) launch_table_bs_np<1, 1>(a, table, single_chunk, sm_count, st);
+        else launch_table_bs_np<2, 1>(a, table, single_chunk, sm_count, st);
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
-    if (span != 1) return -1;
     switch (a.fv.stride) {
     case 1: launch_table_wt<1, 2>(a, table, sm_count, st); break;
     case 2: launch_table_wt<2, 2>(a, table, sm_count, st); break;

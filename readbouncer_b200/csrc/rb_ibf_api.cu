@@ -64,7 +64,9 @@ struct rb_ibf {
     mutable std::mutex table_mu;
     mutable uint64_t *d_table = nullptr;
     mutable uint64_t table_entries = 0;
-    mutable int table_span = 0;             // k-mers per entry (1 or 2)
+    mutable int table_span = 0;             // k-mers per entry: 1 = one k-mer per lane (ibf_table.cu), 2..4 = window
+                                            // entries loaded by adjacent lanes (ibf_wtable.cu)
+    mutable uint64_t table_bytes = 0;
     mutable bool table_tried = false;
     mutable uint64_t table_budget = 0;      // 0 = automatic
 };
@@ -235,17 +237,21 @@ rb::FilterView view_of(const rb_ibf *f)
 // ---- direct k-mer table policy -----------------------------------------------------------------
 constexpr uint64_t kTableMinReads = 1024;   // batches smaller than this never trigger the (GB-sized) table build
 
-// span = consecutive k-mers per entry: entry y is a (k+span-1)-base window, 2*span*col_words words
+// span = consecutive k-mers per entry.  span 1: 4^k entries of 2*col_words words, one lane per entry
+// (ibf_table.cu, rows <= 4 words).  span 2..4: (k+span-1)-base windows, canonical when that length is odd,
+// `lanes` slots of 2*col_words words per entry, loaded by adjacent lanes (ibf_wtable.cu, rows <= 2 words).
 uint64_t table_bytes_needed(const rb_ibf *f, int span)
 {
     if (f->col_words == 0 || f->k + span - 1 > 16) return 0;
-    if (span == 1 && f->col_words > 4) return 0;
-    if (span == 2 && f->col_words > 2) return 0;
-    return (1ull << (2 * (f->k + span - 1))) * 2 * span * f->col_words * 8;
+    if (span == 1) return f->col_words > 4 ? 0 : (1ull << (2 * f->k)) * 2 * f->col_words * 8;
+    int lanes = 0;
+    uint64_t n_entries = 0;
+    if (!rb::wtable_geometry(f->col_words, (uint32_t)f->k, span, &lanes, nullptr, &n_entries)) return 0;
+    return n_entries * (uint64_t)lanes * 2 * f->col_words * 8;
 }
 
 // Builds the table on `st` if the policy allows it; returns the device pointer or null.
-// force: ignore the "filter fits L2" heuristic (tests, explicit rb_ibf_enable_kmer_table).
+// force: ignore the batch-size heuristic (tests, explicit rb_ibf_enable_kmer_table).
 const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint64_t n_reads = ~0ull)
 {
     std::lock_guard<std::mutex> lock(f->table_mu);
@@ -257,29 +263,33 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     if (!force && env && env[0] == '0') return nullptr;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>(free_b / 2, 48ull << 30);
-    // Measured on B200 (profiles/r1_gather_sweep2.jsonl): random gathers are bound by ~42 G L2-missing
-    // 32-byte SECTOR requests/s, so a window entry only pays when two k-mer positions share one sector,
-    // i.e. for one-word rows (16 B per position).  RB_KMER_TABLE_SPAN overrides for experiments.
-    int max_span = f->col_words == 1 ? 2 : 1;
-    if (const char *sp_env = std::getenv("RB_KMER_TABLE_SPAN")) max_span = std::atoi(sp_env) >= 2 ? 2 : 1;
+    // Sized for 180 GB of HBM: the widest window whose table fits 60 % of the free memory (at most 80 GiB)
+    // wins, because the classify kernel is bound by REQUESTS (~43 G/s for anything up to 128 contiguous
+    // bytes, profiles/r1_d_gather_sweep3_coop.jsonl) and a span-S entry answers S positions per request.
+    uint64_t cap = 80ull << 30;
+    if (const char *gb = std::getenv("RB_KMER_TABLE_MAX_GB")) cap = (uint64_t)std::max(0, std::atoi(gb)) << 30;
+    const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>((uint64_t)(free_b * 0.6), cap);
+    int max_span = f->col_words <= 2 ? 4 : 1;
+    if (const char *sp_env = std::getenv("RB_KMER_TABLE_SPAN")) max_span = std::min(4, std::max(1, std::atoi(sp_env)));
     int span = 0;
     uint64_t need = 0;
-    for (int sp = max_span; sp >= 1 && !span; --sp) {   // the widest useful window that fits the budget
+    for (int sp = max_span; sp >= 1 && !span; --sp) {   // the widest window that fits the budget
         const uint64_t b = table_bytes_needed(f, sp);
         if (b && b <= budget && b <= free_b) { span = sp; need = b; }
     }
     if (!span) return nullptr;
     uint64_t *t = nullptr;
     if (cudaMalloc(&t, need) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    const uint64_t entries = 1ull << (2 * (f->k + span - 1));
-    int n = rb::launch_table_build(view_of(f), t, entries, span, f->sm_count, st);
+    const uint64_t entries = 1ull << (2 * f->k);
+    int n = span == 1 ? rb::launch_table_build(view_of(f), t, entries, 1, f->sm_count, st)
+                      : rb::launch_wtable_build(view_of(f), t, span, f->sm_count, st);
     // other host threads may use the table from their own streams right away: finish the build first
     if (n < 0 || cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(t); cudaGetLastError(); return nullptr; }
     g_launches += (uint64_t)n;
     f->d_table = t;
     f->table_entries = entries;
     f->table_span = span;
+    f->table_bytes = need;
     return t;
 }
 
@@ -290,6 +300,7 @@ void drop_table(rb_ibf *f)
     f->d_table = nullptr;
     f->table_entries = 0;
     f->table_span = 0;
+    f->table_bytes = 0;
     f->table_tried = false;
 }
 
@@ -377,8 +388,9 @@ int rb_get_l2_fetch_granularity(int device, uint32_t *bytes)
 
 int rb_set_count_kernel(int which)
 {
-    if (which < 0 || which > 4) return fail(RB_ERR_INVALID_ARG, "kernel selector must be 0..4");
+    if (which < 0 || which > 5) return fail(RB_ERR_INVALID_ARG, "kernel selector must be 0..5");
     g_count_kernel.store(which);
+    rb::set_wtable_variant(which == 5 ? 1 : 0);
     return RB_OK;
 }
 
@@ -648,7 +660,7 @@ int rb_ibf_info(const rb_ibf *f, rb_ibf_info_t *out)
     out->device_bytes = f->n_local_words * 8; out->device = f->device; out->shard = f->shard; out->n_shards = f->n_shards;
     {
         std::lock_guard<std::mutex> lock(f->table_mu);
-        out->kmer_table_bytes = f->d_table ? f->table_entries * 2 * f->table_span * f->col_words * 8 : 0;
+        out->kmer_table_bytes = f->d_table ? f->table_bytes : 0;
         out->kmer_table_span = f->d_table ? f->table_span : 0;
     }
     return RB_OK;
@@ -667,6 +679,13 @@ int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stre
 }
 
 uint64_t *rb_ibf_device_words(const rb_ibf *f) { return f ? f->d_words : nullptr; }
+
+const uint64_t *rb_ibf_device_kmer_table(const rb_ibf *f)
+{
+    if (!f) return nullptr;
+    std::lock_guard<std::mutex> lock(f->table_mu);
+    return f->d_table;
+}
 
 // filter.resizeBins(n), src/IBF/IBFBuild.cpp:274 (update_filter): the number of rows stays, rows get wider
 // when the bin count crosses a multiple of 64; existing bits keep their (row, bin) coordinates.
@@ -773,10 +792,13 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     a.keys = d_keys; a.counts_fwd = d_counts_fwd; a.counts_rev = d_counts_rev; a.read_flag = d_read_flag;
     const int which = g_count_kernel.load();
     const uint64_t *table = nullptr;
-    if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3, n_reads);
+    if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3, n_reads);   // 3..5: table kernels
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
     if (table) {
-        int n = rb::launch_count_table(a, table, f->table_span, max_read_len, which == 4 ? 1 : 0, f->sm_count, (cudaStream_t)stream);
+        // selector 4 (shared-memory atomic counters) exists for one k-mer per entry only
+        int n = f->table_span >= 2
+                    ? rb::launch_count_wtable(a, table, f->table_span, max_read_len, f->sm_count, (cudaStream_t)stream)
+                    : rb::launch_count_table(a, table, 1, max_read_len, which == 4 ? 1 : 0, f->sm_count, (cudaStream_t)stream);
         if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         g_launches += (uint64_t)n;
         return RB_OK;
@@ -817,7 +839,7 @@ int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_
     const uint64_t nbl = f->n_bins_local;
     const uint64_t max_piece_reads = dense ? std::max<uint64_t>(1, std::min<uint64_t>(kPieceReads, (64ull << 20) / (2 * nbl)))
                                            : kPieceReads;
-    std::vector<uint64_t> cut{0};
+    std::vector<uint64_t> cut{0}, piece_max_len;
     uint64_t max_len = 0, max_piece_bases = 0, max_piece_n = 0;
     for (uint64_t i = 0, r0 = 0; i < n_reads; ++i) {
         if (read_off[i + 1] < read_off[i]) return fail(RB_ERR_INVALID_ARG, "read offsets must be non-decreasing");
@@ -827,6 +849,8 @@ int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_
             max_piece_bases = std::max(max_piece_bases, read_off[i + 1] - read_off[r0]);
             max_piece_n = std::max(max_piece_n, i + 1 - r0);
             cut.push_back(i + 1);
+            piece_max_len.push_back(max_len);       // the kernels specialise on the longest read of a launch
+            max_len = 0;
             r0 = i + 1;
         }
     }
@@ -875,7 +899,7 @@ int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_
             uint8_t *d_flag = S.d_small + nk * 7;
             // offsets stay absolute: bias the base pointer instead of rewriting them
             const uint8_t *biased = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(S.d_bases) - (uintptr_t)b0);
-            int s2 = rb_ibf_count_batch_dev(f, biased, S.d_off, n, (uint32_t)std::min<uint64_t>(max_len, 0xFFFFFFFFu),
+            int s2 = rb_ibf_count_batch_dev(f, biased, S.d_off, n, (uint32_t)std::min<uint64_t>(piece_max_len[p], 0xFFFFFFFFu),
                                             d_lut, n_lut, S.d_keys, S.d_cf, S.d_cr, d_flag, S.st);
             if (s2 != RB_OK) return s2;
             s2 = rb_keys_decode_dev(S.d_keys, nk, d_max, d_hit, d_amax, f->device, S.st);

@@ -13,7 +13,7 @@ from conftest import data_path, golden_words, read_fasta
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = {"auto": 0, "tile": 1, "stream": 2, "table": 3, "table_atomic": 4}
+KERNELS = {"auto": 0, "tile": 1, "stream": 2, "table": 3, "table_atomic": 4, "table_warp": 5}
 
 
 @pytest.fixture(autouse=True)
@@ -122,6 +122,16 @@ def test_golden_classify_fastq(golden_ibf_paths):
 
 
 # ---- synthetic differential tests ---------------------------------------------------------------------
+def wtable_bytes(k, bin_width, span):
+    """Size of the window k-mer table (ibf_wtable.cu: wtable_geometry), None when not applicable."""
+    L = k + span - 1
+    if bin_width > 2 or span < 2 or L > 16:
+        return None
+    lanes = 2 if span == 2 else 4
+    entries = 2 ** (2 * L - 1) if L % 2 else 4 ** L
+    return entries * lanes * 16 * bin_width
+
+
 RAGGED = [250] * 40 + [0, 1, 12, 13, 14, 31, 32, 33, 64, 100, 249, 251, 360, 500, 1023, 1024, 1036, 1037, 1500, 2100, 5000]
 
 
@@ -133,6 +143,8 @@ RAGGED = [250] * 40 + [0, 1, 12, 13, 14, 31, 32, 33, 64, 100, 249, 251, 360, 500
     (200, 3000, 4000, 13),       # 200 bins, W=4
     (1, 700 * 2000 + 7, 2000, 13),   # 701 bins, W=11 (odd stride -> 8-byte loads, tiles 4+4+3)
     (1100, 1500, 2000, 11),      # 1100 bins, W=18 (even stride -> 16-byte loads)
+    (60, 3000, 4000, 10),        # 60 bins, W=1, k=10: window tables of span 2 (canonical), 3, 4 (canonical)
+    (100, 3000, 4000, 11),       # 100 bins, W=2, k=11: span 2, 3 (canonical), 4
 ])
 def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
     rb.set_count_kernel(KERNELS[kernel])
@@ -150,14 +162,33 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
         gf.enable_kmer_table(span1)                      # budget admits only one k-mer per entry
         assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (span1, 1)
         assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
-        if gf.bin_width <= 2 and kernel == "table":      # window table: two consecutive k-mers per entry
-            os.environ["RB_KMER_TABLE_SPAN"] = "2"
-            try:
-                gf.enable_kmer_table(0)
-            finally:
-                del os.environ["RB_KMER_TABLE_SPAN"]
-            assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (4 ** (k + 1) * 32 * gf.bin_width, 2)
-            assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+        if gf.bin_width <= 2 and kernel == "table":      # window tables: 2..4 consecutive k-mers per entry
+            for span in (2, 3, 4):
+                need = wtable_bytes(k, gf.bin_width, span)
+                if need is None or need > (70 << 30):
+                    continue
+                os.environ["RB_KMER_TABLE_SPAN"] = str(span)
+                try:
+                    gf.enable_kmer_table(0)
+                finally:
+                    del os.environ["RB_KMER_TABLE_SPAN"]
+                assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (need, span)
+                assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)     # long reads: warp per read
+                # short reads only (<= 127*span positions, <= 561 bases): one read per group of lanes
+                limit = min(127 * span + k - 1, 561)
+                short = [250] * 70 + [0, 1, k - 1, k, k + 1, k + span - 1, k + span, 31, 32, 33, 47, 48, 49, 64, 100,
+                                      249, 251, 255, 256, 257, limit - 1, limit]
+                sb, so = synth.ragged_reads(plan["bases"], short, seed=11 + span, frac_from_ref=0.7, n_frac=0.004,
+                                            lower_frac=0.1)
+                sb[int(so[5]):int(so[6])] = ord("N")                        # an all-N read
+                sb[int(so[7]) + 100] = ord("U")                             # U counts as T
+                sb[int(so[8]) + 249] = ord("R")                             # IUPAC code in the last window
+                sexp = of.count_batch(sb, so, lut, n_threads=4)
+                assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)
+                assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+                rb.set_count_kernel(KERNELS["table_warp"])                  # same reads through the warp-per-read kernel
+                assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)
+                rb.set_count_kernel(KERNELS[kernel])
         return
     assert np.array_equal(lut, oracle.threshold_lut(0.1, k))
     got = gf.count_batch(bases, off, lut, dense=True)
@@ -175,7 +206,7 @@ def test_kmer_table_handles_n_rich_reads_and_is_dropped_by_insert():
     bases[int(off[5])] = ord("U")                               # U counts as T
     lut = rb.threshold_lut(0.1, 13)
     exp = of.count_batch(bases, off, lut, n_threads=4)
-    for which, span in ((3, 2), (3, 1), (4, 1)):
+    for which, span in ((3, 3), (3, 2), (3, 1), (4, 1)):
         rb.set_count_kernel(which)
         os.environ["RB_KMER_TABLE_SPAN"] = str(span)
         try:
@@ -337,7 +368,7 @@ def test_config2_full_size_properties():
     for key in ("max_count", "hit", "argmax_bin"):
         assert np.array_equal(res[key], res_rc[key])
     # (2) all three kernels agree on the whole batch (auto = direct k-mer table at this size)
-    assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (4 ** 13 * 32, 1)
+    assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (wtable_bytes(13, 2, 3), 3)   # 64 GiB, canonical 15-mers
     for which in (1, 2, 4):
         rb.set_count_kernel(which)
         res_s = gf.count_batch(bases, off, lut)
