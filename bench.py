@@ -308,20 +308,27 @@ def run_ours(args, w, n_reads):
         for _ in range(2):
             e2e_step()
         barrier()
+        xfer0 = rb.transfer_bytes()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        xfer1 = rb.transfer_bytes()
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
         assert int((res_hit[:n_reads] > 0).sum()) == hits_dev, "host-API results differ from device-API results"
+        # bytes that crossed PCIe, counted by the library at its copy calls: the host threads turn the ASCII bases into
+        # 3 bit planes before the transfer, so this is less than the size of the host input
         e2e = {"value": world * n_reads * args.steps / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": int(hb.nbytes + ho.nbytes + luts_np.nbytes),
-               "d2h_bytes_per_step": int(res_max.nbytes + res_hit.nbytes + res_am.nbytes + res_flag.nbytes),
-               "ms_per_step": 1000 * e2e_s / args.steps, "api": "rb_ibf_count_batch (host buffers, pinned)"}
+               "h2d_bytes_per_step": (xfer1[0] - xfer0[0]) // args.steps,
+               "d2h_bytes_per_step": (xfer1[1] - xfer0[1]) // args.steps,
+               "host_input_bytes_per_step": int(hb.nbytes + ho.nbytes + luts_np.nbytes),
+               "host_result_bytes_per_step": int(res_max.nbytes + res_hit.nbytes + res_am.nbytes + res_flag.nbytes),
+               "ms_per_step": 1000 * e2e_s / args.steps, "api": "rb_ibf_count_batch (host buffers, pinned)",
+               "host_pack": dict(rb.host_pack_info(), enabled=os.environ.get("RB_HOST_PACK", "1") != "0")}
 
     if rank != 0:
         if world > 1:

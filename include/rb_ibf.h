@@ -166,6 +166,14 @@ RB_API int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t
                               uint8_t *hit, uint32_t *argmax_bin, uint8_t *read_flag,
                               rb_stream stream);
 
+/* Host side of rb_ibf_count_batch: number of host threads that pack reads into bit planes for the
+ * PCIe transfer (env RB_HOST_THREADS, default min(cores, 16); RB_HOST_PACK=0 ships ASCII instead) and
+ * the packer's instruction set (0 scalar, 2 AVX2, 5 AVX-512 BW+VBMI; env RB_HOST_PACK_ISA caps it). */
+RB_API int rb_host_pack_info(int *threads, int *isa);
+/* Bytes rb_ibf_count_batch has moved over PCIe since the library was loaded (all threads): host->device
+ * copies (bit planes or ASCII bases, offsets, thresholds) and device->host results (copies or mapped stores). */
+RB_API int rb_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
+
 /* Packed per-read summary key used by the device API and the bin-sharded combine:
  *   bit 48      hit (some bin passes the threshold)
  *   bits 47..32 max_count

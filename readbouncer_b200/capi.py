@@ -29,7 +29,7 @@ EXPORTS = [
     "rb_ibf_device_words", "rb_ibf_device_kmer_table", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_kernel_launches",
     "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
-    "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins",
+    "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins", "rb_host_pack_info", "rb_transfer_bytes",
 ]
 
 
@@ -107,6 +107,8 @@ def lib():
         "rb_get_l2_fetch_granularity": (i32, [i32, vp]),
         "rb_ibf_enable_kmer_table": (i32, [vp, u64, vp]),
         "rb_ibf_resize_bins": (i32, [vp, u64, vp]),
+        "rb_host_pack_info": (i32, [vp, vp]),
+        "rb_transfer_bytes": (i32, [vp, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -165,6 +167,18 @@ def microbench_gather(d_buf, n_rows, row_bytes, probes_per_thread, n_blocks, d_s
 def microbench_gather_coop(d_buf, n_rows, row_bytes, lane_bytes, probes_per_group, n_blocks, d_sink, stream=None):
     _check(lib().rb_microbench_gather_coop(_dev_ptr(d_buf), n_rows, row_bytes, lane_bytes, probes_per_group, n_blocks,
                                            _dev_ptr(d_sink), _stream_ptr(stream)))
+
+
+def host_pack_info():
+    t, a = C.c_int32(0), C.c_int32(0)
+    _check(lib().rb_host_pack_info(C.byref(t), C.byref(a)))
+    return {"threads": int(t.value), "isa": {0: "scalar", 2: "avx2", 5: "avx512vbmi"}.get(int(a.value), str(a.value))}
+
+
+def transfer_bytes():
+    h, d = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().rb_transfer_bytes(C.byref(h), C.byref(d)))
+    return int(h.value), int(d.value)
 
 
 def set_l2_fetch_granularity(nbytes, device=0):

@@ -1,0 +1,246 @@
+// host_pack.cpp -- see host_pack.hpp.  Compiled by g++ (function-level AVX2, chosen at run time).
+#include "host_pack.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+namespace rb {
+
+namespace {
+
+inline void pack_word_scalar(const uint8_t *p, size_t n, uint32_t &lo, uint32_t &hi, uint32_t &bad)
+{
+    lo = hi = bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t c = p[i], u = c & 0xDFu;
+        if (u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'U') {
+            lo |= ((c >> 1) & 1u) << i;
+            hi |= ((c >> 2) & 1u) << i;
+        } else {
+            bad |= 1u << i;
+        }
+    }
+}
+
+void pack_scalar(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad)
+{
+    const size_t nw = (n + 31) / 32;
+    for (size_t w = 0; w < nw; ++w)
+        pack_word_scalar(bases + 32 * w, std::min<size_t>(32, n - 32 * w), lo[w], hi[w], bad[w]);
+}
+
+#if defined(__x86_64__)
+// Character class by two nibble look-ups (pshufb): low nibble 1/3/7 with high nibble 4/6 = A C G a c g, low nibble
+// 4/5 with high nibble 5/7 = T U t u.  5 vector ops instead of 9 compares and ors.
+__attribute__((target("avx2"))) inline void pack32_avx2(const uint8_t *p, const __m256i lut_lo, const __m256i lut_hi,
+                                                        const __m256i nib, uint32_t &lo, uint32_t &hi, uint32_t &bad)
+{
+    const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+    const __m256i cls = _mm256_and_si256(_mm256_shuffle_epi8(lut_lo, _mm256_and_si256(x, nib)),
+                                         _mm256_shuffle_epi8(lut_hi, _mm256_and_si256(_mm256_srli_epi16(x, 4), nib)));
+    const uint32_t notgood = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(cls, _mm256_setzero_si256()));
+    // movemask takes bit 7 of every byte: shift code bit 1 (resp. 2) of each byte up to it
+    lo = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 6)) & ~notgood;
+    hi = (uint32_t)_mm256_movemask_epi8(_mm256_slli_epi16(x, 5)) & ~notgood;
+    bad = notgood;
+}
+
+__attribute__((target("avx2"))) void pack_avx2(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad)
+{
+    const size_t full = n / 32;
+    // bytes >= 0x80 index the high-nibble table at 8..15 (class 0); pshufb itself zeroes lanes whose index has bit 7
+    // set, which only ever happens for the low-nibble look-up of such bytes -- also class 0
+    const __m256i lut_lo = _mm256_setr_epi8(0, 1, 0, 1, 2, 2, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0,
+                                            0, 1, 0, 1, 2, 2, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i lut_hi = _mm256_setr_epi8(0, 0, 0, 0, 1, 2, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0,
+                                            0, 0, 0, 0, 1, 2, 1, 2, 0, 0, 0, 0, 0, 0, 0, 0);
+    const __m256i nib = _mm256_set1_epi8(0x0F);
+    size_t w = 0;
+    for (; w + 2 <= full; w += 2) {
+        pack32_avx2(bases + 32 * w, lut_lo, lut_hi, nib, lo[w], hi[w], bad[w]);
+        pack32_avx2(bases + 32 * w + 32, lut_lo, lut_hi, nib, lo[w + 1], hi[w + 1], bad[w + 1]);
+    }
+    for (; w < full; ++w) pack32_avx2(bases + 32 * w, lut_lo, lut_hi, nib, lo[w], hi[w], bad[w]);
+    if (n % 32) pack_word_scalar(bases + 32 * full, n % 32, lo[full], hi[full], bad[full]);
+}
+
+// AVX-512 (BW + VBMI): one 128-entry byte look-up (vpermi2b) classifies 64 bases, vptestmb turns code bits into
+// 64-bit masks directly -- no movemask, no shifts.
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const uint8_t *bases, size_t n, uint32_t *lo,
+                                                                        uint32_t *hi, uint32_t *bad)
+{
+    alignas(64) uint8_t tab[128];
+    for (int c = 0; c < 128; ++c) {
+        const int u = c & 0xDF;
+        tab[c] = (u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'U') ? 0xFF : 0x00;
+    }
+    const __m512i t0 = _mm512_load_si512(tab), t1 = _mm512_load_si512(tab + 64);
+    const __m512i c02 = _mm512_set1_epi8(0x02), c04 = _mm512_set1_epi8(0x04);
+    const size_t full = n / 64;
+    for (size_t w = 0; w < full; ++w) {
+        const __m512i x = _mm512_loadu_si512(bases + 64 * w);
+        const __m512i cls = _mm512_permutex2var_epi8(t0, x, t1);              // index = low 7 bits of the byte
+        const __mmask64 good = _mm512_movepi8_mask(cls) & ~_mm512_movepi8_mask(x);   // and the byte is < 0x80
+        const uint64_t l = _mm512_test_epi8_mask(x, c02) & good, h = _mm512_test_epi8_mask(x, c04) & good, b = ~good;
+        std::memcpy(lo + 2 * w, &l, 8);
+        std::memcpy(hi + 2 * w, &h, 8);
+        std::memcpy(bad + 2 * w, &b, 8);
+    }
+    const size_t done = 64 * full, rest = n - done;
+    for (size_t o = 0; o < rest; o += 32)
+        pack_word_scalar(bases + done + o, std::min<size_t>(32, rest - o), lo[2 * full + o / 32], hi[2 * full + o / 32],
+                         bad[2 * full + o / 32]);
+}
+#endif
+
+int detect_isa()     // 0 scalar, 2 AVX2, 5 AVX-512 (BW + VBMI)
+{
+#if defined(__x86_64__)
+    int cap = 5;
+    if (const char *e = std::getenv("RB_HOST_PACK_ISA")) cap = std::atoi(e);
+    if (const char *e = std::getenv("RB_HOST_PACK_SCALAR")) if (e[0] == '1') cap = 0;
+    if (cap >= 5 && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vbmi")) return 5;
+    if (cap >= 2 && __builtin_cpu_supports("avx2")) return 2;
+#endif
+    return 0;
+}
+
+const int g_isa = detect_isa();
+
+// ---- a small pool of spinning-while-busy, sleeping-while-idle threads ---------------------------------
+class Pool {
+public:
+    Pool()
+    {
+        int n = 0;
+        if (const char *e = std::getenv("RB_HOST_THREADS")) n = std::atoi(e);
+        if (n <= 0) n = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        n_workers_ = std::max(0, n - 1);
+        for (int i = 0; i < n_workers_; ++i) threads_.emplace_back([this] { worker(); });
+    }
+    ~Pool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    int size() const { return n_workers_ + 1; }
+
+    void run(size_t n_tasks, const std::function<void(size_t)> &fn, const std::function<void(size_t)> &poll)
+    {
+        std::unique_lock<std::mutex> busy(busy_, std::try_to_lock);
+        if (!busy.owns_lock() || n_workers_ == 0 || n_tasks < 2) {        // pool taken by another call: go alone
+            for (size_t i = 0; i < n_tasks; ++i) { fn(i); if (poll) poll(i + 1); }
+            return;
+        }
+        done_flags_.assign(n_tasks, 0);
+        fn_ = &fn;
+        n_tasks_ = n_tasks;
+        next_.store(0, std::memory_order_relaxed);
+        finished_.store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            ++generation_;
+            job_open_ = true;
+        }
+        cv_.notify_all();
+        size_t prefix = 0;
+        auto advance = [&] {
+            while (prefix < n_tasks && __atomic_load_n(&done_flags_[prefix], __ATOMIC_ACQUIRE)) ++prefix;
+            if (poll) poll(prefix);
+        };
+        for (;;) {
+            const size_t i = next_.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n_tasks) break;
+            fn(i);
+            __atomic_store_n(&done_flags_[i], 1, __ATOMIC_RELEASE);
+            finished_.fetch_add(1, std::memory_order_release);
+            advance();
+        }
+        while (prefix < n_tasks) { advance(); if (prefix < n_tasks) std::this_thread::yield(); }
+        {
+            std::lock_guard<std::mutex> lk(mu_);      // late wakers must not join a job that is over
+            job_open_ = false;
+        }
+        // workers that joined may still be between "no task left" and going idle
+        while (active_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+        fn_ = nullptr;
+    }
+
+private:
+    void worker()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                if (!job_open_) continue;             // woke up after the job had finished
+                active_.fetch_add(1, std::memory_order_acq_rel);
+            }
+            for (;;) {
+                const size_t i = next_.fetch_add(1, std::memory_order_relaxed);
+                if (i >= n_tasks_) break;
+                (*fn_)(i);
+                __atomic_store_n(&done_flags_[i], 1, __ATOMIC_RELEASE);
+                finished_.fetch_add(1, std::memory_order_release);
+            }
+            active_.fetch_sub(1, std::memory_order_acq_rel);
+        }
+    }
+
+    int n_workers_ = 0;
+    std::vector<std::thread> threads_;
+    std::mutex mu_, busy_;
+    std::condition_variable cv_;
+    bool stop_ = false, job_open_ = false;
+    uint64_t generation_ = 0;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t n_tasks_ = 0;
+    std::vector<char> done_flags_;
+    std::atomic<size_t> next_{0}, finished_{0};
+    std::atomic<int> active_{0};
+};
+
+Pool &pool()
+{
+    static Pool *p = new Pool();      // leaked on purpose: worker threads must not be joined from a static destructor
+    return *p;
+}
+
+}  // namespace
+
+void pack_bases(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad)
+{
+#if defined(__x86_64__)
+    if (g_isa == 5) { pack_avx512(bases, n, lo, hi, bad); return; }
+    if (g_isa == 2) { pack_avx2(bases, n, lo, hi, bad); return; }
+#endif
+    pack_scalar(bases, n, lo, hi, bad);
+}
+
+int pack_isa() { return g_isa; }
+
+void parallel_tasks(size_t n_tasks, const std::function<void(size_t)> &fn, const std::function<void(size_t)> &poll)
+{
+    pool().run(n_tasks, fn, poll);
+}
+
+int host_threads() { return pool().size(); }
+
+}  // namespace rb

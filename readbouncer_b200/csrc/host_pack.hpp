@@ -1,0 +1,31 @@
+// host_pack.hpp -- host side of the packed read transfer (internal to the library).
+//
+// The host-buffer classify call (rb_ibf_count_batch) is bound by PCIe when it ships ASCII bases
+// (8 bits per base).  The group-per-read window-table kernel needs the reads as three bit planes anyway
+// (low code bit, high code bit, "not ACGT"), so the host makes those planes -- 3 bits per base -- with
+// AVX-512 or AVX2 (64 or 32 bases per iteration) on a small pool of threads, straight into pinned staging memory.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+
+namespace rb {
+
+// Planes of bases[0, n): bit i of lo/hi/bad = base i.  Codes (ascii >> 1) & 3 = A0 C1 T2 G3, U/u = T;
+// every other character is "bad" (Dna5 rank 4) with code bits 0.  n need not be a multiple of 32: the last
+// word is zero padded.  Writes ceil(n / 32) words per plane.
+void pack_bases(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad);
+
+// Instruction set of the packer in use: 0 scalar, 2 AVX2, 5 AVX-512 BW+VBMI (reported by rb_host_pack_info;
+// env RB_HOST_PACK_ISA caps it).
+int pack_isa();
+
+// Runs fn(task) for task in [0, n_tasks) on the library's host threads plus the caller; `poll` is called by the
+// CALLER between its own tasks and while waiting (it submits finished pieces to the GPU) and receives the number of
+// leading tasks known complete.  Falls back to the caller alone when the pool is busy with another call.
+void parallel_tasks(size_t n_tasks, const std::function<void(size_t)> &fn, const std::function<void(size_t)> &poll);
+
+int host_threads();   // pool size + 1 (the caller)
+
+}  // namespace rb

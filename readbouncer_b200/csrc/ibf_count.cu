@@ -343,6 +343,24 @@ __global__ void keys_decode_kernel(const uint64_t *__restrict__ keys, uint64_t n
     }
 }
 
+// Piece of a batch -> the caller's batch-shaped result arrays: keys [n_lut][n] of reads [out_off, out_off+n) go to
+// out[t * stride + out_off + i].  The outputs may be mapped pinned host memory (zero-copy results: consecutive
+// threads write consecutive elements, so the stores leave the GPU as full PCIe write bursts).
+__global__ void keys_decode_piece_kernel(const uint64_t *__restrict__ keys, const uint8_t *__restrict__ flag_in, uint64_t n,
+                                         uint32_t n_lut, uint64_t stride, uint64_t out_off, uint16_t *max_count,
+                                         uint8_t *hit, uint32_t *argmax_bin, uint8_t *flag_out)
+{
+    const uint64_t total = n * n_lut;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = j / n, i = j - t * n, o = t * stride + out_off + i;
+        const uint64_t key = keys[j];
+        if (max_count) max_count[o] = (uint16_t)((key >> 32) & 0xFFFFu);
+        if (hit) hit[o] = (uint8_t)((key >> 48) & 1u);
+        if (argmax_bin) argmax_bin[o] = key ? ~(uint32_t)(key & 0xFFFFFFFFu) : 0xFFFFFFFFu;
+        if (t == 0 && flag_out) flag_out[out_off + i] = flag_in[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
@@ -453,6 +471,18 @@ int launch_keys_decode(const uint64_t *keys, uint64_t n, uint16_t *max_count, ui
     uint64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     keys_decode_kernel<<<(uint32_t)blocks, 256, 0, st>>>(keys, n, max_count, hit, argmax_bin);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_keys_decode_piece(const uint64_t *keys, const uint8_t *flag_in, uint64_t n, uint32_t n_lut, uint64_t stride,
+                             uint64_t out_off, uint16_t *max_count, uint8_t *hit, uint32_t *argmax_bin, uint8_t *flag_out,
+                             cudaStream_t st)
+{
+    if (n == 0) return 0;
+    uint64_t blocks = (n * n_lut + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    keys_decode_piece_kernel<<<(uint32_t)blocks, 256, 0, st>>>(keys, flag_in, n, n_lut, stride, out_off, max_count, hit,
+                                                             argmax_bin, flag_out);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

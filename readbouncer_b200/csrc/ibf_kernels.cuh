@@ -25,6 +25,10 @@ struct CountArgs {
     uint16_t *counts_fwd;       // [n_reads][n_bins_local] or null
     uint16_t *counts_rev;
     uint8_t *read_flag;         // [n_reads] or null
+    // optional: the bases as three bit streams made by the host packer (rb_pack.hpp); bit i = base pk_base0 + i
+    // of the `bases` coordinate system that read_off uses.  Only the group-per-read window-table kernel reads them.
+    const uint32_t *pk_lo, *pk_hi, *pk_bad;
+    uint64_t pk_base0;
 };
 
 struct InsertArgs {
@@ -51,9 +55,14 @@ bool wtable_geometry(uint64_t stride, uint32_t k, int span, int *lanes, int *can
 int launch_wtable_build(const FilterView &fv, uint64_t *table, int span, int sm_count, cudaStream_t st);
 int launch_count_wtable(const CountArgs &a, const uint64_t *table, int span, uint32_t max_read_len, int sm_count,
                         cudaStream_t st);
+bool wgroup_applicable(uint32_t k, int span, uint32_t max_read_len);
+int get_wtable_variant();
 void set_wtable_variant(int v);   // 0 auto (group-per-read kernel for short reads), 1 always warp-per-read
 int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cudaStream_t st);
 int launch_keys_decode(const uint64_t *keys, uint64_t n, uint16_t *max_count, uint8_t *hit,
                        uint32_t *argmax_bin, cudaStream_t st);
+int launch_keys_decode_piece(const uint64_t *keys, const uint8_t *flag_in, uint64_t n, uint32_t n_lut, uint64_t stride,
+                             uint64_t out_off, uint16_t *max_count, uint8_t *hit, uint32_t *argmax_bin, uint8_t *flag_out,
+                             cudaStream_t st);
 
 }  // namespace rb

@@ -368,8 +368,9 @@ count_wtable_kernel(const CountArgs a, const uint64_t *__restrict__ table)
 // 16-bit word per block and plane (low code bit, high code bit, "not ACGT") with SWAR arithmetic, and
 // kept in shared memory as three bit streams; a block of 8 consecutive entries takes its windows from
 // 64-bit pieces of those streams with compile-time shifts.
-constexpr int kWgMaxBlocks = 36;                 // 16-byte blocks per read: reads of <= 561 bases
-constexpr int kWgRow = kWgMaxBlocks + 8;         // + zero padding read by the last window block
+constexpr int kWgMaxBlocks = 36;                 // 16-base stream units per read (576 bits per plane)
+constexpr int kWgMaxLen = 16 * kWgMaxBlocks - 31;   // longest read: the start can sit 31 bits into its first stream word
+constexpr int kWgRow = kWgMaxBlocks + 12;        // + zero padding read by the last window block
 constexpr int kWgIB = 8;                         // entries per window block
 constexpr int kWgPlanes = 7;                     // per-lane counters hold 0..127
 
@@ -384,6 +385,43 @@ __device__ __forceinline__ void swar4(uint32_t x, uint32_t &lo4, uint32_t &hi4, 
     const uint32_t sel = __byte_perm(y | (y >> 4), 0u, 0x4420);   // code nibbles c0 c1 c2 c3 in the low 16 bits
     const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);    // 'A' 'C' 'T' 'G' by code
     bad = ((x & 0xDFDFDFDFu) != expect) ? 0xFu : 0u;
+}
+
+// hashing path from the bit streams of a PACKED read (host-made planes: "bad" is exact per base and every bad
+// base is Dna5 rank 4, because the packer codes U as T): k-mer starting at stream bit `bit0`
+template <int WT>
+__device__ __noinline__ SlotWords<WT> slot_hashed_streams(const FilterView &fv, const uint32_t *lo, const uint32_t *hi,
+                                                          const uint32_t *bad, uint32_t bit0)
+{
+    SlotWords<WT> out;
+    const HashParams &hp = fv.hp;
+    uint64_t Hf = 0, Hr = 0, pw = 1;
+    for (uint32_t u = 0; u < hp.k; ++u) {
+        const uint32_t b = bit0 + u, w = b >> 5, sft = b & 31u;
+        const uint32_t c = (((hi[w] >> sft) & 1u) << 1) | ((lo[w] >> sft) & 1u);
+        const uint32_t d = ((bad[w] >> sft) & 1u) ? 4u : rank_of_code(c);
+        Hf = Hf * 5 + d;
+        Hr += comp5(d) * pw;
+        pw *= 5;
+    }
+    uint64_t mf[WT], mr[WT];
+#pragma unroll
+    for (int w = 0; w < WT; ++w) { mf[w] = ~0ULL; mr[w] = ~0ULL; }
+#pragma unroll 1
+    for (uint32_t i = 0; i < hp.n_hash; ++i) {
+        const uint64_t *pf = fv.words + hash_row(Hf, hp.pre[i], hp.n_blocks, hp.magic) * fv.stride;
+        const uint64_t *pr = fv.words + hash_row(Hr, hp.pre[i], hp.n_blocks, hp.magic) * fv.stride;
+#pragma unroll
+        for (int w = 0; w < WT; ++w) { mf[w] &= __ldg(pf + w); mr[w] &= __ldg(pr + w); }
+    }
+#pragma unroll
+    for (int w = 0; w < WT; ++w) {
+        out.v[2 * w] = (uint32_t)mf[w];
+        out.v[2 * w + 1] = (uint32_t)(mf[w] >> 32);
+        out.v[2 * WT + 2 * w] = (uint32_t)mr[w];
+        out.v[2 * WT + 2 * w + 1] = (uint32_t)(mr[w] >> 32);
+    }
+    return out;
 }
 
 template <int NP>
@@ -464,7 +502,9 @@ __device__ __forceinline__ void group_epilogue(const CountArgs &a, uint64_t read
     }
 }
 
-template <int WT, int S, int G, bool CANON>
+// PACKED: the bases arrive as the three bit streams already (a.pk_*, made by the host packer of the
+// host-buffer API: 3 bits per base over PCIe instead of 8), bit i of the streams = base a.pk_base0 + i.
+template <int WT, int S, int G, bool CANON, bool PACKED>
 __global__ void __launch_bounds__(kTileWarps * 32, 2)
 count_wgroup_kernel(const CountArgs a, const uint64_t *__restrict__ table)
 {
@@ -493,28 +533,41 @@ count_wgroup_kernel(const CountArgs a, const uint64_t *__restrict__ table)
         uint64_t off = 0, len = 0;
         if (active) { off = a.read_off[read]; len = a.read_off[read + 1] - off; }
         uint32_t flag = read_flag_of(len, k);
-        const uint8_t *const pr = a.bases + off;
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(pr) & 15u);
+        const uint8_t *const pr = PACKED ? nullptr : a.bases + off;
+        const uint64_t rel = PACKED ? off - a.pk_base0 : 0;                      // first base of the read in the streams
+        const uint32_t sh = PACKED ? (uint32_t)(rel & 31u) : (uint32_t)(reinterpret_cast<uintptr_t>(pr) & 15u);
         // a read longer than the caller's max_read_len promised does not fit this kernel's counters: flag 3
-        if (flag == 0 && (len - k + 1 > (uint64_t)S * ((1u << NPL) - 1u) || sh + len > 16u * kWgMaxBlocks)) flag = 3;
+        if (flag == 0 && (len - k + 1 > (uint64_t)S * ((1u << NPL) - 1u) || len > (uint64_t)kWgMaxLen)) flag = 3;
         if (t == 0 && active && a.read_flag) a.read_flag[read] = (uint8_t)flag;
         const uint32_t npos = (active && flag == 0) ? (uint32_t)len - k + 1 : 0u;
-        const uint4 *const pa = reinterpret_cast<const uint4 *>(pr - sh);
-        const uint32_t nblk = npos ? (sh + (uint32_t)len + 15u) >> 4 : 0u;
 
         // ---- bases -> bit streams ------------------------------------------------------------------
         __syncwarp();
-        for (uint32_t j = t; j < nblk + 8; j += G) {
-            uint32_t lo16 = 0, hi16 = 0, bad16 = 0;
-            if (j < nblk) {
-                const uint4 v = __ldg(pa + j);
-                uint32_t l, h, b;
-                swar4(v.x, l, h, b); lo16 = l; hi16 = h; bad16 = b;
-                swar4(v.y, l, h, b); lo16 |= l << 4; hi16 |= h << 4; bad16 |= b << 4;
-                swar4(v.z, l, h, b); lo16 |= l << 8; hi16 |= h << 8; bad16 |= b << 8;
-                swar4(v.w, l, h, b); lo16 |= l << 12; hi16 |= h << 12; bad16 |= b << 12;
+        if constexpr (PACKED) {
+            const uint32_t nw = npos ? (sh + (uint32_t)len + 31u) >> 5 : 0u;
+            const uint64_t w0 = rel >> 5;
+            uint32_t *const d_lo = reinterpret_cast<uint32_t *>(st_lo), *const d_hi = reinterpret_cast<uint32_t *>(st_hi),
+                           *const d_bad = reinterpret_cast<uint32_t *>(st_bad);
+            for (uint32_t j = t; j < nw + 4; j += G) {
+                uint32_t l = 0, h = 0, b = 0;
+                if (j < nw) { l = __ldg(a.pk_lo + w0 + j); h = __ldg(a.pk_hi + w0 + j); b = __ldg(a.pk_bad + w0 + j); }
+                d_lo[j] = l; d_hi[j] = h; d_bad[j] = b;
             }
-            st_lo[j] = (uint16_t)lo16; st_hi[j] = (uint16_t)hi16; st_bad[j] = (uint16_t)bad16;
+        } else {
+            const uint4 *const pa = reinterpret_cast<const uint4 *>(pr - sh);
+            const uint32_t nblk = npos ? (sh + (uint32_t)len + 15u) >> 4 : 0u;
+            for (uint32_t j = t; j < nblk + 8; j += G) {
+                uint32_t lo16 = 0, hi16 = 0, bad16 = 0;
+                if (j < nblk) {
+                    const uint4 v = __ldg(pa + j);
+                    uint32_t l, h, b;
+                    swar4(v.x, l, h, b); lo16 = l; hi16 = h; bad16 = b;
+                    swar4(v.y, l, h, b); lo16 |= l << 4; hi16 |= h << 4; bad16 |= b << 4;
+                    swar4(v.z, l, h, b); lo16 |= l << 8; hi16 |= h << 8; bad16 |= b << 8;
+                    swar4(v.w, l, h, b); lo16 |= l << 12; hi16 |= h << 12; bad16 |= b << 12;
+                }
+                st_lo[j] = (uint16_t)lo16; st_hi[j] = (uint16_t)hi16; st_bad[j] = (uint16_t)bad16;
+            }
         }
         __syncwarp();
 
@@ -576,7 +629,13 @@ count_wgroup_kernel(const CountArgs a, const uint64_t *__restrict__ table)
                                 load_slot<WT>(my_table + (size_t)idx * (G * 2 * WT), m[u]);
                                 flip[u] = fl;
                             } else {
-                                const SlotWords<WT> hs = slot_hashed<WT>(a.fv, pr + pos);
+                                SlotWords<WT> hs;
+                                if constexpr (PACKED)
+                                    hs = slot_hashed_streams<WT>(a.fv, reinterpret_cast<const uint32_t *>(st_lo),
+                                                                 reinterpret_cast<const uint32_t *>(st_hi),
+                                                                 reinterpret_cast<const uint32_t *>(st_bad), sh + pos);
+                                else
+                                    hs = slot_hashed<WT>(a.fv, pr + pos);
 #pragma unroll
                                 for (int w = 0; w < NWP; ++w) m[u][w] = hs.v[w];
                             }
@@ -681,30 +740,32 @@ void launch_count_one(const CountArgs &a, const uint64_t *table, int sm_count, c
     count_wtable_kernel<WT, S, G, CANON, NPA><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }
 
-template <int WT, int S, int G, bool CANON>
+template <int WT, int S, int G, bool CANON, bool PACKED>
 void launch_count_group(const CountArgs &a, const uint64_t *table, int sm_count, cudaStream_t st)
 {
     static int occ = 0;
     if (occ == 0) {
         int o = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, count_wgroup_kernel<WT, S, G, CANON>, kTileWarps * 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, count_wgroup_kernel<WT, S, G, CANON, PACKED>, kTileWarps * 32, 0);
         occ = o > 0 ? o : 1;
     }
     constexpr uint64_t reads_per_cta = (uint64_t)kTileWarps * (32 / G);
     const uint64_t blocks_needed = (a.n_reads + reads_per_cta - 1) / reads_per_cta;
     const uint64_t max_x = (uint64_t)sm_count * occ;
     const uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
-    count_wgroup_kernel<WT, S, G, CANON><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
+    count_wgroup_kernel<WT, S, G, CANON, PACKED><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }
 
 template <int WT, int S, int G, bool CANON>
 void launch_count_np(const CountArgs &a, const uint64_t *table, uint32_t max_read_len, int sm_count, cudaStream_t st)
 {
     // short reads (every 250-base chunk): one read per group of G lanes
-    const uint32_t k = a.fv.hp.k;
-    if (max_read_len != 0 && max_read_len <= 16u * kWgMaxBlocks - 15u &&
-        (max_read_len < k || max_read_len - k + 1 <= (uint32_t)S * ((1u << kWgPlanes) - 1u)) && g_wtable_variant != 1) {
-        launch_count_group<WT, S, G, CANON>(a, table, sm_count, st);
+    if (a.pk_lo) {                                   // bit streams from the host packer: the caller checked the limits
+        launch_count_group<WT, S, G, CANON, true>(a, table, sm_count, st);
+        return;
+    }
+    if (wgroup_applicable(a.fv.hp.k, S, max_read_len) && g_wtable_variant != 1) {
+        launch_count_group<WT, S, G, CANON, false>(a, table, sm_count, st);
         return;
     }
     const bool single = max_read_len != 0 && max_read_len < a.fv.hp.k + (uint32_t)WtShape<S, G>::PIECE;
@@ -730,6 +791,14 @@ bool wtable_geometry(uint64_t stride, uint32_t k, int span, int *lanes, int *can
 }
 
 void set_wtable_variant(int v) { g_wtable_variant = v; }
+int get_wtable_variant() { return g_wtable_variant; }
+
+// reads of a launch fit the group-per-read kernel: known longest read, <= 127*span positions, <= kWgMaxLen bases
+bool wgroup_applicable(uint32_t k, int span, uint32_t max_read_len)
+{
+    return max_read_len != 0 && max_read_len <= (uint32_t)kWgMaxLen &&
+           (max_read_len < k || max_read_len - k + 1 <= (uint32_t)span * ((1u << kWgPlanes) - 1u));
+}
 
 #define RB_WT_DISPATCH(FN, ...)                                                                              \
     do {                                                                                                     \

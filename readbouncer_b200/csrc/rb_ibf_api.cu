@@ -7,7 +7,9 @@
 // every compute entry point fails with RB_ERR_NO_DEVICE when no CUDA device is usable.
 #include "../../include/rb_ibf.h"
 #include "ibf_kernels.cuh"
+#include "host_pack.hpp"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <mutex>
@@ -22,6 +24,7 @@ namespace {
 
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};     // moved by rb_ibf_count_batch (copies and mapped result stores)
 std::atomic<int> g_count_kernel{0};
 
 int fail(int status, const std::string &msg)
@@ -69,6 +72,9 @@ struct rb_ibf {
     mutable uint64_t table_bytes = 0;
     mutable bool table_tried = false;
     mutable uint64_t table_budget = 0;      // 0 = automatic
+    // streams, events and staging buffers of rb_ibf_count_batch, kept between calls (one set per concurrent caller)
+    mutable std::mutex ctx_mu;
+    mutable std::vector<struct CallCtx *> ctx_free;
 };
 
 namespace {
@@ -165,9 +171,12 @@ int alloc_device(rb_ibf *f, bool zero)
     return RB_OK;
 }
 
+void free_call_contexts(rb_ibf *f);
+
 void destroy(rb_ibf *f)
 {
     if (!f) return;
+    free_call_contexts(f);
     if (f->d_words || f->d_err || f->d_table) {
         DeviceGuard g(f->device);
         if (f->d_words) cudaFree(f->d_words);
@@ -328,6 +337,315 @@ struct L2Window {
         cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
     }
 };
+
+
+// ---- host-buffer classify call: pieces, slots, packed transfer ---------------------------------------------
+// The batch is cut into pieces of ~8 MB of bases that flow through kSlots streams: while piece i is
+// classified, piece i+1 is copied in and piece i-1's results leave.  Two ways in:
+//   packed  every read of the piece fits the group-per-read window-table kernel: the host threads turn the ASCII
+//           bases into the three bit planes that kernel works on (host_pack.hpp) in pinned staging memory, and only
+//           those 3 bits per base cross PCIe;
+//   ascii   anything else: the piece's bases are copied as they are.
+// Two ways out: result arrays in pinned (or registered) host memory are written by the decode kernel directly
+// (mapped, coalesced stores); otherwise results gather in a device buffer and are copied at the end.
+constexpr int kSlots = 4;
+constexpr uint64_t kPieceBases = 8ull << 20, kPieceReads = 1ull << 17;
+constexpr uint64_t kPackTask = 128ull << 10;            // bases per packing task (a multiple of 32)
+constexpr uint64_t kStageBases = 512ull << 20;          // bases per round of the packed pipeline (192 MB of planes)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return RB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        RB_CUDA(cudaMalloc(&p, want));
+        cap = want;
+        return RB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return RB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        RB_CUDA(cudaMallocHost(&p, want));
+        cap = want;
+        return RB_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct CallCtx {
+    bool ok = false;
+    cudaStream_t st[kSlots] = {};
+    cudaEvent_t done[kSlots] = {};
+    cudaEvent_t ev_start = nullptr;
+    DevBuf d_off[kSlots], d_keys[kSlots], d_flag[kSlots], d_in[kSlots], d_cf[kSlots], d_cr[kSlots];
+    DevBuf d_lut, d_planes, d_res;
+    HostBuf h_planes;
+    std::vector<uint16_t> lut_host;          // what d_lut holds
+    int init()
+    {
+        for (int s = 0; s < kSlots; ++s) {
+            RB_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+            RB_CUDA(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
+        }
+        RB_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        ok = true;
+        return RB_OK;
+    }
+    ~CallCtx()
+    {
+        for (int s = 0; s < kSlots; ++s) {
+            if (st[s]) { cudaStreamSynchronize(st[s]); cudaStreamDestroy(st[s]); }
+            if (done[s]) cudaEventDestroy(done[s]);
+            d_off[s].release(); d_keys[s].release(); d_flag[s].release(); d_in[s].release(); d_cf[s].release(); d_cr[s].release();
+        }
+        if (ev_start) cudaEventDestroy(ev_start);
+        d_lut.release(); d_planes.release(); d_res.release(); h_planes.release();
+        cudaGetLastError();
+    }
+};
+
+namespace {
+
+CallCtx *acquire_ctx(const rb_ibf *f)
+{
+    {
+        std::lock_guard<std::mutex> lock(f->ctx_mu);
+        if (!f->ctx_free.empty()) {
+            CallCtx *c = f->ctx_free.back();
+            f->ctx_free.pop_back();
+            return c;
+        }
+    }
+    CallCtx *c = new CallCtx();
+    if (c->init() != RB_OK) { delete c; cudaGetLastError(); return nullptr; }
+    return c;
+}
+
+void release_ctx(const rb_ibf *f, CallCtx *c)
+{
+    std::lock_guard<std::mutex> lock(f->ctx_mu);
+    f->ctx_free.push_back(c);
+}
+
+void free_call_contexts(rb_ibf *f)
+{
+    std::lock_guard<std::mutex> lock(f->ctx_mu);
+    if (f->ctx_free.empty()) return;
+    DeviceGuard g(f->device);
+    for (CallCtx *c : f->ctx_free) delete c;
+    f->ctx_free.clear();
+}
+
+// device-visible address of a host result array if it is pinned / registered, else null
+template <typename T>
+T *mapped_ptr(T *host)
+{
+    if (!host) return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return static_cast<T *>(at.devicePointer);
+}
+
+int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads,
+                    const uint16_t *thr_lut, uint32_t n_lut, uint16_t *counts_fwd, uint16_t *counts_rev,
+                    uint16_t *max_count, uint8_t *hit, uint32_t *argmax_bin, uint8_t *read_flag, cudaStream_t user)
+{
+    const bool dense = counts_fwd || counts_rev;
+    const uint64_t nbl = f->n_bins_local;
+    const uint64_t piece_reads_cap = dense ? std::max<uint64_t>(1, std::min<uint64_t>(kPieceReads, (64ull << 20) / (2 * nbl)))
+                                           : kPieceReads;
+    // ---- pieces: ~kPieceBases bases or piece_reads_cap reads, whichever comes first (binary search: offsets are sorted;
+    //      every piece is checked for that when it is submitted) -------------------------------------------------------
+    std::vector<uint64_t> cut{0};
+    while (cut.back() < n_reads) {
+        const uint64_t r0 = cut.back();
+        const uint64_t rmax = std::min<uint64_t>(n_reads, r0 + piece_reads_cap);
+        const uint64_t *lo = read_off + r0 + 1, *hi = read_off + rmax;
+        const uint64_t *it = std::lower_bound(lo, hi, read_off[r0] + kPieceBases);     // first read END >= r0 + piece bases
+        cut.push_back(std::min<uint64_t>(rmax, (uint64_t)(it - read_off)));
+        if (cut.back() <= r0) cut.back() = r0 + 1;
+    }
+    const size_t n_pieces = cut.size() - 1;
+
+    // ---- which way in ----------------------------------------------------------------------------------------------------
+    const int which = g_count_kernel.load();
+    const uint64_t *table = nullptr;
+    if (which == 0 || which >= 3) table = ensure_table(f, user, which >= 3, n_reads);
+    if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
+    bool packed_ok = table && f->table_span >= 2 && !dense && (which == 0 || which == 3);
+    if (const char *e = std::getenv("RB_HOST_PACK")) if (e[0] == '0') packed_ok = false;
+
+    // ---- which way out ---------------------------------------------------------------------------------------------------
+    uint16_t *m_max = mapped_ptr(max_count);
+    uint8_t *m_hit = mapped_ptr(hit), *m_flag = mapped_ptr(read_flag);
+    uint32_t *m_amax = mapped_ptr(argmax_bin);
+    const bool zero_copy = (!max_count || m_max) && (!hit || m_hit) && (!argmax_bin || m_amax) && (!read_flag || m_flag);
+    const uint64_t nk_all = (uint64_t)n_lut * n_reads;
+    if (!zero_copy) {        // device staging in the caller's layout: argmax | max | hit | flag
+        int s2 = ctx->d_res.reserve(nk_all * 7 + n_reads + 64);
+        if (s2 != RB_OK) return s2;
+        uint8_t *b = static_cast<uint8_t *>(ctx->d_res.p);
+        m_amax = argmax_bin ? reinterpret_cast<uint32_t *>(b) : nullptr;
+        m_max = max_count ? reinterpret_cast<uint16_t *>(b + nk_all * 4) : nullptr;
+        m_hit = hit ? b + nk_all * 6 : nullptr;
+        m_flag = read_flag ? b + nk_all * 7 : nullptr;
+    }
+
+    auto body = [&]() -> int {
+        // thresholds: uploaded only when they changed since the last call of this context
+        const size_t lut_elems = (size_t)n_lut * rb::kLutSize;
+        if (ctx->lut_host.size() != lut_elems || std::memcmp(ctx->lut_host.data(), thr_lut, lut_elems * 2) != 0) {
+            int s2 = ctx->d_lut.reserve(lut_elems * 2);
+            if (s2 != RB_OK) return s2;
+            ctx->lut_host.assign(thr_lut, thr_lut + lut_elems);
+            RB_CUDA(cudaMemcpyAsync(ctx->d_lut.p, ctx->lut_host.data(), lut_elems * 2, cudaMemcpyHostToDevice, user));
+            g_h2d_bytes += lut_elems * 2;
+        }
+        RB_CUDA(cudaEventRecord(ctx->ev_start, user));          // slot streams start after the caller's stream
+        for (int s = 0; s < kSlots; ++s) RB_CUDA(cudaStreamWaitEvent(ctx->st[s], ctx->ev_start, 0));
+
+        // one piece: offsets in, classify (packed planes already on their way, or ASCII bases copied here), results out
+        auto submit = [&](size_t p, const uint32_t *d_lo, const uint32_t *d_hi, const uint32_t *d_bad, uint64_t base0) -> int {
+            const int s = (int)(p % kSlots);
+            cudaStream_t sst = ctx->st[s];
+            const uint64_t r0 = cut[p], r1 = cut[p + 1], n = r1 - r0;
+            uint64_t piece_max = 0;
+            for (uint64_t i = r0; i < r1; ++i) piece_max = std::max(piece_max, read_off[i + 1] - read_off[i]);
+            if (piece_max >> 63) return fail(RB_ERR_INVALID_ARG, "read offsets must be non-decreasing");
+            const uint64_t b0 = read_off[r0], nb = read_off[r1] - b0;
+            const uint32_t max_len32 = (uint32_t)std::min<uint64_t>(piece_max, 0xFFFFFFFFu);
+            const bool packed = d_lo && rb::wgroup_applicable((uint32_t)f->k, f->table_span, max_len32);
+            int s2;
+            if ((s2 = ctx->d_off[s].reserve((n + 1) * 8)) != RB_OK) return s2;
+            if ((s2 = ctx->d_keys[s].reserve((uint64_t)n_lut * n * 8)) != RB_OK) return s2;
+            if ((s2 = ctx->d_flag[s].reserve(n)) != RB_OK) return s2;
+            RB_CUDA(cudaMemcpyAsync(ctx->d_off[s].p, read_off + r0, (n + 1) * 8, cudaMemcpyHostToDevice, sst));
+            g_h2d_bytes += (n + 1) * 8;
+            rb::CountArgs a{};
+            a.fv = view_of(f);
+            a.read_off = static_cast<const uint64_t *>(ctx->d_off[s].p);
+            a.n_reads = n; a.lut = static_cast<const uint16_t *>(ctx->d_lut.p); a.n_lut = n_lut;
+            a.keys = static_cast<uint64_t *>(ctx->d_keys[s].p);
+            a.read_flag = static_cast<uint8_t *>(ctx->d_flag[s].p);
+            if (packed) {
+                a.pk_lo = d_lo; a.pk_hi = d_hi; a.pk_bad = d_bad; a.pk_base0 = base0;
+                int nl = rb::launch_count_wtable(a, table, f->table_span, max_len32, f->sm_count, sst);
+                if (nl < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+                g_launches += (uint64_t)nl;
+            } else {
+                if ((s2 = ctx->d_in[s].reserve(nb ? nb : 1)) != RB_OK) return s2;
+                RB_CUDA(cudaMemcpyAsync(ctx->d_in[s].p, bases + b0, nb, cudaMemcpyHostToDevice, sst));
+                g_h2d_bytes += nb;
+                uint16_t *d_cf = nullptr, *d_cr = nullptr;
+                if (counts_fwd) { if ((s2 = ctx->d_cf[s].reserve(n * nbl * 2)) != RB_OK) return s2; d_cf = static_cast<uint16_t *>(ctx->d_cf[s].p); }
+                if (counts_rev) { if ((s2 = ctx->d_cr[s].reserve(n * nbl * 2)) != RB_OK) return s2; d_cr = static_cast<uint16_t *>(ctx->d_cr[s].p); }
+                // offsets stay absolute: bias the base pointer instead of rewriting them
+                const uint8_t *biased = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(ctx->d_in[s].p) - (uintptr_t)b0);
+                s2 = rb_ibf_count_batch_dev(f, biased, a.read_off, n, max_len32, a.lut, n_lut, a.keys, d_cf, d_cr, a.read_flag, sst);
+                if (s2 != RB_OK) return s2;
+                if (counts_fwd) RB_CUDA(cudaMemcpyAsync(counts_fwd + r0 * nbl, d_cf, n * nbl * 2, cudaMemcpyDeviceToHost, sst));
+                if (counts_rev) RB_CUDA(cudaMemcpyAsync(counts_rev + r0 * nbl, d_cr, n * nbl * 2, cudaMemcpyDeviceToHost, sst));
+            }
+            int nl = rb::launch_keys_decode_piece(a.keys, a.read_flag, n, n_lut, n_reads, r0, m_max, m_hit, m_amax, m_flag, sst);
+            if (nl < 0) return fail(RB_ERR_CUDA, "decode launch failed");
+            g_launches += (uint64_t)nl;
+            return RB_OK;
+        };
+
+        if (!packed_ok) {
+            for (size_t p = 0; p < n_pieces; ++p) { int s2 = submit(p, nullptr, nullptr, nullptr, 0); if (s2 != RB_OK) return s2; }
+        } else {
+            // rounds of at most kStageBases bases; inside a round the host threads pack 128 K-base tasks in order and the
+            // calling thread submits every piece as soon as the tasks covering it are done
+            size_t p_begin = 0;
+            while (p_begin < n_pieces) {
+                size_t p_end = p_begin + 1;
+                const uint64_t B0 = read_off[cut[p_begin]];
+                while (p_end < n_pieces && read_off[cut[p_end + 1]] - B0 <= kStageBases) ++p_end;
+                const uint64_t NB = read_off[cut[p_end]] - B0;                 // bases of this round
+                const uint64_t NW = (NB + 31) / 32 + 8;                         // words per plane (+ slack for the kernel's tail reads)
+                int s2;
+                if ((s2 = ctx->h_planes.reserve(NW * 12)) != RB_OK) return s2;
+                if ((s2 = ctx->d_planes.reserve(NW * 12)) != RB_OK) return s2;
+                uint32_t *h_lo = static_cast<uint32_t *>(ctx->h_planes.p), *h_hi = h_lo + NW, *h_bad = h_hi + NW;
+                uint32_t *d_lo = static_cast<uint32_t *>(ctx->d_planes.p), *d_hi = d_lo + NW, *d_bad = d_hi + NW;
+                const size_t n_tasks = (size_t)((NB + kPackTask - 1) / kPackTask);
+                size_t next_piece = p_begin;
+                int err = RB_OK;
+                auto pack_task = [&](size_t t) {
+                    const uint64_t o = (uint64_t)t * kPackTask, m = std::min<uint64_t>(kPackTask, NB - o);
+                    rb::pack_bases(bases + B0 + o, m, h_lo + o / 32, h_hi + o / 32, h_bad + o / 32);
+                };
+                auto poll = [&](size_t tasks_done) {
+                    while (err == RB_OK && next_piece < p_end) {
+                        const uint64_t e_base = read_off[cut[next_piece + 1]] - B0;            // one past the piece's last base
+                        const size_t need = (size_t)((e_base + kPackTask - 1) / kPackTask);   // tasks that must be complete
+                        if (tasks_done < std::min(need, n_tasks)) break;
+                        const uint64_t w_lo = (read_off[cut[next_piece]] - B0) / 32, w_hi = (e_base + 31) / 32;
+                        cudaStream_t sst = ctx->st[next_piece % kSlots];
+                        cudaError_t ce = cudaSuccess;
+                        if (w_hi > w_lo) {
+                            ce = cudaMemcpyAsync(d_lo + w_lo, h_lo + w_lo, (w_hi - w_lo) * 4, cudaMemcpyHostToDevice, sst);
+                            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_hi + w_lo, h_hi + w_lo, (w_hi - w_lo) * 4, cudaMemcpyHostToDevice, sst);
+                            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_bad + w_lo, h_bad + w_lo, (w_hi - w_lo) * 4, cudaMemcpyHostToDevice, sst);
+                        }
+                        if (ce != cudaSuccess) { err = fail(RB_ERR_CUDA, std::string("plane copy: ") + cudaGetErrorString(ce)); break; }
+                        g_h2d_bytes += (w_hi - w_lo) * 12;
+                        err = submit(next_piece, d_lo, d_hi, d_bad, B0);
+                        ++next_piece;
+                    }
+                };
+                rb::parallel_tasks(n_tasks, pack_task, poll);
+                poll(n_tasks);
+                if (err != RB_OK) return err;
+                if (p_end < n_pieces) {            // the staging planes are reused by the next round
+                    for (int s = 0; s < kSlots; ++s) RB_CUDA(cudaStreamSynchronize(ctx->st[s]));
+                }
+                p_begin = p_end;
+            }
+        }
+        for (int s = 0; s < kSlots; ++s) {
+            RB_CUDA(cudaEventRecord(ctx->done[s], ctx->st[s]));
+            RB_CUDA(cudaStreamWaitEvent(user, ctx->done[s], 0));
+        }
+        if (!zero_copy) {
+            if (argmax_bin) RB_CUDA(cudaMemcpyAsync(argmax_bin, m_amax, nk_all * 4, cudaMemcpyDeviceToHost, user));
+            if (max_count) RB_CUDA(cudaMemcpyAsync(max_count, m_max, nk_all * 2, cudaMemcpyDeviceToHost, user));
+            if (hit) RB_CUDA(cudaMemcpyAsync(hit, m_hit, nk_all, cudaMemcpyDeviceToHost, user));
+            if (read_flag) RB_CUDA(cudaMemcpyAsync(read_flag, m_flag, n_reads, cudaMemcpyDeviceToHost, user));
+        }
+        g_d2h_bytes += (argmax_bin ? nk_all * 4 : 0) + (max_count ? nk_all * 2 : 0) + (hit ? nk_all : 0) + (read_flag ? n_reads : 0) +
+                       ((counts_fwd ? 1 : 0) + (counts_rev ? 1 : 0)) * n_reads * nbl * 2;
+        cudaError_t e = cudaStreamSynchronize(user);
+        if (e != cudaSuccess) return fail(RB_ERR_COUNT_KMER, std::string("Error counting kmers in IBF bins: ") + cudaGetErrorString(e));
+        return RB_OK;
+    };
+    int st = body();
+    if (st != RB_OK) {                       // drain whatever was enqueued before the buffers are reused
+        const std::string keep = g_last_error;
+        for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(ctx->st[s]);
+        cudaStreamSynchronize(user);
+        cudaGetLastError();
+        g_last_error = keep;
+    }
+    return st;
+}
 
 }  // namespace
 
@@ -831,114 +1149,28 @@ int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_
     if (!bases || !read_off || !thr_lut) return fail(RB_ERR_INVALID_ARG, "null pointer");
     if (n_lut == 0 || n_lut > (uint32_t)rb::kMaxLut) return fail(RB_ERR_INVALID_ARG, "n_lut must be 1..4");
     if (n_reads > 0x7FFFFFFFull) return fail(RB_ERR_INVALID_ARG, "more than 2^31-1 reads in one batch");
-
-    // ---- cut the batch into pieces of ~16 MB of bases: piece i+1 is copied in while piece i is
-    //      classified and piece i-1 is copied out (three slots, three streams) ------------------------
-    const uint64_t kPieceBytes = 16ull << 20, kPieceReads = 1ull << 18;
-    const bool dense = counts_fwd || counts_rev;
-    const uint64_t nbl = f->n_bins_local;
-    const uint64_t max_piece_reads = dense ? std::max<uint64_t>(1, std::min<uint64_t>(kPieceReads, (64ull << 20) / (2 * nbl)))
-                                           : kPieceReads;
-    std::vector<uint64_t> cut{0}, piece_max_len;
-    uint64_t max_len = 0, max_piece_bases = 0, max_piece_n = 0;
-    for (uint64_t i = 0, r0 = 0; i < n_reads; ++i) {
-        if (read_off[i + 1] < read_off[i]) return fail(RB_ERR_INVALID_ARG, "read offsets must be non-decreasing");
-        max_len = std::max(max_len, read_off[i + 1] - read_off[i]);
-        const bool last = i + 1 == n_reads;
-        if (last || read_off[i + 1] - read_off[r0] >= kPieceBytes || i + 1 - r0 >= max_piece_reads) {
-            max_piece_bases = std::max(max_piece_bases, read_off[i + 1] - read_off[r0]);
-            max_piece_n = std::max(max_piece_n, i + 1 - r0);
-            cut.push_back(i + 1);
-            piece_max_len.push_back(max_len);       // the kernels specialise on the longest read of a launch
-            max_len = 0;
-            r0 = i + 1;
-        }
-    }
-    const size_t n_pieces = cut.size() - 1;
-    const int n_slots = (int)std::min<size_t>(3, n_pieces);
-
+    if (read_off[n_reads] < read_off[0]) return fail(RB_ERR_INVALID_ARG, "read offsets must be non-decreasing");
     DeviceGuard g(f->device);
-    cudaStream_t user = (cudaStream_t)stream;
-    struct Slot {
-        cudaStream_t st = nullptr;
-        cudaEvent_t done = nullptr;
-        uint8_t *d_bases = nullptr, *d_small = nullptr;
-        uint64_t *d_off = nullptr, *d_keys = nullptr;
-        uint16_t *d_cf = nullptr, *d_cr = nullptr;
-    } slot[3];
-    uint16_t *d_lut = nullptr;
-    cudaEvent_t ev_start = nullptr;
-    const uint64_t nkp = (uint64_t)n_lut * max_piece_n;
-
-    auto body = [&]() -> int {
-        RB_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-        RB_CUDA(cudaMallocAsync(&d_lut, (size_t)n_lut * rb::kLutSize * 2, user));
-        RB_CUDA(cudaMemcpyAsync(d_lut, thr_lut, (size_t)n_lut * rb::kLutSize * 2, cudaMemcpyHostToDevice, user));
-        for (int s = 0; s < n_slots; ++s) {
-            Slot &S = slot[s];
-            RB_CUDA(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
-            RB_CUDA(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
-            RB_CUDA(cudaMallocAsync(&S.d_bases, max_piece_bases ? max_piece_bases : 1, user));
-            RB_CUDA(cudaMallocAsync(&S.d_off, (max_piece_n + 1) * 8, user));
-            RB_CUDA(cudaMallocAsync(&S.d_keys, nkp * 8, user));
-            RB_CUDA(cudaMallocAsync(&S.d_small, nkp * 7 + max_piece_n + 16, user));   // argmax | max | hit | flag
-            if (counts_fwd) RB_CUDA(cudaMallocAsync(&S.d_cf, max_piece_n * nbl * 2, user));
-            if (counts_rev) RB_CUDA(cudaMallocAsync(&S.d_cr, max_piece_n * nbl * 2, user));
-        }
-        RB_CUDA(cudaEventRecord(ev_start, user));          // slot streams start after the caller's stream
-        for (int s = 0; s < n_slots; ++s) RB_CUDA(cudaStreamWaitEvent(slot[s].st, ev_start, 0));
-        for (size_t p = 0; p < n_pieces; ++p) {
-            Slot &S = slot[p % n_slots];
-            const uint64_t r0 = cut[p], r1 = cut[p + 1], n = r1 - r0, nk = (uint64_t)n_lut * n;
-            const uint64_t b0 = read_off[r0], nb = read_off[r1] - b0;
-            RB_CUDA(cudaMemcpyAsync(S.d_bases, bases + b0, nb, cudaMemcpyHostToDevice, S.st));
-            RB_CUDA(cudaMemcpyAsync(S.d_off, read_off + r0, (n + 1) * 8, cudaMemcpyHostToDevice, S.st));
-            uint32_t *d_amax = reinterpret_cast<uint32_t *>(S.d_small);
-            uint16_t *d_max = reinterpret_cast<uint16_t *>(S.d_small + nk * 4);
-            uint8_t *d_hit = S.d_small + nk * 6;
-            uint8_t *d_flag = S.d_small + nk * 7;
-            // offsets stay absolute: bias the base pointer instead of rewriting them
-            const uint8_t *biased = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(S.d_bases) - (uintptr_t)b0);
-            int s2 = rb_ibf_count_batch_dev(f, biased, S.d_off, n, (uint32_t)std::min<uint64_t>(piece_max_len[p], 0xFFFFFFFFu),
-                                            d_lut, n_lut, S.d_keys, S.d_cf, S.d_cr, d_flag, S.st);
-            if (s2 != RB_OK) return s2;
-            s2 = rb_keys_decode_dev(S.d_keys, nk, d_max, d_hit, d_amax, f->device, S.st);
-            if (s2 != RB_OK) return s2;
-            for (uint32_t t = 0; t < n_lut; ++t) {
-                const uint64_t ho = (uint64_t)t * n_reads + r0, dofs = (uint64_t)t * n;
-                if (max_count) RB_CUDA(cudaMemcpyAsync(max_count + ho, d_max + dofs, n * 2, cudaMemcpyDeviceToHost, S.st));
-                if (hit) RB_CUDA(cudaMemcpyAsync(hit + ho, d_hit + dofs, n, cudaMemcpyDeviceToHost, S.st));
-                if (argmax_bin) RB_CUDA(cudaMemcpyAsync(argmax_bin + ho, d_amax + dofs, n * 4, cudaMemcpyDeviceToHost, S.st));
-            }
-            if (read_flag) RB_CUDA(cudaMemcpyAsync(read_flag + r0, d_flag, n, cudaMemcpyDeviceToHost, S.st));
-            if (counts_fwd) RB_CUDA(cudaMemcpyAsync(counts_fwd + r0 * nbl, S.d_cf, n * nbl * 2, cudaMemcpyDeviceToHost, S.st));
-            if (counts_rev) RB_CUDA(cudaMemcpyAsync(counts_rev + r0 * nbl, S.d_cr, n * nbl * 2, cudaMemcpyDeviceToHost, S.st));
-        }
-        for (int s = 0; s < n_slots; ++s) {
-            RB_CUDA(cudaEventRecord(slot[s].done, slot[s].st));
-            RB_CUDA(cudaStreamWaitEvent(user, slot[s].done, 0));
-        }
-        cudaError_t e = cudaStreamSynchronize(user);
-        if (e != cudaSuccess) return fail(RB_ERR_COUNT_KMER, std::string("Error counting kmers in IBF bins: ") + cudaGetErrorString(e));
-        return RB_OK;
-    };
-    int st = body();
-    if (st != RB_OK) {                       // drain whatever was enqueued before releasing buffers
-        for (int s = 0; s < n_slots; ++s) if (slot[s].st) cudaStreamSynchronize(slot[s].st);
-        cudaStreamSynchronize(user);
-        cudaGetLastError();
-    }
-    for (int s = 0; s < 3; ++s) {
-        Slot &S = slot[s];
-        void *bufs[] = {S.d_bases, S.d_off, S.d_keys, S.d_small, S.d_cf, S.d_cr};
-        for (void *p : bufs) if (p) cudaFreeAsync(p, user);
-        if (S.done) cudaEventDestroy(S.done);
-        if (S.st) cudaStreamDestroy(S.st);
-    }
-    if (d_lut) cudaFreeAsync(d_lut, user);
-    if (ev_start) cudaEventDestroy(ev_start);
-    cudaStreamSynchronize(user);
+    CallCtx *ctx = acquire_ctx(f);
+    if (!ctx) return fail(RB_ERR_CUDA, "cannot create streams for the classify call");
+    int st = run_count_batch(f, ctx, reinterpret_cast<const uint8_t *>(bases), read_off, n_reads, thr_lut, n_lut, counts_fwd,
+                             counts_rev, max_count, hit, argmax_bin, read_flag, (cudaStream_t)stream);
+    release_ctx(f, ctx);
     return st;
+}
+
+int rb_transfer_bytes(uint64_t *h2d, uint64_t *d2h)
+{
+    if (h2d) *h2d = g_h2d_bytes.load();
+    if (d2h) *d2h = g_d2h_bytes.load();
+    return RB_OK;
+}
+
+int rb_host_pack_info(int *threads, int *isa)
+{
+    if (threads) *threads = rb::host_threads();
+    if (isa) *isa = rb::pack_isa();
+    return RB_OK;
 }
 
 }  // extern "C"

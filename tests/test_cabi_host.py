@@ -127,6 +127,17 @@ def test_fast_mod_exhaustive_edges(tmp_path):
     assert out.returncode == 0 and "fast_mod OK" in out.stdout, out.stdout + out.stderr
 
 
+@pytest.mark.parametrize("isa", ["5", "2", "0"])
+def test_host_packer_matches_restatement(tmp_path, isa):
+    """Bit planes of the host packer (AVX-512 / AVX2 / scalar paths, thread pool) against a plain loop."""
+    csrc = os.path.join(ROOT, "readbouncer_b200", "csrc")
+    exe = str(tmp_path / "test_host_pack")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I" + csrc, os.path.join(ROOT, "tests", "cpp", "test_host_pack.cpp"),
+                           os.path.join(csrc, "host_pack.cpp"), "-lpthread", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, env=dict(os.environ, RB_HOST_PACK_ISA=isa, RB_HOST_THREADS="4"))
+    assert out.returncode == 0 and "host_pack OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_cpp_shim_host_checks(tmp_path, golden_ibf_paths):
     rb.build_library()
     exe = _compile(os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"), str(tmp_path / "test_shim"))
