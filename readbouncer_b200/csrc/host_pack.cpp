@@ -77,8 +77,9 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *bases, size_t n, u
 // AVX-512 (BW + VBMI): one 128-entry byte look-up (vpermi2b) classifies 64 bases, vptestmb turns code bits into
 // 64-bit masks directly -- no movemask, no shifts.
 __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const uint8_t *bases, size_t n, uint32_t *lo,
-                                                                        uint32_t *hi, uint32_t *bad)
+                                                                        uint32_t *hi, uint32_t *bad, bool nt)
 {
+    nt = nt && ((reinterpret_cast<uintptr_t>(lo) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(bad)) & 7) == 0;
     alignas(64) uint8_t tab[128];
     for (int c = 0; c < 128; ++c) {
         const int u = c & 0xDF;
@@ -92,10 +93,17 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const ui
         const __m512i cls = _mm512_permutex2var_epi8(t0, x, t1);              // index = low 7 bits of the byte
         const __mmask64 good = _mm512_movepi8_mask(cls) & ~_mm512_movepi8_mask(x);   // and the byte is < 0x80
         const uint64_t l = _mm512_test_epi8_mask(x, c02) & good, h = _mm512_test_epi8_mask(x, c04) & good, b = ~good;
-        std::memcpy(lo + 2 * w, &l, 8);
-        std::memcpy(hi + 2 * w, &h, 8);
-        std::memcpy(bad + 2 * w, &b, 8);
+        if (nt) {        // write-combining stores: the planes go to DRAM for the DMA engine, not into this core's cache
+            _mm_stream_si64(reinterpret_cast<long long *>(lo + 2 * w), (long long)l);
+            _mm_stream_si64(reinterpret_cast<long long *>(hi + 2 * w), (long long)h);
+            _mm_stream_si64(reinterpret_cast<long long *>(bad + 2 * w), (long long)b);
+        } else {
+            std::memcpy(lo + 2 * w, &l, 8);
+            std::memcpy(hi + 2 * w, &h, 8);
+            std::memcpy(bad + 2 * w, &b, 8);
+        }
     }
+    if (nt) _mm_sfence();
     const size_t done = 64 * full, rest = n - done;
     for (size_t o = 0; o < rest; o += 32)
         pack_word_scalar(bases + done + o, std::min<size_t>(32, rest - o), lo[2 * full + o / 32], hi[2 * full + o / 32],
@@ -124,7 +132,12 @@ public:
     {
         int n = 0;
         if (const char *e = std::getenv("RB_HOST_THREADS")) n = std::atoi(e);
-        if (n <= 0) n = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (n <= 0) {
+            // share the cores between the ranks of one node (torchrun exports LOCAL_WORLD_SIZE), at most 16 each
+            unsigned cores = std::max(1u, std::thread::hardware_concurrency()), ranks = 1;
+            if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, std::atoi(e));
+            n = (int)std::min<unsigned>(std::max(1u, cores / ranks), 16u);
+        }
         n_workers_ = std::max(0, n - 1);
         for (int i = 0; i < n_workers_; ++i) threads_.emplace_back([this] { worker(); });
     }
@@ -225,10 +238,35 @@ Pool &pool()
 
 }  // namespace
 
-void pack_bases(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad)
+#if defined(__x86_64__)
+namespace {
+__attribute__((target("avx512f"))) uint64_t max_diff_avx512(const uint64_t *off, size_t n)
+{
+    __m512i m = _mm512_setzero_si512();
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8)
+        m = _mm512_max_epu64(m, _mm512_sub_epi64(_mm512_loadu_si512(off + i + 1), _mm512_loadu_si512(off + i)));
+    uint64_t r = _mm512_reduce_max_epu64(m);
+    for (; i < n; ++i) r = std::max(r, off[i + 1] - off[i]);
+    return r;
+}
+}  // namespace
+#endif
+
+uint64_t max_read_length(const uint64_t *off, size_t n)
 {
 #if defined(__x86_64__)
-    if (g_isa == 5) { pack_avx512(bases, n, lo, hi, bad); return; }
+    if (g_isa == 5) return max_diff_avx512(off, n);
+#endif
+    uint64_t r = 0;
+    for (size_t i = 0; i < n; ++i) r = std::max(r, off[i + 1] - off[i]);
+    return r;
+}
+
+void pack_bases(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad, bool streaming_stores)
+{
+#if defined(__x86_64__)
+    if (g_isa == 5) { pack_avx512(bases, n, lo, hi, bad, streaming_stores); return; }
     if (g_isa == 2) { pack_avx2(bases, n, lo, hi, bad); return; }
 #endif
     pack_scalar(bases, n, lo, hi, bad);

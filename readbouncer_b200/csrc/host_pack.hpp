@@ -15,7 +15,11 @@ namespace rb {
 // Planes of bases[0, n): bit i of lo/hi/bad = base i.  Codes (ascii >> 1) & 3 = A0 C1 T2 G3, U/u = T;
 // every other character is "bad" (Dna5 rank 4) with code bits 0.  n need not be a multiple of 32: the last
 // word is zero padded.  Writes ceil(n / 32) words per plane.
-void pack_bases(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad);
+// streaming_stores: write the planes with non-temporal stores (staging memory that a DMA engine reads next).
+void pack_bases(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad, bool streaming_stores = false);
+
+// max over i < n of off[i+1] - off[i] as unsigned 64-bit (a decreasing pair shows up as a value >= 2^63)
+uint64_t max_read_length(const uint64_t *off, size_t n);
 
 // Instruction set of the packer in use: 0 scalar, 2 AVX2, 5 AVX-512 BW+VBMI (reported by rb_host_pack_info;
 // env RB_HOST_PACK_ISA caps it).

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <mutex>
 #include <cstdio>
@@ -349,7 +350,7 @@ struct L2Window {
 // Two ways out: result arrays in pinned (or registered) host memory are written by the decode kernel directly
 // (mapped, coalesced stores); otherwise results gather in a device buffer and are copied at the end.
 constexpr int kSlots = 4;
-constexpr uint64_t kPieceBases = 8ull << 20, kPieceReads = 1ull << 17;
+constexpr uint64_t kPieceBases = 8ull << 20, kPieceReads = 1ull << 18;   // env RB_PIECE_MB overrides the former
 constexpr uint64_t kPackTask = 128ull << 10;            // bases per packing task (a multiple of 32)
 constexpr uint64_t kStageBases = 512ull << 20;          // bases per round of the packed pipeline (192 MB of planes)
 
@@ -393,7 +394,7 @@ struct CallCtx {
     cudaEvent_t done[kSlots] = {};
     cudaEvent_t ev_start = nullptr;
     DevBuf d_off[kSlots], d_keys[kSlots], d_flag[kSlots], d_in[kSlots], d_cf[kSlots], d_cr[kSlots];
-    DevBuf d_lut, d_planes, d_res;
+    DevBuf d_lut, d_res;
     HostBuf h_planes;
     std::vector<uint16_t> lut_host;          // what d_lut holds
     int init()
@@ -414,7 +415,7 @@ struct CallCtx {
             d_off[s].release(); d_keys[s].release(); d_flag[s].release(); d_in[s].release(); d_cf[s].release(); d_cr[s].release();
         }
         if (ev_start) cudaEventDestroy(ev_start);
-        d_lut.release(); d_planes.release(); d_res.release(); h_planes.release();
+        d_lut.release(); d_res.release(); h_planes.release();
         cudaGetLastError();
     }
 };
@@ -466,18 +467,34 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
                     const uint16_t *thr_lut, uint32_t n_lut, uint16_t *counts_fwd, uint16_t *counts_rev,
                     uint16_t *max_count, uint8_t *hit, uint32_t *argmax_bin, uint8_t *read_flag, cudaStream_t user)
 {
+    // RB_TRACE=1: host-clock milestones of the call on stderr (where does the end-to-end time go)
+    static const int trace_level = [] { const char *e = std::getenv("RB_TRACE"); return e ? std::atoi(e) : 0; }();
+    const bool trace = trace_level >= 1;
+    // RB_TRACE=2: additionally a device timeline per piece (CUDA events after the copies, the count and the decode kernel)
+    struct PieceEv { cudaEvent_t h2d, cnt, dec; double t_submit; };
+    std::vector<PieceEv> pev;
+    cudaEvent_t ev_t0 = nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double t_setup = 0, t_first_submit = -1, t_packed = 0, t_submitted = 0;
     const bool dense = counts_fwd || counts_rev;
     const uint64_t nbl = f->n_bins_local;
     const uint64_t piece_reads_cap = dense ? std::max<uint64_t>(1, std::min<uint64_t>(kPieceReads, (64ull << 20) / (2 * nbl)))
                                            : kPieceReads;
     // ---- pieces: ~kPieceBases bases or piece_reads_cap reads, whichever comes first (binary search: offsets are sorted;
     //      every piece is checked for that when it is submitted) -------------------------------------------------------
+    auto env_mb = [](const char *name, uint64_t dflt) {       // test / tuning overrides, read at every call
+        const char *e = std::getenv(name);
+        const long v = e ? std::atol(e) : 0;
+        return v > 0 ? (uint64_t)v << 20 : dflt;
+    };
+    const uint64_t piece_bases = env_mb("RB_PIECE_MB", kPieceBases), stage_bases = env_mb("RB_STAGE_MB", kStageBases);
     std::vector<uint64_t> cut{0};
     while (cut.back() < n_reads) {
         const uint64_t r0 = cut.back();
         const uint64_t rmax = std::min<uint64_t>(n_reads, r0 + piece_reads_cap);
         const uint64_t *lo = read_off + r0 + 1, *hi = read_off + rmax;
-        const uint64_t *it = std::lower_bound(lo, hi, read_off[r0] + kPieceBases);     // first read END >= r0 + piece bases
+        const uint64_t *it = std::lower_bound(lo, hi, read_off[r0] + piece_bases);     // first read END >= r0 + piece bases
         cut.push_back(std::min<uint64_t>(rmax, (uint64_t)(it - read_off)));
         if (cut.back() <= r0) cut.back() = r0 + 1;
     }
@@ -517,16 +534,18 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
             RB_CUDA(cudaMemcpyAsync(ctx->d_lut.p, ctx->lut_host.data(), lut_elems * 2, cudaMemcpyHostToDevice, user));
             g_h2d_bytes += lut_elems * 2;
         }
+        if (trace_level >= 2) { cudaEventCreate(&ev_t0); cudaEventRecord(ev_t0, user); }
         RB_CUDA(cudaEventRecord(ctx->ev_start, user));          // slot streams start after the caller's stream
         for (int s = 0; s < kSlots; ++s) RB_CUDA(cudaStreamWaitEvent(ctx->st[s], ctx->ev_start, 0));
 
         // one piece: offsets in, classify (packed planes already on their way, or ASCII bases copied here), results out
+        t_setup = ms_since();
         auto submit = [&](size_t p, const uint32_t *d_lo, const uint32_t *d_hi, const uint32_t *d_bad, uint64_t base0) -> int {
+            if (t_first_submit < 0) t_first_submit = ms_since();
             const int s = (int)(p % kSlots);
             cudaStream_t sst = ctx->st[s];
             const uint64_t r0 = cut[p], r1 = cut[p + 1], n = r1 - r0;
-            uint64_t piece_max = 0;
-            for (uint64_t i = r0; i < r1; ++i) piece_max = std::max(piece_max, read_off[i + 1] - read_off[i]);
+            const uint64_t piece_max = rb::max_read_length(read_off + r0, n);
             if (piece_max >> 63) return fail(RB_ERR_INVALID_ARG, "read offsets must be non-decreasing");
             const uint64_t b0 = read_off[r0], nb = read_off[r1] - b0;
             const uint32_t max_len32 = (uint32_t)std::min<uint64_t>(piece_max, 0xFFFFFFFFu);
@@ -537,6 +556,11 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
             if ((s2 = ctx->d_flag[s].reserve(n)) != RB_OK) return s2;
             RB_CUDA(cudaMemcpyAsync(ctx->d_off[s].p, read_off + r0, (n + 1) * 8, cudaMemcpyHostToDevice, sst));
             g_h2d_bytes += (n + 1) * 8;
+            PieceEv pe{};
+            if (trace_level >= 2) {
+                cudaEventCreate(&pe.h2d); cudaEventCreate(&pe.cnt); cudaEventCreate(&pe.dec);
+                pe.t_submit = ms_since();
+            }
             rb::CountArgs a{};
             a.fv = view_of(f);
             a.read_off = static_cast<const uint64_t *>(ctx->d_off[s].p);
@@ -545,6 +569,7 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
             a.read_flag = static_cast<uint8_t *>(ctx->d_flag[s].p);
             if (packed) {
                 a.pk_lo = d_lo; a.pk_hi = d_hi; a.pk_bad = d_bad; a.pk_base0 = base0;
+                if (trace_level >= 2) cudaEventRecord(pe.h2d, sst);
                 int nl = rb::launch_count_wtable(a, table, f->table_span, max_len32, f->sm_count, sst);
                 if (nl < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
                 g_launches += (uint64_t)nl;
@@ -562,9 +587,11 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
                 if (counts_fwd) RB_CUDA(cudaMemcpyAsync(counts_fwd + r0 * nbl, d_cf, n * nbl * 2, cudaMemcpyDeviceToHost, sst));
                 if (counts_rev) RB_CUDA(cudaMemcpyAsync(counts_rev + r0 * nbl, d_cr, n * nbl * 2, cudaMemcpyDeviceToHost, sst));
             }
+            if (trace_level >= 2) cudaEventRecord(pe.cnt, sst);
             int nl = rb::launch_keys_decode_piece(a.keys, a.read_flag, n, n_lut, n_reads, r0, m_max, m_hit, m_amax, m_flag, sst);
             if (nl < 0) return fail(RB_ERR_CUDA, "decode launch failed");
             g_launches += (uint64_t)nl;
+            if (trace_level >= 2) { cudaEventRecord(pe.dec, sst); pev.push_back(pe); }
             return RB_OK;
         };
 
@@ -572,54 +599,69 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
             for (size_t p = 0; p < n_pieces; ++p) { int s2 = submit(p, nullptr, nullptr, nullptr, 0); if (s2 != RB_OK) return s2; }
         } else {
             // rounds of at most kStageBases bases; inside a round the host threads pack 128 K-base tasks in order and the
-            // calling thread submits every piece as soon as the tasks covering it are done
+            // calling thread submits every piece as soon as its tasks are done.  Every piece has its own region of the
+            // pinned staging buffer -- [low plane][high plane][bad plane], bit i = base base0 + i -- so it crosses PCIe
+            // as ONE copy.
+            struct Region { uint64_t base0, nb, nw; size_t h_word, task0, n_tasks; };
             size_t p_begin = 0;
             while (p_begin < n_pieces) {
                 size_t p_end = p_begin + 1;
-                const uint64_t B0 = read_off[cut[p_begin]];
-                while (p_end < n_pieces && read_off[cut[p_end + 1]] - B0 <= kStageBases) ++p_end;
-                const uint64_t NB = read_off[cut[p_end]] - B0;                 // bases of this round
-                const uint64_t NW = (NB + 31) / 32 + 8;                         // words per plane (+ slack for the kernel's tail reads)
+                const uint64_t R0 = read_off[cut[p_begin]];
+                while (p_end < n_pieces && read_off[cut[p_end + 1]] - R0 <= stage_bases) ++p_end;
+                std::vector<Region> reg(p_end - p_begin);
+                std::vector<uint32_t> task_piece;
+                size_t h_words = 0;
+                for (size_t p = p_begin; p < p_end; ++p) {
+                    Region &r = reg[p - p_begin];
+                    const uint64_t b0 = read_off[cut[p]], b1 = read_off[cut[p + 1]];
+                    r.base0 = b0 - ((b0 - R0) & 31u);                        // word aligned, never before the round's first base
+                    r.nb = b1 - r.base0;
+                    r.nw = ((r.nb + 31) / 32 + 2 + 15) / 16 * 16;             // 64-byte multiples: streaming stores, aligned planes
+                    r.h_word = h_words;
+                    r.task0 = task_piece.size();
+                    r.n_tasks = (size_t)std::max<uint64_t>(1, (r.nb + kPackTask - 1) / kPackTask);
+                    task_piece.insert(task_piece.end(), r.n_tasks, (uint32_t)(p - p_begin));
+                    h_words += 3 * r.nw;
+                }
                 int s2;
-                if ((s2 = ctx->h_planes.reserve(NW * 12)) != RB_OK) return s2;
-                if ((s2 = ctx->d_planes.reserve(NW * 12)) != RB_OK) return s2;
-                uint32_t *h_lo = static_cast<uint32_t *>(ctx->h_planes.p), *h_hi = h_lo + NW, *h_bad = h_hi + NW;
-                uint32_t *d_lo = static_cast<uint32_t *>(ctx->d_planes.p), *d_hi = d_lo + NW, *d_bad = d_hi + NW;
-                const size_t n_tasks = (size_t)((NB + kPackTask - 1) / kPackTask);
+                if ((s2 = ctx->h_planes.reserve(h_words * 4)) != RB_OK) return s2;
+                uint32_t *const h_base = static_cast<uint32_t *>(ctx->h_planes.p);
+                const size_t n_tasks = task_piece.size();
                 size_t next_piece = p_begin;
                 int err = RB_OK;
                 auto pack_task = [&](size_t t) {
-                    const uint64_t o = (uint64_t)t * kPackTask, m = std::min<uint64_t>(kPackTask, NB - o);
-                    rb::pack_bases(bases + B0 + o, m, h_lo + o / 32, h_hi + o / 32, h_bad + o / 32);
+                    const Region &r = reg[task_piece[t]];
+                    const uint64_t o = (uint64_t)(t - r.task0) * kPackTask;
+                    if (o >= r.nb) return;
+                    const uint64_t m = std::min<uint64_t>(kPackTask, r.nb - o);
+                    uint32_t *h = h_base + r.h_word + o / 32;
+                    rb::pack_bases(bases + r.base0 + o, m, h, h + r.nw, h + 2 * r.nw, true);
                 };
                 auto poll = [&](size_t tasks_done) {
                     while (err == RB_OK && next_piece < p_end) {
-                        const uint64_t e_base = read_off[cut[next_piece + 1]] - B0;            // one past the piece's last base
-                        const size_t need = (size_t)((e_base + kPackTask - 1) / kPackTask);   // tasks that must be complete
-                        if (tasks_done < std::min(need, n_tasks)) break;
-                        const uint64_t w_lo = (read_off[cut[next_piece]] - B0) / 32, w_hi = (e_base + 31) / 32;
-                        cudaStream_t sst = ctx->st[next_piece % kSlots];
-                        cudaError_t ce = cudaSuccess;
-                        if (w_hi > w_lo) {
-                            ce = cudaMemcpyAsync(d_lo + w_lo, h_lo + w_lo, (w_hi - w_lo) * 4, cudaMemcpyHostToDevice, sst);
-                            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_hi + w_lo, h_hi + w_lo, (w_hi - w_lo) * 4, cudaMemcpyHostToDevice, sst);
-                            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_bad + w_lo, h_bad + w_lo, (w_hi - w_lo) * 4, cudaMemcpyHostToDevice, sst);
-                        }
+                        const Region &r = reg[next_piece - p_begin];
+                        if (tasks_done < r.task0 + r.n_tasks) break;
+                        const int s = (int)(next_piece % kSlots);
+                        if ((err = ctx->d_in[s].reserve(r.nw * 12)) != RB_OK) break;
+                        uint32_t *d = static_cast<uint32_t *>(ctx->d_in[s].p);
+                        cudaError_t ce = cudaMemcpyAsync(d, h_base + r.h_word, r.nw * 12, cudaMemcpyHostToDevice, ctx->st[s]);
                         if (ce != cudaSuccess) { err = fail(RB_ERR_CUDA, std::string("plane copy: ") + cudaGetErrorString(ce)); break; }
-                        g_h2d_bytes += (w_hi - w_lo) * 12;
-                        err = submit(next_piece, d_lo, d_hi, d_bad, B0);
+                        g_h2d_bytes += r.nw * 12;
+                        err = submit(next_piece, d, d + r.nw, d + 2 * r.nw, r.base0);
                         ++next_piece;
                     }
                 };
                 rb::parallel_tasks(n_tasks, pack_task, poll);
+                t_packed = ms_since();
                 poll(n_tasks);
                 if (err != RB_OK) return err;
-                if (p_end < n_pieces) {            // the staging planes are reused by the next round
+                if (p_end < n_pieces) {            // the staging buffer is reused by the next round
                     for (int s = 0; s < kSlots; ++s) RB_CUDA(cudaStreamSynchronize(ctx->st[s]));
                 }
                 p_begin = p_end;
             }
         }
+        t_submitted = ms_since();
         for (int s = 0; s < kSlots; ++s) {
             RB_CUDA(cudaEventRecord(ctx->done[s], ctx->st[s]));
             RB_CUDA(cudaStreamWaitEvent(user, ctx->done[s], 0));
@@ -634,6 +676,19 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
                        ((counts_fwd ? 1 : 0) + (counts_rev ? 1 : 0)) * n_reads * nbl * 2;
         cudaError_t e = cudaStreamSynchronize(user);
         if (e != cudaSuccess) return fail(RB_ERR_COUNT_KMER, std::string("Error counting kmers in IBF bins: ") + cudaGetErrorString(e));
+        if (trace_level >= 2 && ev_t0) {
+            for (size_t i = 0; i < pev.size(); ++i) {
+                float a1 = 0, a2 = 0, a3 = 0;
+                cudaEventElapsedTime(&a1, ev_t0, pev[i].h2d); cudaEventElapsedTime(&a2, ev_t0, pev[i].cnt); cudaEventElapsedTime(&a3, ev_t0, pev[i].dec);
+                std::fprintf(stderr, "[rb piece %2zu] submit %.3f | h2d done %.3f count done %.3f decode done %.3f ms\n", i, pev[i].t_submit, a1, a2, a3);
+                cudaEventDestroy(pev[i].h2d); cudaEventDestroy(pev[i].cnt); cudaEventDestroy(pev[i].dec);
+            }
+            cudaEventDestroy(ev_t0);
+        }
+        if (trace)
+            std::fprintf(stderr, "[rb trace] reads %llu pieces %zu packed %d zero_copy %d | setup %.3f first_submit %.3f packed %.3f "
+                                 "submitted %.3f done %.3f ms\n", (unsigned long long)n_reads, n_pieces, (int)packed_ok, (int)zero_copy,
+                         t_setup, t_first_submit, t_packed, t_submitted, ms_since());
         return RB_OK;
     };
     int st = body();

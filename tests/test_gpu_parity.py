@@ -228,6 +228,49 @@ def test_kmer_table_handles_n_rich_reads_and_is_dropped_by_insert():
     assert got["hit"].all() and gf.kmer_table_bytes() > 0
 
 
+def test_host_buffer_pipeline_packed_pieces_and_rounds(monkeypatch):
+    """rb_ibf_count_batch with many pieces and several staging rounds: reads packed into bit planes by the host threads
+    (ragged lengths, offsets not multiples of 32, N / IUPAC / U / lower case, an over-long read that sends its piece down
+    the ASCII path) must give the oracle's answers, pinned and pageable result buffers alike."""
+    import torch
+    plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
+    rng = np.random.default_rng(5)
+    lengths = rng.integers(0, 394, size=60000).tolist()
+    lengths[40000] = 3000                                   # not a group-kernel read: its piece is shipped as ASCII
+    bases, off = synth.ragged_reads(plan["bases"], lengths, seed=3, frac_from_ref=0.6, n_frac=0.002, lower_frac=0.05)
+    bases[::9973] = ord("U"); bases[5::7919] = ord("R")
+    luts = np.stack([rb.threshold_lut(0.1, 13), rb.threshold_lut(0.08, 13)])
+    gf.enable_kmer_table(0)
+    assert gf.kmer_table_span() == 3
+    monkeypatch.setenv("RB_PIECE_MB", "1")                  # ~12 pieces
+    monkeypatch.setenv("RB_STAGE_MB", "4")                  # ~3 rounds
+    got = gf.count_batch(bases, off, luts)                  # pageable numpy buffers: results copied at the end
+    exp = [of.count_batch(bases, off, luts[t], n_threads=8) for t in range(2)]
+    for t in range(2):
+        for key in ("max_count", "hit", "argmax_bin"):
+            assert np.array_equal(got[key][t], exp[t][key]), (t, key)
+    assert np.array_equal(got["read_flag"], exp[0]["short_read"])
+    # pinned inputs and outputs (mapped result stores), straight through the C ABI
+    n = len(lengths)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    hb, ho = pin(bases), pin(off)
+    r_max = torch.empty(2 * n, dtype=torch.int16, pin_memory=True).numpy().view(np.uint16)
+    r_hit = torch.empty(2 * n, dtype=torch.uint8, pin_memory=True).numpy()
+    r_am = torch.empty(2 * n, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+    r_flag = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
+    P = rb.capi._np_ptr
+    for pack in ("1", "0"):
+        monkeypatch.setenv("RB_HOST_PACK", pack)
+        r_max[:] = 0xFFFF; r_hit[:] = 7; r_am[:] = 5; r_flag[:] = 9
+        rb.capi._check(rb.lib().rb_ibf_count_batch(gf._h, P(hb), P(ho), n, P(luts), 2, None, None, P(r_max), P(r_hit), P(r_am),
+                                                   P(r_flag), None))
+        for t in range(2):
+            assert np.array_equal(r_max[t * n:(t + 1) * n], exp[t]["max_count"]), pack
+            assert np.array_equal(r_hit[t * n:(t + 1) * n], exp[t]["hit"]), pack
+            assert np.array_equal(r_am[t * n:(t + 1) * n], exp[t]["argmax_bin"]), pack
+        assert np.array_equal(r_flag, exp[0]["short_read"]), pack
+
+
 def test_two_threshold_tables_in_one_pass():
     plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
     bases, off, _ = synth.sample_reads(plan["bases"], 3000, 250, seed=5, error_rate=0.12)
