@@ -340,7 +340,8 @@ def run_ours(args, w, n_reads):
     peak, peak_src = measured_peaks()
     achieved = n_reads * bytes_per_chunk / (kernel_ms * 1e-3) / 1e9
     span = gf.kmer_table_span()
-    kernel_name = ("count_wtable_kernel" if span >= 2 else "count_table_kernel" if span == 1 else
+    group_ok = span >= 2 and w["chunk"] - w["k"] + 1 <= 127 * span and w["chunk"] <= 545   # ibf_wtable.cu: wgroup_applicable
+    kernel_name = ("count_wgroup_kernel" if group_ok else "count_wtable_kernel" if span >= 2 else "count_table_kernel" if span == 1 else
                    "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
