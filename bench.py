@@ -341,7 +341,7 @@ def run_ours(args, w, n_reads):
     achieved = n_reads * bytes_per_chunk / (kernel_ms * 1e-3) / 1e9
     span = gf.kmer_table_span()
     group_ok = span >= 2 and w["chunk"] - w["k"] + 1 <= 127 * span and w["chunk"] <= 545   # ibf_wtable.cu: wgroup_applicable
-    kernel_name = ("count_wgroup_kernel" if group_ok else "count_wtable_kernel" if span >= 2 else "count_table_kernel" if span == 1 else
+    kernel_name = ("count_postings_kernel" if gf.kmer_table_kind() == 2 else "count_wgroup_kernel" if group_ok else "count_wtable_kernel" if span >= 2 else "count_table_kernel" if span == 1 else
                    "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel")
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -369,7 +369,9 @@ def run_ours(args, w, n_reads):
         return ev0.elapsed_time(ev1) / 2
 
     npos = w["chunk"] - w["k"] + 1
-    if span >= 2:       # window table: one request per entry of `lanes` slots, adjacent lanes
+    if gf.kmer_table_kind() == 2:
+        pass                # postings lists are streamed: the HBM-bandwidth roofline above applies
+    elif span >= 2:     # window table: one request per entry of `lanes` slots, adjacent lanes
         lanes = 2 if span == 2 else 4
         entry_bytes = lanes * 16 * int(gf.col_words)
         n_rows = gf.kmer_table_bytes() // entry_bytes
@@ -436,7 +438,7 @@ def run_ours(args, w, n_reads):
                    "thresholds_per_pass": n_lut, "l2_fetch_granularity": rb.get_l2_fetch_granularity(local), "error_rate": ERROR_RATE, "read_mix": "50% reference-derived @10% errors, 50% iid",
                    "l2": "no flush: inputs (%.0f MB reads + %.0f MB filter) exceed the 126 MB L2" % (
                        bases_np.nbytes / 1e6, plan["n_bits"] / 8e6),
-                   "hit_fraction": hits_dev / n_reads, "kmer_table_bytes": gf.kmer_table_bytes(), "kmer_table_span": gf.kmer_table_span(), "ibf_build_ms_gpu": build_ms,
+                   "hit_fraction": hits_dev / n_reads, "kmer_table_bytes": gf.kmer_table_bytes(), "kmer_table_span": gf.kmer_table_span(), "kmer_table_kind": gf.kmer_table_kind(), "ibf_build_ms_gpu": build_ms,
                    "ibf_build_kmers_per_s": n_kmers_ref / (build_ms * 1e-3)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

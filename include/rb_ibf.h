@@ -80,7 +80,8 @@ typedef struct rb_ibf_info_t {
     int32_t device;
     int32_t shard, n_shards;
     int32_t kmer_table_span;   /* consecutive k-mers per table entry (1..4), 0 if not built */
-    uint64_t kmer_table_bytes; /* bytes of the direct k-mer table, 0 if not built */
+    uint64_t kmer_table_bytes; /* bytes of the k-mer table, 0 if not built */
+    int32_t kmer_table_kind;   /* 0 none, 1 dense k-mer / window table (rows <= 4 words), 2 postings (wider rows) */
 } rb_ibf_info_t;
 
 /* ---- host-side scalar helpers (FP64, bit-exact with the reference) ------- */
@@ -209,7 +210,11 @@ RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_ma
  * min(60 % of the free HBM, 80 GiB) (env RB_KMER_TABLE=0 disables, RB_KMER_TABLE_MAX_GB changes the
  * cap, RB_KMER_TABLE_SPAN the widest span tried); dropped by rb_ibf_insert_batch*.  This call
  * (re)builds it now under the given byte budget (0 = automatic); UINT64_MAX disables the table for
- * this handle. */
+ * this handle.
+ * Wide filters (rows > 4 words, < 65535 local bins, k <= 15) get a POSTINGS table instead: the AND of
+ * the probed rows is ~1 % dense by the reference's own sizing, so the sorted list of set bins of every
+ * k-mer (2 bytes each, ~50 GB for a human-genome filter at k=13) replaces streaming 2*h rows of
+ * thousands of bytes per position; same policy, budget and env switches. */
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);
 
 /* Kernel selection override for tests/benchmarks: 0 auto, 1 warp-per-read tile kernel,

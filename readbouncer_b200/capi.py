@@ -43,7 +43,7 @@ class _Info(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_bins", "n_hash", "kmer_size", "n_bits", "bin_width", "n_blocks",
                                           "col_begin", "col_words", "bin_begin", "n_bins_local", "device_bytes")] + \
                [("device", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32), ("kmer_table_span", C.c_int32),
-                ("kmer_table_bytes", C.c_uint64)]
+                ("kmer_table_bytes", C.c_uint64), ("kmer_table_kind", C.c_int32)]
 
 
 def lib_path():
@@ -240,7 +240,7 @@ class IBF:
         info = _Info()
         _check(lib().rb_ibf_info(self._h, C.byref(info)))
         for name, _ in _Info._fields_:
-            if name not in ("kmer_table_span", "kmer_table_bytes"):      # the latter changes over time: see method
+            if name not in ("kmer_table_span", "kmer_table_bytes", "kmer_table_kind"):      # the latter changes over time: see method
                 setattr(self, name, int(getattr(info, name)))
         self.k = self.kmer_size
         self.n_local_words = self.device_bytes // 8
@@ -297,6 +297,11 @@ class IBF:
         info = _Info()
         _check(lib().rb_ibf_info(self._h, C.byref(info)))
         return int(info.kmer_table_span)
+
+    def kmer_table_kind(self):
+        info = _Info()
+        _check(lib().rb_ibf_info(self._h, C.byref(info)))
+        return int(info.kmer_table_kind)
 
     def device_words_ptr(self):
         return int(lib().rb_ibf_device_words(self._h) or 0)

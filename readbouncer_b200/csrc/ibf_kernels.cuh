@@ -55,6 +55,14 @@ bool wtable_geometry(uint64_t stride, uint32_t k, int span, int *lanes, int *can
 int launch_wtable_build(const FilterView &fv, uint64_t *table, int span, int sm_count, cudaStream_t st);
 int launch_count_wtable(const CountArgs &a, const uint64_t *table, int span, uint32_t max_read_len, int sm_count,
                         cudaStream_t st);
+// k-mer postings table for wide filters (ibf_postings.cu)
+bool postings_applicable(const FilterView &fv);
+int postings_sample_units(const FilterView &fv, uint32_t *d_scratch, uint32_t n_sample, double *mean_units, int sm_count,
+                          cudaStream_t st);
+int postings_build_ptr(const FilterView &fv, uint32_t *d_ptr, uint64_t *total_units, int sm_count, cudaStream_t st);
+int postings_fill(const FilterView &fv, const uint32_t *d_ptr, uint16_t *d_ids, int sm_count, cudaStream_t st);
+int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint16_t *d_ids, uint32_t max_read_len, int sm_count,
+                          cudaStream_t st);
 bool wgroup_applicable(uint32_t k, int span, uint32_t max_read_len);
 int get_wtable_variant();
 void set_wtable_variant(int v);   // 0 auto (group-per-read kernel for short reads), 1 always warp-per-read

@@ -1,0 +1,407 @@
+// ibf_postings.cu -- k-mer postings table for WIDE filters (rows of more than 4 words; BASELINE configs #3, #5).
+//
+// What seqan::count does per k-mer and strand (src/IBF/IBFClassify.cpp:149-150) is a pure
+// function of the k-mer: the AND of the h rows its hashes select.  For a wide filter that AND is a row of
+// thousands of bits -- 3 880 bytes for the 31 008 bins of a human reference -- but it is SPARSE: a bin's bit
+// survives the AND only if the bin holds the k-mer or all h probes are false positives, about 1 % by the
+// reference's own sizing (max_fp = 0.01, IBFBuild.cpp:404-413).  Tabulated densely the function needs 260 GB
+// (k = 13); as postings -- the sorted list of set bins per k-mer, 2 bytes each -- it needs ~50 GB and fits HBM.
+//
+//   ptr[x], ptr[x+1]   list of k-mer x in units of 8 ids (16 bytes), x = sum rank_j * 4^(k-1-j), ranks A0 C1 G2 T3
+//   ids[8 * u + i]     local bin indices, ascending; lists are padded to a multiple of 8 with the sentinel n_bins_local
+//
+// Classifying a 250-base chunk then reads 476 lists (~340 KB) instead of streaming 2 x 238 x 3 rows (5.5 MB), and
+// counts with shared-memory atomics on packed 8-bit (or 16-bit) counters.  The reverse strand of k-mer x is the
+// list of revcomp(x).  Windows containing a non-ACGT base take the hashing path on the bit matrix itself, so
+// every output equals the reference's.
+#include "ibf_device.cuh"
+
+#include <cub/device/device_scan.cuh>
+
+#include <vector>
+
+namespace rb {
+
+namespace {
+
+constexpr int kPostThreads = 256;
+constexpr int kPostWarps = kPostThreads / 32;
+constexpr int kPostPiece = 512;               // k-mer positions staged per pass over a read
+
+// base-5 hashes of the forward and reverse-complement strand of the ACGT k-mer x (ranks, first base most significant)
+__device__ __forceinline__ void kmer_hashes(uint64_t x, uint32_t k, uint64_t &Hf, uint64_t &Hr)
+{
+    Hf = 0; Hr = 0;
+    uint64_t pw = 1;
+    for (uint32_t j = 0; j < k; ++j) {
+        const uint32_t d = (uint32_t)(x >> (2 * (k - 1 - j))) & 3u;
+        Hf = Hf * 5 + d;
+        Hr += (uint64_t)(3u - d) * pw;
+        pw *= 5;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// build: pass 1 counts, pass 2 fills; one warp per k-mer, lanes stride over the row words
+// ------------------------------------------------------------------------------------------
+// x = first + i * step for i < n (step > 1: a sample to estimate the table size)
+__global__ void __launch_bounds__(256) postings_count_kernel(const FilterView fv, uint64_t first, uint64_t step, uint64_t n,
+                                                             uint32_t *__restrict__ units)
+{
+    const HashParams &hp = fv.hp;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp0; i < n; i += n_warps) {
+        uint64_t Hf, Hr;
+        kmer_hashes(first + i * step, hp.k, Hf, Hr);
+        const uint64_t *rows[kMaxHash];
+#pragma unroll
+        for (int h = 0; h < kMaxHash; ++h)
+            rows[h] = (uint32_t)h < hp.n_hash ? fv.words + hash_row(Hf, hp.pre[h], hp.n_blocks, hp.magic) * fv.stride : nullptr;
+        uint32_t c = 0;
+        for (uint64_t w = lane; w < fv.stride; w += 32) {
+            uint64_t m = ~0ULL;
+#pragma unroll
+            for (int h = 0; h < kMaxHash; ++h)
+                if ((uint32_t)h < hp.n_hash) m &= __ldg(rows[h] + w);
+            c += (uint32_t)__popcll(m);
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) units[i] = (c + 7u) >> 3;
+    }
+}
+
+__global__ void __launch_bounds__(256) postings_fill_kernel(const FilterView fv, uint64_t n_kmers, const uint32_t *__restrict__ ptr,
+                                                            uint16_t *__restrict__ ids)
+{
+    const HashParams &hp = fv.hp;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint16_t sentinel = (uint16_t)fv.n_bins_local;
+    for (uint64_t x = warp0; x < n_kmers; x += n_warps) {
+        uint64_t Hf, Hr;
+        kmer_hashes(x, hp.k, Hf, Hr);
+        const uint64_t *rows[kMaxHash];
+#pragma unroll
+        for (int h = 0; h < kMaxHash; ++h)
+            rows[h] = (uint32_t)h < hp.n_hash ? fv.words + hash_row(Hf, hp.pre[h], hp.n_blocks, hp.magic) * fv.stride : nullptr;
+        uint16_t *out = ids + (uint64_t)ptr[x] * 8;
+        const uint64_t end = (uint64_t)ptr[x + 1] * 8 - (uint64_t)ptr[x] * 8;
+        uint64_t run = 0;                                           // ids written so far (same in all lanes)
+        for (uint64_t w0 = 0; w0 < fv.stride; w0 += 32) {
+            const uint64_t w = w0 + lane;
+            uint64_t m = 0;
+            if (w < fv.stride) {
+                m = ~0ULL;
+#pragma unroll
+                for (int h = 0; h < kMaxHash; ++h)
+                    if ((uint32_t)h < hp.n_hash) m &= __ldg(rows[h] + w);
+            }
+            const uint32_t c = (uint32_t)__popcll(m);
+            uint32_t incl = c;                                      // inclusive prefix over the lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            uint64_t pos = run + incl - c;
+            while (m) {
+                const int b = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                out[pos++] = (uint16_t)(w * 64 + b);
+            }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        for (uint64_t p = run + lane; p < end; p += 32) out[p] = sentinel;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// lookup: CTA per read, warps take (position, strand) pairs, counters in shared memory
+// ------------------------------------------------------------------------------------------
+// CB = counter bits (8: reads of <= 255 positions, 16: any read the API accepts)
+template <int CB>
+__device__ __forceinline__ void add_ids(uint32_t *cnt, const uint4 v)
+{
+    constexpr int PER = 32 / CB;                 // counters per 32-bit word
+    constexpr int SH = (PER == 4) ? 2 : 1;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t a = w[i] & 0xFFFFu, b = w[i] >> 16;
+        atomicAdd(cnt + (a >> SH), 1u << ((a & (PER - 1)) * CB));
+        atomicAdd(cnt + (b >> SH), 1u << ((b & (PER - 1)) * CB));
+    }
+}
+
+// hashing path of one (position, strand): AND of the probed rows, one warp, counters by atomics
+template <int CB>
+__device__ __noinline__ void add_hashed(const FilterView &fv, const uint8_t *dig, uint32_t strand, uint32_t *cnt, int lane)
+{
+    constexpr int PER = 32 / CB;
+    constexpr int SH = (PER == 4) ? 2 : 1;
+    const HashParams &hp = fv.hp;
+    uint64_t H = 0, pw = 1;
+    for (uint32_t u = 0; u < hp.k; ++u) {
+        const uint32_t d = dig[u];
+        if (strand == 0) H = H * 5 + d;
+        else { H += comp5(d) * pw; pw *= 5; }
+    }
+    for (uint64_t w = lane; w < fv.stride; w += 32) {
+        uint64_t m = ~0ULL;
+        for (uint32_t h = 0; h < hp.n_hash; ++h)
+            m &= __ldg(fv.words + hash_row(H, hp.pre[h], hp.n_blocks, hp.magic) * fv.stride + w);
+        while (m) {
+            const uint32_t id = (uint32_t)(w * 64) + (uint32_t)__ffsll((long long)m) - 1u;
+            m &= m - 1;
+            atomicAdd(cnt + (id >> SH), 1u << ((id & (PER - 1)) * CB));
+        }
+    }
+}
+
+template <int CB>
+__device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return CB == 8 ? __vmaxu4(a, b) : __vmaxu2(a, b); }
+
+template <int CB>
+__global__ void __launch_bounds__(kPostThreads)
+count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const uint4 *__restrict__ ids, const uint32_t cnt_words)
+{
+    constexpr int PER = 32 / CB;
+    constexpr uint32_t CMASK = (CB == 8) ? 0xFFu : 0xFFFFu;
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint32_t *const cntF = s_mem, *const cntR = s_mem + cnt_words;
+    uint32_t *const s_x = s_mem + 2 * cnt_words;                         // [kPostPiece] packed k-mer or ~0u (not ACGT)
+    uint8_t *const s_dig = reinterpret_cast<uint8_t *>(s_x + kPostPiece); // [kPostPiece + 32] Dna5 ranks
+    __shared__ uint32_t s_red[kPostWarps];
+    __shared__ uint32_t s_best;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t k = a.fv.hp.k;
+    const uint32_t kbits = 2 * k;
+    const uint32_t kmask = kbits >= 32 ? ~0u : ((1u << kbits) - 1u);
+    const uint64_t nbl = a.fv.n_bins_local;
+
+    for (uint32_t w = tid; w < 2 * cnt_words; w += kPostThreads) s_mem[w] = 0;
+
+    for (uint64_t read = blockIdx.x; read < a.n_reads; read += gridDim.x) {
+        const uint64_t off = a.read_off[read];
+        const uint64_t len = a.read_off[read + 1] - off;
+        uint32_t flag = read_flag_of(len, k);
+        if (flag == 0 && CB == 8 && len - k + 1 > 255) flag = 3;         // longer than the caller's max_read_len promised
+        if (tid == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
+        __syncthreads();                                                   // counters are zero and visible
+
+        if (flag == 0) {
+            const uint32_t npos = (uint32_t)len - k + 1;
+            for (uint32_t cs = 0; cs < npos; cs += kPostPiece) {
+                const uint32_t cn = min((uint32_t)kPostPiece, npos - cs);
+                __syncthreads();
+                for (uint32_t i = tid; i < cn + k - 1; i += kPostThreads) s_dig[i] = (uint8_t)dna5(a.bases[off + cs + i]);
+                __syncthreads();
+                for (uint32_t j = tid; j < cn; j += kPostThreads) {
+                    uint32_t x = 0, bad = 0;
+                    for (uint32_t u = 0; u < k; ++u) {
+                        const uint32_t d = s_dig[j + u];
+                        x = (x << 2) | (d & 3u);
+                        bad |= d >> 2;
+                    }
+                    s_x[j] = bad ? ~0u : (x & kmask);
+                }
+                __syncthreads();
+                // (position, strand) pairs: 32 per warp round, list bounds fetched by the lanes, lists walked by the warp
+                const uint32_t n_pairs = 2 * cn;
+                for (uint32_t q0 = warp * 32; q0 < n_pairs; q0 += kPostWarps * 32) {
+                    const uint32_t q = q0 + lane;
+                    uint32_t p0 = 0, p1 = 0;
+                    bool hashed = false;
+                    if (q < n_pairs) {
+                        const uint32_t x = s_x[q >> 1];
+                        if (x == ~0u) hashed = true;
+                        else {
+                            uint32_t idx = x;
+                            if (q & 1u) {                                  // reverse strand: the list of revcomp(x)
+                                uint32_t v = __brev(~x);
+                                v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+                                idx = v >> (32 - kbits);
+                            }
+                            p0 = __ldg(ptr + idx);
+                            p1 = __ldg(ptr + idx + 1);
+                        }
+                    }
+                    const uint32_t any_hashed = __ballot_sync(0xffffffffu, hashed);
+                    const uint32_t n_here = min(32u, n_pairs - q0);
+                    for (uint32_t t = 0; t < n_here; t += 2) {             // two lists in flight
+                        const uint32_t a0 = __shfl_sync(0xffffffffu, p0, t), a1 = __shfl_sync(0xffffffffu, p1, t);
+                        const uint32_t t2 = min(t + 1, 31u);
+                        uint32_t b0 = __shfl_sync(0xffffffffu, p0, t2), b1 = __shfl_sync(0xffffffffu, p1, t2);
+                        if (t + 1 >= n_here) { b0 = 0; b1 = 0; }
+                        uint32_t *const ca = ((q0 + t) & 1u) ? cntR : cntF;
+                        uint32_t *const cb = ((q0 + t + 1) & 1u) ? cntR : cntF;
+                        uint4 va[2], vb[2];
+                        bool ha[2], hb[2];
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            ha[r] = a0 + 32u * r + lane < a1;
+                            hb[r] = b0 + 32u * r + lane < b1;
+                            if (ha[r]) va[r] = __ldg(ids + a0 + 32u * r + lane);
+                            if (hb[r]) vb[r] = __ldg(ids + b0 + 32u * r + lane);
+                        }
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            if (ha[r]) add_ids<CB>(ca, va[r]);
+                            if (hb[r]) add_ids<CB>(cb, vb[r]);
+                        }
+                        for (uint32_t u = a0 + 64u + lane; u < a1; u += 32) add_ids<CB>(ca, __ldg(ids + u));   // long lists
+                        for (uint32_t u = b0 + 64u + lane; u < b1; u += 32) add_ids<CB>(cb, __ldg(ids + u));
+                    }
+                    if (any_hashed) {
+                        for (uint32_t t = 0; t < n_here; ++t)
+                            if ((any_hashed >> t) & 1u)
+                                add_hashed<CB>(a.fv, s_dig + ((q0 + t) >> 1), (q0 + t) & 1u, ((q0 + t) & 1u) ? cntR : cntF, lane);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- epilogue: M = max over bins of max(fwd, rev), its lowest bin; counters back to zero ----------------
+        // the sentinel's counter (index nbl) is not a bin
+        if (tid == 0) {
+            const uint32_t sw = (uint32_t)nbl / PER, sb = ((uint32_t)nbl % PER) * CB;
+            cntF[sw] &= ~(CMASK << sb);
+            cntR[sw] &= ~(CMASK << sb);
+        }
+        __syncthreads();
+        uint32_t mx = 0;
+        for (uint32_t w = tid; w < cnt_words; w += kPostThreads) mx = vmax<CB>(mx, vmax<CB>(cntF[w], cntR[w]));
+        uint32_t m1 = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) m1 = max(m1, (mx >> (i * CB)) & CMASK);
+        m1 = __reduce_max_sync(0xffffffffu, m1);
+        if (lane == 0) s_red[warp] = m1;
+        if (tid == 0) s_best = 0xFFFFFFFFu;
+        __syncthreads();
+        uint32_t M = 0;
+#pragma unroll
+        for (int i = 0; i < kPostWarps; ++i) M = max(M, s_red[i]);
+        // second pass: lowest bin attaining M, dense counts, and zero the counters for the next read
+        uint32_t best = 0xFFFFFFFFu;
+        for (uint32_t w = tid; w < cnt_words; w += kPostThreads) {
+            const uint32_t f = cntF[w], r = cntR[w];
+            cntF[w] = 0; cntR[w] = 0;
+            const uint32_t m = vmax<CB>(f, r);
+#pragma unroll
+            for (int i = PER - 1; i >= 0; --i) {
+                const uint32_t bin = w * PER + i;
+                if (bin < nbl) {
+                    if (((m >> (i * CB)) & CMASK) == M) best = min(best, bin);
+                    if (a.counts_fwd) a.counts_fwd[read * nbl + bin] = (uint16_t)((f >> (i * CB)) & CMASK);
+                    if (a.counts_rev) a.counts_rev[read * nbl + bin] = (uint16_t)((r >> (i * CB)) & CMASK);
+                }
+            }
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0 && best != 0xFFFFFFFFu) atomicMin(&s_best, best);
+        __syncthreads();
+        if (tid < (int)a.n_lut) {
+            uint64_t key = 0;
+            if (flag == 0) {
+                const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)tid * kLutSize + len);
+                if (M >= thr) key = pack_key(M, (uint32_t)(a.fv.bin_begin + s_best));
+            }
+            a.keys[(size_t)tid * a.n_reads + read] = key;
+        }
+    }
+}
+
+size_t postings_smem_bytes(uint64_t n_bins_local, int counter_bits, uint32_t *cnt_words)
+{
+    const uint32_t per = 32 / counter_bits;
+    const uint32_t words = (uint32_t)((n_bins_local + 1 + per - 1) / per + 1);     // + the sentinel's counter
+    if (cnt_words) *cnt_words = words;
+    return (size_t)2 * words * 4 + kPostPiece * 4 + kPostPiece + 32;
+}
+
+}  // namespace
+
+// Applicable: wide row, k-mer index fits 32 bits, bin ids fit 16 bits with the sentinel, 8-bit counters fit shared memory.
+bool postings_applicable(const FilterView &fv)
+{
+    return fv.stride > 4 && fv.hp.k <= 15 && fv.n_bins_local < 65535 && fv.hp.n_blocks > 0 &&
+           postings_smem_bytes(fv.n_bins_local, 8, nullptr) <= 200u * 1024u;
+}
+
+// Average list length in 16-byte units over a sample of k-mers (size estimate before committing to the build).
+// d_scratch: at least n_sample uint32.  Synchronises the stream.
+int postings_sample_units(const FilterView &fv, uint32_t *d_scratch, uint32_t n_sample, double *mean_units, int sm_count,
+                          cudaStream_t st)
+{
+    const uint64_t n_kmers = 1ull << (2 * fv.hp.k);
+    const uint64_t step = n_kmers / n_sample ? n_kmers / n_sample : 1;
+    postings_count_kernel<<<sm_count * 8, 256, 0, st>>>(fv, step / 2, step, n_sample, d_scratch);
+    std::vector<uint32_t> h(n_sample);
+    if (cudaMemcpyAsync(h.data(), d_scratch, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    double s = 0;
+    for (uint32_t v : h) s += v;
+    *mean_units = s / n_sample;
+    return 1;
+}
+
+// Pass 1 + scan: d_ptr[4^k + 1] (uint32 units).  Returns launches or < 0; *total_units = d_ptr[4^k] (host), stream synchronised.
+int postings_build_ptr(const FilterView &fv, uint32_t *d_ptr, uint64_t *total_units, int sm_count, cudaStream_t st)
+{
+    const uint64_t n_kmers = 1ull << (2 * fv.hp.k);
+    postings_count_kernel<<<sm_count * 16, 256, 0, st>>>(fv, 0, 1, n_kmers, d_ptr);
+    if (cudaMemsetAsync(d_ptr + n_kmers, 0, 4, st) != cudaSuccess) return -1;
+    // the table never exceeds 2^32 units (64 GiB of ids): the caller checked the sampled estimate; a wrap would show below
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_ptr, d_ptr, n_kmers + 1, st);
+    if (cudaMallocAsync(&d_tmp, tmp_bytes, st) != cudaSuccess) return -1;
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_ptr, d_ptr, n_kmers + 1, st);
+    cudaFreeAsync(d_tmp, st);
+    uint32_t last = 0;
+    if (cudaMemcpyAsync(&last, d_ptr + n_kmers, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    *total_units = last;
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+int postings_fill(const FilterView &fv, const uint32_t *d_ptr, uint16_t *d_ids, int sm_count, cudaStream_t st)
+{
+    postings_fill_kernel<<<sm_count * 16, 256, 0, st>>>(fv, 1ull << (2 * fv.hp.k), d_ptr, d_ids);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// counter width by the longest read of the launch; returns launches, -1 on error, -2 if this launch cannot use postings
+int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint16_t *d_ids, uint32_t max_read_len, int sm_count,
+                          cudaStream_t st)
+{
+    if (a.n_reads == 0) return 0;
+    if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut) return -1;
+    const uint32_t k = a.fv.hp.k;
+    const bool narrow = max_read_len != 0 && (max_read_len < k || max_read_len - k + 1 <= 255);
+    uint32_t cnt_words = 0;
+    const size_t smem = postings_smem_bytes(a.fv.n_bins_local, narrow ? 8 : 16, &cnt_words);
+    if (smem > 220u * 1024u) return -2;
+    const uint4 *ids = reinterpret_cast<const uint4 *>(d_ids);
+    int occ = 1;
+    if (narrow) {
+        cudaFuncSetAttribute(count_postings_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_postings_kernel<8>, kPostThreads, smem);
+    } else {
+        cudaFuncSetAttribute(count_postings_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_postings_kernel<16>, kPostThreads, smem);
+    }
+    if (occ < 1) occ = 1;
+    const uint64_t cap = (uint64_t)sm_count * occ;
+    const uint32_t gx = (uint32_t)(a.n_reads < cap ? a.n_reads : cap);
+    if (narrow) count_postings_kernel<8><<<gx, kPostThreads, smem, st>>>(a, d_ptr, ids, cnt_words);
+    else count_postings_kernel<16><<<gx, kPostThreads, smem, st>>>(a, d_ptr, ids, cnt_words);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace rb

@@ -71,6 +71,10 @@ struct rb_ibf {
     mutable int table_span = 0;             // k-mers per entry: 1 = one k-mer per lane (ibf_table.cu), 2..4 = window
                                             // entries loaded by adjacent lanes (ibf_wtable.cu)
     mutable uint64_t table_bytes = 0;
+    // wide filters: k-mer postings table (ibf_postings.cu) instead of the dense window table
+    mutable int table_kind = 0;             // 0 none, 1 dense k-mer / window table, 2 postings
+    mutable uint32_t *d_post_ptr = nullptr;
+    mutable uint16_t *d_post_ids = nullptr;
     mutable bool table_tried = false;
     mutable uint64_t table_budget = 0;      // 0 = automatic
     // streams, events and staging buffers of rb_ibf_count_batch, kept between calls (one set per concurrent caller)
@@ -178,11 +182,13 @@ void destroy(rb_ibf *f)
 {
     if (!f) return;
     free_call_contexts(f);
-    if (f->d_words || f->d_err || f->d_table) {
+    if (f->d_words || f->d_err || f->d_table || f->d_post_ptr || f->d_post_ids) {
         DeviceGuard g(f->device);
         if (f->d_words) cudaFree(f->d_words);
         if (f->d_err) cudaFree(f->d_err);
         if (f->d_table) cudaFree(f->d_table);
+        if (f->d_post_ptr) cudaFree(f->d_post_ptr);
+        if (f->d_post_ids) cudaFree(f->d_post_ids);
     }
     delete f;
 }
@@ -266,6 +272,7 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
 {
     std::lock_guard<std::mutex> lock(f->table_mu);
     if (f->d_table) return f->d_table;
+    if (f->table_kind == 2) return reinterpret_cast<const uint64_t *>(f->d_post_ptr);
     if (f->table_tried && !force) return nullptr;
     if (!force && n_reads < kTableMinReads) return nullptr;     // not "tried": a later large batch builds it
     f->table_tried = true;
@@ -279,6 +286,39 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     uint64_t cap = 80ull << 30;
     if (const char *gb = std::getenv("RB_KMER_TABLE_MAX_GB")) cap = (uint64_t)std::max(0, std::atoi(gb)) << 30;
     const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>((uint64_t)(free_b * 0.6), cap);
+    if (f->col_words > 4) {
+        // wide rows: postings.  Size known only after counting: sample first, then count everything, then fill.
+        const rb::FilterView fv = view_of(f);
+        if (!rb::postings_applicable(fv)) return nullptr;
+        const uint64_t n_kmers = 1ull << (2 * f->k);
+        const uint64_t ptr_bytes = (n_kmers + 1) * 4;
+        if (ptr_bytes > budget) return nullptr;
+        uint32_t *d_ptr = nullptr;
+        if (cudaMalloc(&d_ptr, ptr_bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        auto give_up = [&]() -> const uint64_t * { cudaFree(d_ptr); cudaGetLastError(); return nullptr; };
+        const uint32_t n_sample = (uint32_t)std::min<uint64_t>(65536, n_kmers);
+        double mean_units = 0;
+        if (rb::postings_sample_units(fv, d_ptr, n_sample, &mean_units, f->sm_count, st) < 0) return give_up();
+        const double est_units = mean_units * (double)n_kmers;
+        if (est_units * 16.0 * 0.95 + (double)ptr_bytes > (double)budget || est_units > 4.0e9) return give_up();
+        uint64_t total_units = 0;
+        int n1 = rb::postings_build_ptr(fv, d_ptr, &total_units, f->sm_count, st);
+        if (n1 < 0) return give_up();
+        const uint64_t ids_bytes = std::max<uint64_t>(16, total_units * 16);
+        if (ids_bytes + ptr_bytes > budget) return give_up();
+        uint16_t *d_ids = nullptr;
+        if (cudaMalloc(&d_ids, ids_bytes) != cudaSuccess) return give_up();
+        int n2 = rb::postings_fill(fv, d_ptr, d_ids, f->sm_count, st);
+        if (n2 < 0 || cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d_ids); return give_up(); }
+        g_launches += (uint64_t)(1 + n1 + n2);
+        f->d_post_ptr = d_ptr;
+        f->d_post_ids = d_ids;
+        f->table_kind = 2;
+        f->table_span = 1;
+        f->table_entries = n_kmers;
+        f->table_bytes = ids_bytes + ptr_bytes;
+        return reinterpret_cast<const uint64_t *>(d_ptr);
+    }
     int max_span = f->col_words <= 2 ? 4 : 1;
     if (const char *sp_env = std::getenv("RB_KMER_TABLE_SPAN")) max_span = std::min(4, std::max(1, std::atoi(sp_env)));
     int span = 0;
@@ -297,6 +337,7 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     if (n < 0 || cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(t); cudaGetLastError(); return nullptr; }
     g_launches += (uint64_t)n;
     f->d_table = t;
+    f->table_kind = 1;
     f->table_entries = entries;
     f->table_span = span;
     f->table_bytes = need;
@@ -306,8 +347,16 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
 void drop_table(rb_ibf *f)
 {
     std::lock_guard<std::mutex> lock(f->table_mu);
-    if (f->d_table) { cudaDeviceSynchronize(); cudaFree(f->d_table); }
+    if (f->d_table || f->d_post_ptr || f->d_post_ids) {
+        cudaDeviceSynchronize();
+        if (f->d_table) cudaFree(f->d_table);
+        if (f->d_post_ptr) cudaFree(f->d_post_ptr);
+        if (f->d_post_ids) cudaFree(f->d_post_ids);
+    }
     f->d_table = nullptr;
+    f->d_post_ptr = nullptr;
+    f->d_post_ids = nullptr;
+    f->table_kind = 0;
     f->table_entries = 0;
     f->table_span = 0;
     f->table_bytes = 0;
@@ -1033,8 +1082,9 @@ int rb_ibf_info(const rb_ibf *f, rb_ibf_info_t *out)
     out->device_bytes = f->n_local_words * 8; out->device = f->device; out->shard = f->shard; out->n_shards = f->n_shards;
     {
         std::lock_guard<std::mutex> lock(f->table_mu);
-        out->kmer_table_bytes = f->d_table ? f->table_bytes : 0;
-        out->kmer_table_span = f->d_table ? f->table_span : 0;
+        out->kmer_table_bytes = f->table_kind ? f->table_bytes : 0;
+        out->kmer_table_span = f->table_kind ? f->table_span : 0;
+        out->kmer_table_kind = f->table_kind;
     }
     return RB_OK;
 }
@@ -1047,7 +1097,7 @@ int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stre
     drop_table(f);
     f->table_budget = max_table_bytes;
     if (!ensure_table(f, (cudaStream_t)stream, true))
-        return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable (row > 4 words, k > 16) or over the memory budget");
+        return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable (k > 16, bins >= 65535 for postings) or over the memory budget");
     return RB_OK;
 }
 
@@ -1057,7 +1107,7 @@ const uint64_t *rb_ibf_device_kmer_table(const rb_ibf *f)
 {
     if (!f) return nullptr;
     std::lock_guard<std::mutex> lock(f->table_mu);
-    return f->d_table;
+    return f->table_kind == 2 ? reinterpret_cast<const uint64_t *>(f->d_post_ids) : f->d_table;
 }
 
 // filter.resizeBins(n), src/IBF/IBFBuild.cpp:274 (update_filter): the number of rows stays, rows get wider
@@ -1167,6 +1217,12 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     const uint64_t *table = nullptr;
     if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3, n_reads);   // 3..5: table kernels
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
+    if (table && f->table_kind == 2) {
+        int n = rb::launch_count_postings(a, f->d_post_ptr, f->d_post_ids, max_read_len, f->sm_count, (cudaStream_t)stream);
+        if (n == -1) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        if (n >= 0) { g_launches += (uint64_t)n; return RB_OK; }
+        table = nullptr;                          // -2: this launch's reads need wider counters than shared memory holds
+    }
     if (table) {
         // selector 4 (shared-memory atomic counters) exists for one k-mer per entry only
         int n = f->table_span >= 2

@@ -153,9 +153,20 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
     bases, off = synth.ragged_reads(plan["bases"], RAGGED, seed=7, frac_from_ref=0.7, n_frac=0.003, lower_frac=0.1)
     lut = rb.threshold_lut(0.1, k)
     if kernel.startswith("table"):
-        if gf.bin_width > 4:
-            with pytest.raises(rb.RBError):
-                gf.count_batch(np.frombuffer(b"ACGTACGTACGTACGTACGT", np.uint8), np.array([0, 20], np.uint64), lut)
+        if gf.bin_width > 4:                             # wide rows: postings table (sorted bin lists per k-mer)
+            exp = of.count_batch(bases, off, lut, n_threads=4)
+            gf.enable_kmer_table(0)
+            assert gf.kmer_table_kind() == 2 and gf.kmer_table_bytes() > 4 ** k * 4
+            assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)          # long reads: 16-bit counters
+            short = [250] * 70 + [0, 1, k - 1, k, k + 1, 31, 32, 33, 64, 100, 249, 251, 254 + k, 255 + k - 1]
+            sb, so = synth.ragged_reads(plan["bases"], short, seed=12, frac_from_ref=0.7, n_frac=0.004, lower_frac=0.1)
+            sb[int(so[5]):int(so[6])] = ord("N")
+            sb[int(so[7]) + 100] = ord("U")
+            sexp = of.count_batch(sb, so, lut, n_threads=4)
+            assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)             # <= 255 positions: 8-bit counters
+            assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+            gf.disable_kmer_table()
+            assert gf.kmer_table_kind() == 0
             return
         exp = of.count_batch(bases, off, lut, n_threads=4)
         span1 = 4 ** k * 16 * gf.bin_width
