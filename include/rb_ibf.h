@@ -223,6 +223,12 @@ RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stre
  * 5 k-mer table, window tables always through the warp-per-read kernel (auto uses the
  * group-per-read kernel when every read of the launch has <= 127*span positions). */
 RB_API int rb_set_count_kernel(int which);
+/* Build kernel selection for tests/benchmarks: 0 auto, 1 one 64-bit RED.OR per (k-mer, hash) straight
+ * into the interleaved matrix, 2 column build (a bin's bit column is filled in shared memory, then
+ * 32x32 bit tiles are transposed into the matrix) whenever noOfBlocks bits fit in shared memory
+ * (<= ~1.7 M rows; the reference's default fragment_size = 100 000 gives 1 236 269).  Auto takes the
+ * column build when it fits and the call has at least one fragment and one bin per SM. */
+RB_API int rb_set_insert_kernel(int which);
 /* Number of kernels this library launched since load (all threads); evidence for gpu_launches. */
 RB_API uint64_t rb_kernel_launches(void);
 

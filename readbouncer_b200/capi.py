@@ -27,7 +27,7 @@ EXPORTS = [
     "rb_threshold_lut", "rb_cut_out_nnns", "rb_fragment_schedule", "rb_ibf_create", "rb_ibf_load",
     "rb_ibf_load_shard", "rb_ibf_from_words", "rb_ibf_store", "rb_ibf_download", "rb_ibf_free", "rb_ibf_info",
     "rb_ibf_device_words", "rb_ibf_device_kmer_table", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
-    "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_kernel_launches",
+    "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_set_insert_kernel", "rb_kernel_launches",
     "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
     "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins", "rb_host_pack_info", "rb_transfer_bytes",
 ]
@@ -100,6 +100,7 @@ def lib():
         "rb_ibf_count_batch_dev": (i32, [vp, vp, vp, u64, u32, vp, u32, vp, vp, vp, vp, vp]),
         "rb_keys_decode_dev": (i32, [vp, u64, vp, vp, vp, i32, vp]),
         "rb_set_count_kernel": (i32, [i32]),
+        "rb_set_insert_kernel": (i32, [i32]),
         "rb_kernel_launches": (u64, []),
         "rb_microbench_gather": (i32, [vp, u64, u32, u64, u32, vp, vp]),
         "rb_microbench_gather_coop": (i32, [vp, u64, u32, u32, u64, u32, vp, vp]),
@@ -157,6 +158,10 @@ def kernel_launches():
 
 def set_count_kernel(which):
     _check(lib().rb_set_count_kernel(int(which)))
+
+
+def set_insert_kernel(which):
+    _check(lib().rb_set_insert_kernel(int(which)))
 
 
 def microbench_gather(d_buf, n_rows, row_bytes, probes_per_thread, n_blocks, d_sink, stream=None):

@@ -67,6 +67,8 @@ bool wgroup_applicable(uint32_t k, int span, uint32_t max_read_len);
 int get_wtable_variant();
 void set_wtable_variant(int v);   // 0 auto (group-per-read kernel for short reads), 1 always warp-per-read
 int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cudaStream_t st);
+int get_insert_variant();
+void set_insert_variant(int v);   // 0 auto, 1 always 64-bit RED.OR per (k-mer, hash), 2 column build whenever the column fits
 int launch_keys_decode(const uint64_t *keys, uint64_t n, uint16_t *max_count, uint8_t *hit,
                        uint32_t *argmax_bin, cudaStream_t st);
 int launch_keys_decode_piece(const uint64_t *keys, const uint8_t *flag_in, uint64_t n, uint32_t n_lut, uint64_t stride,

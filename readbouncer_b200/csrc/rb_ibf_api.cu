@@ -816,6 +816,13 @@ int rb_set_count_kernel(int which)
     return RB_OK;
 }
 
+int rb_set_insert_kernel(int which)
+{
+    if (which < 0 || which > 2) return fail(RB_ERR_INVALID_ARG, "insert kernel selector must be 0..2");
+    rb::set_insert_variant(which);
+    return RB_OK;
+}
+
 // ---- scalar helpers ----------------------------------------------------------------------------
 uint64_t rb_ibf_size_bits(uint64_t fragment_length, uint32_t kmer_size, uint32_t n_hash, double max_fp,
                           uint64_t n_bins)

@@ -127,6 +127,13 @@ def test_fast_mod_exhaustive_edges(tmp_path):
     assert out.returncode == 0 and "fast_mod OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_bit_transpose_matches_definition(tmp_path):
+    """rb::transpose32 (the column build's 32 bins x 32 rows tile) against the bit-by-bit definition."""
+    exe = _compile(os.path.join(ROOT, "tests", "cpp", "test_transpose.cpp"), str(tmp_path / "test_transpose"), link=False)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("isa", ["5", "2", "0"])
 def test_host_packer_matches_restatement(tmp_path, isa):
     """Bit planes of the host packer (AVX-512 / AVX2 / scalar paths, thread pool) against a plain loop."""

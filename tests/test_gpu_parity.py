@@ -20,6 +20,7 @@ KERNELS = {"auto": 0, "tile": 1, "stream": 2, "table": 3, "table_atomic": 4, "ta
 def _reset_kernel_choice():
     yield
     rb.set_count_kernel(0)
+    rb.set_insert_kernel(0)
 
 
 def make_filter_pair(n_seqs, seq_len, fragment_length, k=13, seed=100, n_hash=3):
@@ -371,6 +372,108 @@ def test_insert_is_idempotent_and_order_free():
     perm = np.random.default_rng(0).permutation(len(plan["frag_bin"]))
     gf.insert_batch(plan["bases"], plan["frag_begin"][perm], plan["frag_end"][perm], plan["frag_bin"][perm])
     assert np.array_equal(gf.download(), before)
+
+
+# ---- column build (shared-memory bit columns + bit-tile transpose) vs the RED.OR kernel and the oracle ----------
+def _messy_reference(n_seqs, seq_len, seed):
+    """Sequences with N runs (cut by cutOutNNNs), lower-case bases and IUPAC codes (rank 4 k-mers are hashed too)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_seqs):
+        s = synth.random_bases(seq_len + int(rng.integers(0, 50)), seed + i).copy()
+        for _ in range(3):
+            a = int(rng.integers(0, len(s) - 40))
+            s[a:a + int(rng.integers(1, 30))] = ord("N")
+        low = rng.integers(0, len(s), 200)
+        s[low] |= 0x20
+        s[rng.integers(0, len(s), 20)] = ord("R")
+        out.append(s)
+    return out
+
+
+@pytest.mark.parametrize("n_seqs,seq_len,frag,k,scratch_mb", [
+    (3, 250_000, 100_000, 13, 0),        # the reference's default sizing: 1 236 269 rows, 154 KB columns, one word per row
+    (1, 700 * 2000 + 7, 2000, 13, 0),    # 701 bins (two 512-bin groups, partial last word), 24 785 rows
+    (1, 1300 * 2000 + 7, 2000, 15, 2),   # three groups, scratch capped at 2 MB: one 512-bin group per pass
+    (40, 3000, 100_000, 11, 0),          # one short fragment per bin, n_hash = 3, rows not a multiple of 1024
+    (3, 450_000, 200_000, 13, 0),        # 2 472 526 rows: the column (309 KB) no longer fits shared memory -> scratch columns in L2
+    (70, 30_000, 1_000_000, 13, 0),      # 12.4 M rows, 70 bins (two words per row), 1.5 MB columns through the L2 path
+])
+def test_column_build_equals_red_kernel_and_oracle(monkeypatch, n_seqs, seq_len, frag, k, scratch_mb):
+    if scratch_mb:
+        monkeypatch.setenv("RB_INSERT_SCRATCH_MB", str(scratch_mb))
+    ref = _messy_reference(n_seqs, seq_len, 300)
+    plan = synth.build_plan(ref, frag, k)
+    of = oracle.OracleIBF.create(plan["n_bins"], 3, k, plan["n_bits"])
+    of.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"], n_threads=4)
+    exp = of.words()[:plan["n_bits"] // 64]
+    got = {}
+    for variant in (1, 2):
+        rb.set_insert_kernel(variant)
+        gf = rb.IBF.create(plan["n_bins"], 3, k, plan["n_bits"])
+        launches0 = rb.kernel_launches()
+        gf.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+        got[variant] = rb.kernel_launches() - launches0
+        assert np.array_equal(gf.download(), exp), variant
+        gf.close()
+    assert got[1] == 1 and got[2] >= 5           # the column path really ran (3 list kernels + build + merge per pass)
+    if scratch_mb:
+        assert got[2] == 3 + 2 * 3
+
+
+def test_column_build_merges_into_existing_bits_shards_and_bad_bins():
+    """Second insert ORs into what is there; several fragments per bin; fragments shorter than k; a bin past the end
+    raises InsertSequenceException but the rest is written; bin shards take only their own columns."""
+    rb.set_insert_kernel(2)
+    ref = _messy_reference(2, 150 * 2000, 301)
+    plan = synth.build_plan(ref, 2000, 13)
+    n = len(plan["frag_bin"])
+    rng = np.random.default_rng(5)
+    fbin = plan["frag_bin"].copy()
+    fbin[rng.integers(0, n, 40)] = rng.integers(0, plan["n_bins"], 40)       # crowd some bins
+    fb = np.concatenate([plan["frag_begin"], [10, 500]]).astype(np.uint64)
+    fe = np.concatenate([plan["frag_end"], [10 + 12, 500]]).astype(np.uint64)       # 12 bases (< k) and empty
+    fbin = np.concatenate([fbin, [3, 4]]).astype(np.uint64)
+    of = oracle.OracleIBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    gf = rb.IBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    half = n // 2
+    for sl in (slice(0, half), slice(half, None)):
+        of.insert_batch(plan["bases"], fb[sl], fe[sl], fbin[sl])
+        gf.insert_batch(plan["bases"], fb[sl], fe[sl], fbin[sl])
+    exp = of.words()[:plan["n_bits"] // 64]
+    assert np.array_equal(gf.download(), exp)
+    # out-of-range bin: reported, everything else still inserted
+    g2 = rb.IBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    bad = fbin.copy()
+    bad[7] = plan["n_bins"]
+    with pytest.raises(rb.RBError) as e:
+        g2.insert_batch(plan["bases"], fb, fe, bad)
+    assert e.value.status == 7
+    o2 = oracle.OracleIBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
+    keep = np.arange(len(bad)) != 7
+    o2.insert_batch(plan["bases"], fb[keep], fe[keep], bad[keep])
+    assert np.array_equal(g2.download(), o2.words()[:plan["n_bits"] // 64])
+    # bin shards
+    full = exp.reshape(gf.n_blocks, gf.bin_width)
+    zeros = np.zeros(plan["n_bits"] // 64, np.uint64)
+    for s in range(3):
+        sh = rb.IBF.from_words(zeros, plan["n_bins"], 3, 13, plan["n_bits"], shard=s, n_shards=3)
+        sh.insert_batch(plan["bases"], fb, fe, fbin)
+        loc = sh.download().reshape(sh.n_blocks, sh.col_words)
+        assert np.array_equal(loc, full[:, sh.col_begin:sh.col_begin + sh.col_words]), s
+
+
+def test_golden_rebuild_with_column_build(known, golden_sparse):
+    """The reference's own .ibf fixtures, rebuilt through the column path (two fragments per bin pair)."""
+    rb.set_insert_kernel(2)
+    for name, fasta, k in (("lib_test", "lib_test.fasta", 13), ("lib_test1", "lib_test1.fasta", 13),
+                           ("classify_test", "classify_test.fasta", 15)):
+        seqs = [s for _, s in read_fasta(data_path(fasta))]
+        plan = synth.build_plan(seqs + seqs, 100000, k)
+        meta, words = golden_words(known, golden_sparse, name)
+        f = rb.IBF.create(plan["n_bins"], 3, k, plan["n_bits"])
+        f.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+        assert np.array_equal(f.download(), words[:plan["n_bits"] // 64]), name
 
 
 # ---- BASELINE config #1: usage=classify on testData/testQueries.fasta vs an IBF of a synthetic 5 Mb reference ---
