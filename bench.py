@@ -200,12 +200,18 @@ def run_ours(args, w, n_reads):
     d_fbin = torch.from_numpy(plan["frag_bin"].astype(np.int64)).to(dev)
     max_frag = int((plan["frag_end"] - plan["frag_begin"]).max())
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record(stream)
-    gf_full.insert_batch_dev(d_ref, d_fb, d_fe, d_fbin, len(plan["frag_bin"]), max_frag, stream=stream)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    build_ms = ev0.elapsed_time(ev1)
+    # the same fragments twice (inserts are idempotent ORs, so the bits are those of one build): the first call pays the
+    # one-off costs of the process (memory-pool growth for the scratch columns, kernel attributes), the second is timed
+    build_cold_ms = None
+    for it in range(2):
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        gf_full.insert_batch_dev(d_ref, d_fb, d_fe, d_fbin, len(plan["frag_bin"]), max_frag, stream=stream)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        build_ms = ev0.elapsed_time(ev1)
+        if it == 0:
+            build_cold_ms = build_ms
     n_kmers_ref = int(np.maximum(plan["frag_end"] - plan["frag_begin"], w["k"] - 1).sum() - (w["k"] - 1) * len(plan["frag_bin"]))
     del d_ref, d_fb, d_fe, d_fbin
     gf = gf_full
@@ -438,7 +444,7 @@ def run_ours(args, w, n_reads):
                    "thresholds_per_pass": n_lut, "l2_fetch_granularity": rb.get_l2_fetch_granularity(local), "error_rate": ERROR_RATE, "read_mix": "50% reference-derived @10% errors, 50% iid",
                    "l2": "no flush: inputs (%.0f MB reads + %.0f MB filter) exceed the 126 MB L2" % (
                        bases_np.nbytes / 1e6, plan["n_bits"] / 8e6),
-                   "hit_fraction": hits_dev / n_reads, "kmer_table_bytes": gf.kmer_table_bytes(), "kmer_table_span": gf.kmer_table_span(), "kmer_table_kind": gf.kmer_table_kind(), "ibf_build_ms_gpu": build_ms,
+                   "hit_fraction": hits_dev / n_reads, "kmer_table_bytes": gf.kmer_table_bytes(), "kmer_table_span": gf.kmer_table_span(), "kmer_table_kind": gf.kmer_table_kind(), "ibf_build_ms_gpu": build_ms, "ibf_build_ms_gpu_first_call": build_cold_ms,
                    "ibf_build_kmers_per_s": n_kmers_ref / (build_ms * 1e-3)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

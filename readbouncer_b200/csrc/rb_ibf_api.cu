@@ -402,6 +402,7 @@ constexpr int kSlots = 4;
 constexpr uint64_t kPieceBases = 8ull << 20, kPieceReads = 1ull << 18;   // env RB_PIECE_MB overrides the former
 constexpr uint64_t kPackTask = 128ull << 10;            // bases per packing task (a multiple of 32)
 constexpr uint64_t kStageBases = 512ull << 20;          // bases per round of the packed pipeline (192 MB of planes)
+constexpr double kAsciiShare = 0.2;                     // pieces shipped as ASCII next to the packed ones (pinned input, >= 8 pieces)
 
 struct DevBuf {
     void *p = nullptr;
@@ -651,32 +652,58 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
             // calling thread submits every piece as soon as its tasks are done.  Every piece has its own region of the
             // pinned staging buffer -- [low plane][high plane][bad plane], bit i = base base0 + i -- so it crosses PCIe
             // as ONE copy.
-            struct Region { uint64_t base0, nb, nw; size_t h_word, task0, n_tasks; };
+            //
+            // Mixed transfer: the packer (host cores) and the PCIe link are separate resources, so when the caller's bases
+            // are in pinned memory (the copy engine reads them without any host work) a share of the pieces is shipped as
+            // ASCII while the host threads pack the others; the ASCII pieces are queued first, so the link is busy from
+            // the start of the round.  RB_ASCII_SHARE overrides the share (0 = pack everything).
+            struct Region { uint64_t base0, nb, nw; size_t piece, h_word, task0, n_tasks; };
+            double ascii_share = 0.0;
+            {
+                cudaPointerAttributes at{};
+                const bool pinned_in = cudaPointerGetAttributes(&at, bases) == cudaSuccess && at.type == cudaMemoryTypeHost;
+                cudaGetLastError();
+                if (pinned_in && n_pieces >= 8) {
+                    ascii_share = kAsciiShare;
+                    if (const char *e = std::getenv("RB_ASCII_SHARE")) ascii_share = std::min(1.0, std::max(0.0, std::atof(e)));
+                }
+            }
+            double ascii_acc = 0.0;
             size_t p_begin = 0;
             while (p_begin < n_pieces) {
                 size_t p_end = p_begin + 1;
                 const uint64_t R0 = read_off[cut[p_begin]];
                 while (p_end < n_pieces && read_off[cut[p_end + 1]] - R0 <= stage_bases) ++p_end;
-                std::vector<Region> reg(p_end - p_begin);
+                std::vector<Region> reg;
+                reg.reserve(p_end - p_begin);
                 std::vector<uint32_t> task_piece;
                 size_t h_words = 0;
                 for (size_t p = p_begin; p < p_end; ++p) {
-                    Region &r = reg[p - p_begin];
+                    ascii_acc += ascii_share;
+                    if (ascii_acc >= 1.0) {                                   // this piece goes as it is, right now
+                        ascii_acc -= 1.0;
+                        int s3 = submit(p, nullptr, nullptr, nullptr, 0);
+                        if (s3 != RB_OK) return s3;
+                        continue;
+                    }
+                    Region r{};
                     const uint64_t b0 = read_off[cut[p]], b1 = read_off[cut[p + 1]];
+                    r.piece = p;
                     r.base0 = b0 - ((b0 - R0) & 31u);                        // word aligned, never before the round's first base
                     r.nb = b1 - r.base0;
                     r.nw = ((r.nb + 31) / 32 + 2 + 15) / 16 * 16;             // 64-byte multiples: streaming stores, aligned planes
                     r.h_word = h_words;
                     r.task0 = task_piece.size();
                     r.n_tasks = (size_t)std::max<uint64_t>(1, (r.nb + kPackTask - 1) / kPackTask);
-                    task_piece.insert(task_piece.end(), r.n_tasks, (uint32_t)(p - p_begin));
+                    task_piece.insert(task_piece.end(), r.n_tasks, (uint32_t)reg.size());
                     h_words += 3 * r.nw;
+                    reg.push_back(r);
                 }
                 int s2;
-                if ((s2 = ctx->h_planes.reserve(h_words * 4)) != RB_OK) return s2;
+                if ((s2 = ctx->h_planes.reserve(h_words * 4 + 64)) != RB_OK) return s2;
                 uint32_t *const h_base = static_cast<uint32_t *>(ctx->h_planes.p);
                 const size_t n_tasks = task_piece.size();
-                size_t next_piece = p_begin;
+                size_t next_reg = 0;
                 int err = RB_OK;
                 auto pack_task = [&](size_t t) {
                     const Region &r = reg[task_piece[t]];
@@ -687,20 +714,20 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
                     rb::pack_bases(bases + r.base0 + o, m, h, h + r.nw, h + 2 * r.nw, true);
                 };
                 auto poll = [&](size_t tasks_done) {
-                    while (err == RB_OK && next_piece < p_end) {
-                        const Region &r = reg[next_piece - p_begin];
+                    while (err == RB_OK && next_reg < reg.size()) {
+                        const Region &r = reg[next_reg];
                         if (tasks_done < r.task0 + r.n_tasks) break;
-                        const int s = (int)(next_piece % kSlots);
+                        const int s = (int)(r.piece % kSlots);
                         if ((err = ctx->d_in[s].reserve(r.nw * 12)) != RB_OK) break;
                         uint32_t *d = static_cast<uint32_t *>(ctx->d_in[s].p);
                         cudaError_t ce = cudaMemcpyAsync(d, h_base + r.h_word, r.nw * 12, cudaMemcpyHostToDevice, ctx->st[s]);
                         if (ce != cudaSuccess) { err = fail(RB_ERR_CUDA, std::string("plane copy: ") + cudaGetErrorString(ce)); break; }
                         g_h2d_bytes += r.nw * 12;
-                        err = submit(next_piece, d, d + r.nw, d + 2 * r.nw, r.base0);
-                        ++next_piece;
+                        err = submit(r.piece, d, d + r.nw, d + 2 * r.nw, r.base0);
+                        ++next_reg;
                     }
                 };
-                rb::parallel_tasks(n_tasks, pack_task, poll);
+                if (n_tasks) rb::parallel_tasks(n_tasks, pack_task, poll);
                 t_packed = ms_since();
                 poll(n_tasks);
                 if (err != RB_OK) return err;

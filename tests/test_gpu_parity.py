@@ -271,8 +271,15 @@ def test_host_buffer_pipeline_packed_pieces_and_rounds(monkeypatch):
     r_am = torch.empty(2 * n, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
     r_flag = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
     P = rb.capi._np_ptr
-    for pack in ("1", "0"):
+    xfer = {}
+    for pack, share in (("1", None), ("1", "0"), ("1", "0.5"), ("0", None)):
+        # pinned bases: a share of the pieces crosses PCIe as ASCII while the host threads pack the others
         monkeypatch.setenv("RB_HOST_PACK", pack)
+        if share is None:
+            monkeypatch.delenv("RB_ASCII_SHARE", raising=False)
+        else:
+            monkeypatch.setenv("RB_ASCII_SHARE", share)
+        x0 = rb.transfer_bytes()[0]
         r_max[:] = 0xFFFF; r_hit[:] = 7; r_am[:] = 5; r_flag[:] = 9
         rb.capi._check(rb.lib().rb_ibf_count_batch(gf._h, P(hb), P(ho), n, P(luts), 2, None, None, P(r_max), P(r_hit), P(r_am),
                                                    P(r_flag), None))
@@ -281,6 +288,8 @@ def test_host_buffer_pipeline_packed_pieces_and_rounds(monkeypatch):
             assert np.array_equal(r_hit[t * n:(t + 1) * n], exp[t]["hit"]), pack
             assert np.array_equal(r_am[t * n:(t + 1) * n], exp[t]["argmax_bin"]), pack
         assert np.array_equal(r_flag, exp[0]["short_read"]), pack
+        xfer[(pack, share)] = rb.transfer_bytes()[0] - x0
+    assert xfer[("1", "0")] < xfer[("1", None)] < xfer[("1", "0.5")] < xfer[("0", None)]
 
 
 def test_two_threshold_tables_in_one_pass():
