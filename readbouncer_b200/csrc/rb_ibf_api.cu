@@ -402,7 +402,10 @@ constexpr int kSlots = 4;
 constexpr uint64_t kPieceBases = 8ull << 20, kPieceReads = 1ull << 18;   // env RB_PIECE_MB overrides the former
 constexpr uint64_t kPackTask = 128ull << 10;            // bases per packing task (a multiple of 32)
 constexpr uint64_t kStageBases = 512ull << 20;          // bases per round of the packed pipeline (192 MB of planes)
-constexpr double kAsciiShare = 0.2;                     // pieces shipped as ASCII next to the packed ones (pinned input, >= 8 pieces)
+// share of the pieces shipped as ASCII next to the packed ones (pinned input, >= 8 pieces).  0: on the measured host the
+// packer and the copy engine compete for the same host-memory bandwidth, every share > 0 was slower
+// (profiles/r1_k_e2e_ascii_share_sweep.jsonl); RB_ASCII_SHARE turns it on for hosts where they do not.
+constexpr double kAsciiShare = 0.0;
 
 struct DevBuf {
     void *p = nullptr;
@@ -656,7 +659,7 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
             // Mixed transfer: the packer (host cores) and the PCIe link are separate resources, so when the caller's bases
             // are in pinned memory (the copy engine reads them without any host work) a share of the pieces is shipped as
             // ASCII while the host threads pack the others; the ASCII pieces are queued first, so the link is busy from
-            // the start of the round.  RB_ASCII_SHARE overrides the share (0 = pack everything).
+            // the start of the round.  Off by default (kAsciiShare); RB_ASCII_SHARE sets the share.
             struct Region { uint64_t base0, nb, nw; size_t piece, h_word, task0, n_tasks; };
             double ascii_share = 0.0;
             {

@@ -272,7 +272,7 @@ def test_host_buffer_pipeline_packed_pieces_and_rounds(monkeypatch):
     r_flag = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
     P = rb.capi._np_ptr
     xfer = {}
-    for pack, share in (("1", None), ("1", "0"), ("1", "0.5"), ("0", None)):
+    for pack, share in (("1", None), ("1", "0.25"), ("1", "0.5"), ("0", None)):
         # pinned bases: a share of the pieces crosses PCIe as ASCII while the host threads pack the others
         monkeypatch.setenv("RB_HOST_PACK", pack)
         if share is None:
@@ -289,7 +289,7 @@ def test_host_buffer_pipeline_packed_pieces_and_rounds(monkeypatch):
             assert np.array_equal(r_am[t * n:(t + 1) * n], exp[t]["argmax_bin"]), pack
         assert np.array_equal(r_flag, exp[0]["short_read"]), pack
         xfer[(pack, share)] = rb.transfer_bytes()[0] - x0
-    assert xfer[("1", "0")] < xfer[("1", None)] < xfer[("1", "0.5")] < xfer[("0", None)]
+    assert xfer[("1", None)] < xfer[("1", "0.25")] < xfer[("1", "0.5")] < xfer[("0", None)]
 
 
 def test_two_threshold_tables_in_one_pass():

@@ -25,18 +25,20 @@ r_flag = torch.empty(n, dtype=torch.uint8, pin_memory=True).numpy()
 call = lambda: rb.capi._check(rb.lib().rb_ibf_count_batch(gf._h, P(hb), P(ho), n, P(luts), 2, None, None, P(r_max), P(r_hit), P(r_am), P(r_flag), None))
 call()
 ref_max = r_max.copy()
-for piece in ("8", "4", "16"):
+pieces = os.environ.get("SWEEP_PIECES", "8,4,16").split(",")
+shares = os.environ.get("SWEEP_SHARES", "0,0.1,0.15,0.2,0.25,0.3,0.4,0.5,1").split(",")
+for piece in pieces:
     os.environ["RB_PIECE_MB"] = piece
-    for share in ("0", "0.1", "0.15", "0.2", "0.25", "0.3", "0.4", "0.5", "1"):
+    for share in shares:
         os.environ["RB_ASCII_SHARE"] = share
         for _ in range(3):
             call()
         x0 = rb.transfer_bytes()
         ts = []
-        for _ in range(12):
+        for _ in range(int(os.environ.get('SWEEP_CALLS', '12'))):
             t0 = time.perf_counter(); call(); ts.append(time.perf_counter() - t0)
         x1 = rb.transfer_bytes()
         assert np.array_equal(r_max, ref_max)
         ts.sort()
         print(json.dumps({"piece_mb": int(piece), "ascii_share": float(share), "reads": n, "median_ms": 1e3 * ts[len(ts) // 2], "min_ms": 1e3 * ts[0],
-                          "mean_ms": 1e3 * sum(ts) / len(ts), "chunks_per_s_mean": n * len(ts) / sum(ts), "h2d_bytes": (x1[0] - x0[0]) // 12}), flush=True)
+                          "mean_ms": 1e3 * sum(ts) / len(ts), "chunks_per_s_mean": n * len(ts) / sum(ts), "h2d_bytes": (x1[0] - x0[0]) // max(1, len(ts))}), flush=True)
