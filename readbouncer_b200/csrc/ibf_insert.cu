@@ -319,7 +319,7 @@ int insert_column_mode(const InsertArgs &a)
 }
 
 // Returns launches, -1 on a CUDA error, -2 when the scratch memory could not be had (caller falls back to insert_kernel).
-static int launch_insert_columns(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cudaStream_t st)
+static int launch_insert_columns(const InsertArgs &a, uint64_t max_frag_len, int sm_count, ScratchBuf *scr, cudaStream_t st)
 {
     ColumnArgs c{};
     c.in = a;
@@ -332,7 +332,7 @@ static int launch_insert_columns(const InsertArgs &a, uint64_t max_frag_len, int
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return -1;
     const uint64_t groups = (n_local + kTrBins - 1) / kTrBins;
-    uint64_t budget = free_b / 2;
+    uint64_t budget = (free_b + scr->cap) / 2;             // the cached block is ours to reuse
     if (const char *e = std::getenv("RB_INSERT_SCRATCH_MB")) {            // tests: force several passes
         const uint64_t mb = std::strtoull(e, nullptr, 10);
         if (mb) budget = std::min<uint64_t>(budget, mb << 20);
@@ -343,29 +343,32 @@ static int launch_insert_columns(const InsertArgs &a, uint64_t max_frag_len, int
     // the last group of a pass may be partial: never allocate more columns than exist
     const uint64_t scratch_cols = groups_per_pass * kTrBins < n_local ? groups_per_pass * kTrBins : n_local;
 
-    uint32_t *d_meta = nullptr;        // bin_ptr [n_local + 1] | bin_fill [n_local] | frag_list [n_frags]
-    void *d_tmp = nullptr;
+    // one cached allocation (kept by the filter handle between calls, so only the first build pays for it):
+    // bin_ptr [n_local + 1] | bin_fill [n_local] | frag_list [n_frags] | CUB scan storage | scratch columns
     const uint64_t meta_words = (n_local + 1) + n_local + a.n_frags;
-    if (cudaMallocAsync(&d_meta, meta_words * 4, st) != cudaSuccess) { cudaGetLastError(); return -2; }
-    if (cudaMallocAsync(&c.scratch, scratch_cols * col_bytes, st) != cudaSuccess) {
-        cudaGetLastError();
-        cudaFreeAsync(d_meta, st);
-        return -2;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(n_local + 1), st);
+    const size_t meta_bytes = (meta_words * 4 + 255) & ~(size_t)255, tmp_pad = (tmp_bytes + 255) & ~(size_t)255;
+    const size_t need = meta_bytes + tmp_pad + scratch_cols * col_bytes;
+    if (need > scr->cap) {
+        if (scr->p) cudaFree(scr->p);           // synchronises: nothing in flight uses the old block afterwards
+        scr->p = nullptr; scr->cap = 0;
+        if (cudaMalloc(&scr->p, need) != cudaSuccess) { cudaGetLastError(); scr->p = nullptr; return -2; }
+        scr->cap = need;
     }
+    uint8_t *const base = static_cast<uint8_t *>(scr->p);
+    uint32_t *const d_meta = reinterpret_cast<uint32_t *>(base);
+    void *const d_tmp = base + meta_bytes;
+    c.scratch = reinterpret_cast<uint32_t *>(base + meta_bytes + tmp_pad);
     c.bin_ptr = d_meta; c.bin_fill = d_meta + n_local + 1; c.frag_list = c.bin_fill + n_local;
     int launches = 0;
     bool ok = cudaMemsetAsync(d_meta, 0, (2 * n_local + 1) * 4, st) == cudaSuccess;
     const uint32_t fgrid = (uint32_t)std::min<uint64_t>((a.n_frags + 255) / 256, (uint64_t)sm_count * 8);
     if (ok) {
         column_count_kernel<<<fgrid, 256, 0, st>>>(c);
-        size_t tmp_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c.bin_ptr, c.bin_ptr, (int)(n_local + 1), st);
-        ok = cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, st) == cudaSuccess;
-        if (ok) {
-            cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, c.bin_ptr, c.bin_ptr, (int)(n_local + 1), st);
-            column_fill_kernel<<<fgrid, 256, 0, st>>>(c);
-            launches += 3;
-        }
+        cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, c.bin_ptr, c.bin_ptr, (int)(n_local + 1), st);
+        column_fill_kernel<<<fgrid, 256, 0, st>>>(c);
+        launches += 3;
     }
     constexpr size_t tr_smem = 16 * kTrWarpStride * sizeof(uint32_t);
     if (ok)     // per-device attributes; setting them again is harmless
@@ -389,13 +392,10 @@ static int launch_insert_columns(const InsertArgs &a, uint64_t max_frag_len, int
         launches += 2;
         ok = cudaGetLastError() == cudaSuccess;
     }
-    if (d_tmp) cudaFreeAsync(d_tmp, st);
-    cudaFreeAsync(c.scratch, st);
-    cudaFreeAsync(d_meta, st);
     return ok && cudaGetLastError() == cudaSuccess ? launches : -1;
 }
 
-int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cudaStream_t st)
+int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, ScratchBuf *scr, cudaStream_t st)
 {
     if (a.n_frags == 0) return 0;
     // column build (variant 0 auto, 1 always RED.OR, 2 column build whenever applicable).  Auto: shared-memory columns
@@ -403,9 +403,9 @@ int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cuda
     const int variant = get_insert_variant();
     const int mode = variant == 1 ? 0 : insert_column_mode(a);
     const uint64_t n_local = a.bin_end - a.bin_begin;
-    if (mode != 0 && (variant == 2 || (mode == 1 && a.n_frags >= (uint64_t)sm_count && n_local >= (uint64_t)sm_count) ||
+    if (mode != 0 && scr && (variant == 2 || (mode == 1 && a.n_frags >= (uint64_t)sm_count && n_local >= (uint64_t)sm_count) ||
                       (mode == 2 && a.n_frags * (max_frag_len ? max_frag_len : 1) >= (64ull << 20)))) {
-        int n = launch_insert_columns(a, max_frag_len, sm_count, st);
+        int n = launch_insert_columns(a, max_frag_len, sm_count, scr, st);
         if (n != -2) return n;
     }
     uint32_t gx = (uint32_t)(a.n_frags < 16384 ? a.n_frags : 16384);

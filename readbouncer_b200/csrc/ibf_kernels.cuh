@@ -66,7 +66,10 @@ int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint1
 bool wgroup_applicable(uint32_t k, int span, uint32_t max_read_len);
 int get_wtable_variant();
 void set_wtable_variant(int v);   // 0 auto (group-per-read kernel for short reads), 1 always warp-per-read
-int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, cudaStream_t st);
+// device memory the column build works in (fragment lists, scan storage, bit columns); owned by the caller and kept
+// between calls so that only the first build of a handle allocates
+struct ScratchBuf { void *p = nullptr; size_t cap = 0; };
+int launch_insert(const InsertArgs &a, uint64_t max_frag_len, int sm_count, ScratchBuf *scr, cudaStream_t st);
 int get_insert_variant();
 void set_insert_variant(int v);   // 0 auto, 1 always 64-bit RED.OR per (k-mer, hash), 2 column build whenever the column fits
 int launch_keys_decode(const uint64_t *keys, uint64_t n, uint16_t *max_count, uint8_t *hit,

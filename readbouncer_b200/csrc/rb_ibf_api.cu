@@ -76,6 +76,8 @@ struct rb_ibf {
     mutable uint32_t *d_post_ptr = nullptr;
     mutable uint16_t *d_post_ids = nullptr;
     mutable bool table_tried = false;
+    // working memory of the column build (ibf_insert.cu), kept between insert calls; released when the k-mer table is built
+    mutable rb::ScratchBuf build_scratch;
     mutable uint64_t table_budget = 0;      // 0 = automatic
     // streams, events and staging buffers of rb_ibf_count_batch, kept between calls (one set per concurrent caller)
     mutable std::mutex ctx_mu;
@@ -182,8 +184,9 @@ void destroy(rb_ibf *f)
 {
     if (!f) return;
     free_call_contexts(f);
-    if (f->d_words || f->d_err || f->d_table || f->d_post_ptr || f->d_post_ids) {
+    if (f->d_words || f->d_err || f->d_table || f->d_post_ptr || f->d_post_ids || f->build_scratch.p) {
         DeviceGuard g(f->device);
+        if (f->build_scratch.p) cudaFree(f->build_scratch.p);
         if (f->d_words) cudaFree(f->d_words);
         if (f->d_err) cudaFree(f->d_err);
         if (f->d_table) cudaFree(f->d_table);
@@ -278,6 +281,10 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     f->table_tried = true;
     const char *env = std::getenv("RB_KMER_TABLE");
     if (!force && env && env[0] == '0') return nullptr;
+    if (f->build_scratch.p) {             // the build is over: its working memory goes to the table
+        cudaFree(f->build_scratch.p);
+        f->build_scratch = rb::ScratchBuf{};
+    }
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     // Sized for 180 GB of HBM: the widest window whose table fits 60 % of the free memory (at most 80 GiB)
@@ -1195,7 +1202,7 @@ int rb_ibf_insert_batch_dev(rb_ibf *f, const uint8_t *d_bases, const uint64_t *d
     a.bin_begin = 64 * f->col_begin; a.bin_end = a.bin_begin + f->n_bins_local; a.n_bins = f->n_bins;
     a.hp = f->hp; a.bases = d_bases; a.frag_begin = d_frag_begin; a.frag_end = d_frag_end; a.frag_bin = d_frag_bin;
     a.n_frags = n_frags; a.error_flag = f->d_err;
-    int n = rb::launch_insert(a, max_frag_len, f->sm_count, (cudaStream_t)stream);
+    int n = rb::launch_insert(a, max_frag_len, f->sm_count, &f->build_scratch, (cudaStream_t)stream);
     if (n < 0) return fail(RB_ERR_CUDA, std::string("insert launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     g_launches += (uint64_t)n;
     return RB_OK;
