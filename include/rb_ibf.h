@@ -174,6 +174,11 @@ RB_API int rb_host_pack_info(int *threads, int *isa);
 /* Bytes rb_ibf_count_batch has moved over PCIe since the library was loaded (all threads): host->device
  * copies (bit planes or ASCII bases, offsets, thresholds) and device->host results (copies or mapped stores). */
 RB_API int rb_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
+/* How rb_ibf_count_batch ships large batches (>= 8 pieces of ~8 MB) of this filter: the library times its 2nd packed and
+ * its 2nd ASCII call and keeps the faster way (ASCII only if >= 5 % faster); smaller batches are packed.  choice: -1 not
+ * decided yet, 0 packed bit planes, 1 ASCII; the two measured times in ns per base (0 = not measured).  RB_HOST_PACK=1 / 0
+ * pins the choice and skips the measurement. */
+RB_API int rb_ibf_transfer_policy(const rb_ibf *f, int *choice, double *ns_per_base_packed, double *ns_per_base_ascii);
 
 /* Packed per-read summary key used by the device API and the bin-sharded combine:
  *   bit 48      hit (some bin passes the threshold)

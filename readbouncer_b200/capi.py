@@ -30,6 +30,7 @@ EXPORTS = [
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_set_insert_kernel", "rb_kernel_launches",
     "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
     "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins", "rb_host_pack_info", "rb_transfer_bytes",
+    "rb_ibf_transfer_policy",
 ]
 
 
@@ -110,6 +111,7 @@ def lib():
         "rb_ibf_resize_bins": (i32, [vp, u64, vp]),
         "rb_host_pack_info": (i32, [vp, vp]),
         "rb_transfer_bytes": (i32, [vp, vp]),
+        "rb_ibf_transfer_policy": (i32, [vp, vp, vp, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -307,6 +309,13 @@ class IBF:
         info = _Info()
         _check(lib().rb_ibf_info(self._h, C.byref(info)))
         return int(info.kmer_table_kind)
+
+    def transfer_policy(self):
+        """How large host-buffer batches are shipped: packed bit planes or ASCII (rb_ibf_transfer_policy)."""
+        c, a, b = C.c_int32(0), C.c_double(0), C.c_double(0)
+        _check(lib().rb_ibf_transfer_policy(self._h, C.byref(c), C.byref(a), C.byref(b)))
+        return {"choice": {-1: "undecided", 0: "packed", 1: "ascii"}[int(c.value)],
+                "ns_per_base_packed": float(a.value), "ns_per_base_ascii": float(b.value)}
 
     def device_words_ptr(self):
         return int(lib().rb_ibf_device_words(self._h) or 0)

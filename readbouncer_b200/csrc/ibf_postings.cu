@@ -8,16 +8,20 @@
 // (k = 13); as postings -- the sorted list of set bins per k-mer, 2 bytes each -- it needs ~50 GB and fits HBM.
 //
 //   ptr[x], ptr[x+1]   list of k-mer x in units of 8 ids (16 bytes), x = sum rank_j * 4^(k-1-j), ranks A0 C1 G2 T3
-//   ids[8 * u + i]     local bin indices, ascending; lists are padded to a multiple of 8 with the sentinel n_bins_local
+//   ids[8 * u + i]     local bin indices; lists are padded to a multiple of 8 with the sentinel n_bins_local.  Inside a
+//                      list the ids are dealt over the groups one ATOMS instruction serves so that few of them share a
+//                      shared-memory bank (ibf_postings_layout.cuh); RB_POSTINGS_ORDER=0 keeps them ascending
 //
 // Classifying a 250-base chunk then reads 476 lists (~340 KB) instead of streaming 2 x 238 x 3 rows (5.5 MB), and
 // counts with shared-memory atomics on packed 8-bit (or 16-bit) counters.  The reverse strand of k-mer x is the
 // list of revcomp(x).  Windows containing a non-ACGT base take the hashing path on the bit matrix itself, so
 // every output equals the reference's.
 #include "ibf_device.cuh"
+#include "ibf_postings_layout.cuh"
 
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
 #include <vector>
 
 namespace rb {
@@ -27,6 +31,7 @@ namespace {
 constexpr int kPostThreads = 256;
 constexpr int kPostWarps = kPostThreads / 32;
 constexpr int kPostPiece = 512;               // k-mer positions staged per pass over a read
+constexpr int kPostInFlight = 4;              // lists a warp loads before it counts them (even: strands alternate)
 
 // base-5 hashes of the forward and reverse-complement strand of the ACGT k-mer x (ranks, first base most significant)
 __device__ __forceinline__ void kmer_hashes(uint64_t x, uint32_t k, uint64_t &Hf, uint64_t &Hr)
@@ -72,14 +77,20 @@ __global__ void __launch_bounds__(256) postings_count_kernel(const FilterView fv
     }
 }
 
+constexpr int kFillStage = 2048;              // ids of one list staged per warp for the reordering (longer lists stay ascending)
+
 __global__ void __launch_bounds__(256) postings_fill_kernel(const FilterView fv, uint64_t n_kmers, const uint32_t *__restrict__ ptr,
-                                                            uint16_t *__restrict__ ids)
+                                                            uint16_t *__restrict__ ids, const int deal)
 {
+    __shared__ uint16_t s_stage[8][kFillStage];
+    __shared__ uint32_t s_off[8][32];
     const HashParams &hp = fv.hp;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint16_t sentinel = (uint16_t)fv.n_bins_local;
+    uint16_t *const stage = s_stage[wib];
+    uint32_t *const off = s_off[wib];
     for (uint64_t x = warp0; x < n_kmers; x += n_warps) {
         uint64_t Hf, Hr;
         kmer_hashes(x, hp.k, Hf, Hr);
@@ -87,8 +98,10 @@ __global__ void __launch_bounds__(256) postings_fill_kernel(const FilterView fv,
 #pragma unroll
         for (int h = 0; h < kMaxHash; ++h)
             rows[h] = (uint32_t)h < hp.n_hash ? fv.words + hash_row(Hf, hp.pre[h], hp.n_blocks, hp.magic) * fv.stride : nullptr;
-        uint16_t *out = ids + (uint64_t)ptr[x] * 8;
+        uint16_t *const out = ids + (uint64_t)ptr[x] * 8;
         const uint64_t end = (uint64_t)ptr[x + 1] * 8 - (uint64_t)ptr[x] * 8;
+        const bool staged = deal && end <= (uint64_t)kFillStage;
+        uint16_t *const dst = staged ? stage : out;
         uint64_t run = 0;                                           // ids written so far (same in all lanes)
         for (uint64_t w0 = 0; w0 < fv.stride; w0 += 32) {
             const uint64_t w = w0 + lane;
@@ -110,11 +123,45 @@ __global__ void __launch_bounds__(256) postings_fill_kernel(const FilterView fv,
             while (m) {
                 const int b = __ffsll((long long)m) - 1;
                 m &= m - 1;
-                out[pos++] = (uint16_t)(w * 64 + b);
+                dst[pos++] = (uint16_t)(w * 64 + b);
             }
             run += __shfl_sync(0xffffffffu, incl, 31);
         }
         for (uint64_t p = run + lane; p < end; p += 32) out[p] = sentinel;
+        if (!staged) continue;
+        // ---- deal the staged (ascending) ids over the groups of the list, bank by bank (ibf_postings_layout.cuh) ----
+        const uint32_t n = (uint32_t)run;
+        off[lane] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&off[counter_bank(stage[i])], 1u);
+        __syncwarp();
+        {
+            const uint32_t load = off[lane];
+            uint32_t incl = load;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            __syncwarp();
+            off[lane] = incl - load;                                // first dealing index of bank `lane`
+        }
+        __syncwarp();
+        const ListShape shape = list_shape(n);
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {                   // rank inside the bank = ascending order (deterministic)
+            const uint32_t i = i0 + lane;
+            const bool valid = i < n;
+            const uint32_t id = valid ? stage[i] : 0u;
+            const uint32_t b = counter_bank(id);
+            const uint32_t same = __match_any_sync(0xffffffffu, valid ? b : 32u + lane);
+            const uint32_t before = __popc(same & ((1u << lane) - 1u));
+            const uint32_t c = valid ? off[b] + before : 0u;
+            __syncwarp();
+            if (valid && before == 0) off[b] += __popc(same);
+            __syncwarp();
+            if (valid) out[list_position(shape, c)] = (uint16_t)id;
+        }
+        __syncwarp();
     }
 }
 
@@ -122,18 +169,74 @@ __global__ void __launch_bounds__(256) postings_fill_kernel(const FilterView fv,
 // lookup: CTA per read, warps take (position, strand) pairs, counters in shared memory
 // ------------------------------------------------------------------------------------------
 // CB = counter bits (8: reads of <= 255 positions, 16: any read the API accepts)
+// One increment.  `v` holds the id in its low 16 bits; whatever sits above is ignored (the byte offset of the counter word
+// is a mask of the low bits, the shift amount is taken modulo 32 by the funnel shift), so the low id of a pair needs no
+// extraction at all.
+template <int CB>
+__device__ __forceinline__ void bump(uint32_t *cnt, const uint32_t v)
+{
+    if (CB == 8)
+        atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(cnt) + (v & 0xFFFCu)), __funnelshift_l(0u, 1u, v << 3));
+    else
+        atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(cnt) + ((v & 0xFFFEu) << 1)), __funnelshift_l(0u, 1u, v << 4));
+}
+
+template <int CB>
+__device__ __forceinline__ void bump_pair(uint32_t *cnt, const uint32_t w)
+{
+    bump<CB>(cnt, w);
+    bump<CB>(cnt, w >> 16);
+}
+
 template <int CB>
 __device__ __forceinline__ void add_ids(uint32_t *cnt, const uint4 v)
 {
-    constexpr int PER = 32 / CB;                 // counters per 32-bit word
-    constexpr int SH = (PER == 4) ? 2 : 1;
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t a = w[i] & 0xFFFFu, b = w[i] >> 16;
-        atomicAdd(cnt + (a >> SH), 1u << ((a & (PER - 1)) * CB));
-        atomicAdd(cnt + (b >> SH), 1u << ((b & (PER - 1)) * CB));
+    bump_pair<CB>(cnt, v.x);
+    bump_pair<CB>(cnt, v.y);
+    bump_pair<CB>(cnt, v.z);
+    bump_pair<CB>(cnt, v.w);
+}
+
+// One list as the warp walks it (layout: ibf_postings_layout.cuh): the first full round and the tail are loaded up front
+// (`fetch`), so that several lists are in flight before the first counter is touched; `count` adds them and walks the
+// further rounds of a list of more than 511 ids.
+struct ListRegs {
+    uint4 full, tail;
+    uint32_t u0, n_u;          // first unit, units (warp-uniform)
+};
+
+__device__ __forceinline__ void fetch_list(ListRegs &r, const uint4 *__restrict__ ids, const uint32_t u0, const uint32_t n_u, const int lane)
+{
+    r.u0 = u0; r.n_u = n_u;
+    r.full = make_uint4(0, 0, 0, 0); r.tail = make_uint4(0, 0, 0, 0);
+    if (n_u >= 32u) r.full = __ldg(ids + u0 + lane);
+    const uint32_t tu = n_u & 31u, ub = u0 + (n_u & ~31u);
+    if (tu > 16u) { if ((uint32_t)lane < tu) r.tail = __ldg(ids + ub + lane); }
+    else if (tu > 8u) {
+        if ((uint32_t)lane < 2u * tu) { const uint2 t = __ldg(reinterpret_cast<const uint2 *>(ids + ub) + lane); r.tail.x = t.x; r.tail.y = t.y; }
+    } else if (tu > 4u) { if ((uint32_t)lane < 4u * tu) r.tail.x = __ldg(reinterpret_cast<const uint32_t *>(ids + ub) + lane); }
+    else if (tu > 0u) { if ((uint32_t)lane < 8u * tu) r.tail.x = __ldg(reinterpret_cast<const uint16_t *>(ids + ub) + lane); }
+}
+
+template <int CB>
+__device__ __forceinline__ void count_list(const ListRegs &r, uint32_t *cnt, const uint4 *__restrict__ ids, const int lane,
+                                           const uint32_t sentinel)
+{
+    const uint32_t n_u = r.n_u;
+    if (n_u >= 32u) {
+        add_ids<CB>(cnt, r.full);
+        for (uint32_t rr = 1; rr < (n_u >> 5); ++rr) add_ids<CB>(cnt, __ldg(ids + r.u0 + 32u * rr + lane));     // long lists
     }
+    const uint32_t tu = n_u & 31u;
+    if (tu > 16u) { if ((uint32_t)lane < tu) add_ids<CB>(cnt, r.tail); }
+    else if (tu > 8u) { if ((uint32_t)lane < 2u * tu) { bump_pair<CB>(cnt, r.tail.x); bump_pair<CB>(cnt, r.tail.y); } }
+    else if (tu > 4u) {
+        // the few sentinels of a short tail would meet in one instruction: skip them
+        if ((uint32_t)lane < 4u * tu) {
+            if ((r.tail.x & 0xFFFFu) != sentinel) bump<CB>(cnt, r.tail.x);
+            if ((r.tail.x >> 16) != sentinel) bump<CB>(cnt, r.tail.x >> 16);
+        }
+    } else if (tu > 0u) { if ((uint32_t)lane < 8u * tu && r.tail.x != sentinel) bump<CB>(cnt, r.tail.x); }
 }
 
 // hashing path of one (position, strand): AND of the probed rows, one warp, counters by atomics
@@ -232,29 +335,17 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                     }
                     const uint32_t any_hashed = __ballot_sync(0xffffffffu, hashed);
                     const uint32_t n_here = min(32u, n_pairs - q0);
-                    for (uint32_t t = 0; t < n_here; t += 2) {             // two lists in flight
-                        const uint32_t a0 = __shfl_sync(0xffffffffu, p0, t), a1 = __shfl_sync(0xffffffffu, p1, t);
-                        const uint32_t t2 = min(t + 1, 31u);
-                        uint32_t b0 = __shfl_sync(0xffffffffu, p0, t2), b1 = __shfl_sync(0xffffffffu, p1, t2);
-                        if (t + 1 >= n_here) { b0 = 0; b1 = 0; }
-                        uint32_t *const ca = ((q0 + t) & 1u) ? cntR : cntF;
-                        uint32_t *const cb = ((q0 + t + 1) & 1u) ? cntR : cntF;
-                        uint4 va[2], vb[2];
-                        bool ha[2], hb[2];
+                    for (uint32_t t = 0; t < n_here; t += kPostInFlight) {  // kPostInFlight lists in flight
+                        ListRegs lr[kPostInFlight];
 #pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            ha[r] = a0 + 32u * r + lane < a1;
-                            hb[r] = b0 + 32u * r + lane < b1;
-                            if (ha[r]) va[r] = __ldg(ids + a0 + 32u * r + lane);
-                            if (hb[r]) vb[r] = __ldg(ids + b0 + 32u * r + lane);
+                        for (int j = 0; j < kPostInFlight; ++j) {
+                            const uint32_t tj = min(t + j, 31u);
+                            const uint32_t u0 = __shfl_sync(0xffffffffu, p0, tj), u1 = __shfl_sync(0xffffffffu, p1, tj);
+                            fetch_list(lr[j], ids, u0, t + j < n_here ? u1 - u0 : 0u, lane);
                         }
 #pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            if (ha[r]) add_ids<CB>(ca, va[r]);
-                            if (hb[r]) add_ids<CB>(cb, vb[r]);
-                        }
-                        for (uint32_t u = a0 + 64u + lane; u < a1; u += 32) add_ids<CB>(ca, __ldg(ids + u));   // long lists
-                        for (uint32_t u = b0 + 64u + lane; u < b1; u += 32) add_ids<CB>(cb, __ldg(ids + u));
+                        for (int j = 0; j < kPostInFlight; ++j)         // q0 and t are even: list j is strand j & 1
+                            count_list<CB>(lr[j], (j & 1) ? cntR : cntF, ids, lane, (uint32_t)nbl);
                     }
                     if (any_hashed) {
                         for (uint32_t t = 0; t < n_here; ++t)
@@ -372,7 +463,9 @@ int postings_build_ptr(const FilterView &fv, uint32_t *d_ptr, uint64_t *total_un
 
 int postings_fill(const FilterView &fv, const uint32_t *d_ptr, uint16_t *d_ids, int sm_count, cudaStream_t st)
 {
-    postings_fill_kernel<<<sm_count * 16, 256, 0, st>>>(fv, 1ull << (2 * fv.hp.k), d_ptr, d_ids);
+    int deal = 1;                                               // RB_POSTINGS_ORDER=0: ascending ids (A/B measurements)
+    if (const char *e = std::getenv("RB_POSTINGS_ORDER")) deal = e[0] != '0';
+    postings_fill_kernel<<<sm_count * 16, 256, 0, st>>>(fv, 1ull << (2 * fv.hp.k), d_ptr, d_ids, deal);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -82,6 +82,13 @@ struct rb_ibf {
     // streams, events and staging buffers of rb_ibf_count_batch, kept between calls (one set per concurrent caller)
     mutable std::mutex ctx_mu;
     mutable std::vector<struct CallCtx *> ctx_free;
+    // rb_ibf_count_batch, large batches: bit planes packed by the host threads or the ASCII bases as they are -- whichever
+    // this host moves faster (it depends on the cores and the memory bandwidth each GPU's process is left with), decided
+    // by timing the 2nd call of each kind.  RB_HOST_PACK=1 / 0 pins the choice.
+    mutable std::mutex pol_mu;
+    mutable int pol_calls = 0;                       // large packable calls seen while undecided
+    mutable double pol_ns_per_base[2] = {0.0, 0.0};  // [0] packed, [1] ASCII
+    mutable int pol_choice = -1;                     // -1 undecided, 0 packed, 1 ASCII
 };
 
 namespace {
@@ -413,6 +420,9 @@ constexpr uint64_t kStageBases = 512ull << 20;          // bases per round of th
 // packer and the copy engine compete for the same host-memory bandwidth, every share > 0 was slower
 // (profiles/r1_k_e2e_ascii_share_sweep.jsonl); RB_ASCII_SHARE turns it on for hosts where they do not.
 constexpr double kAsciiShare = 0.0;
+// packed or ASCII for batches of at least kPolicyMinPieces pieces: ASCII has to be this much faster to be chosen
+constexpr size_t kPolicyMinPieces = 8;
+constexpr double kPolicyMargin = 0.95;
 
 struct DevBuf {
     void *p = nullptr;
@@ -566,7 +576,21 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
     if (which == 0 || which >= 3) table = ensure_table(f, user, which >= 3, n_reads);
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
     bool packed_ok = table && f->table_span >= 2 && !dense && (which == 0 || which == 3);
-    if (const char *e = std::getenv("RB_HOST_PACK")) if (e[0] == '0') packed_ok = false;
+    int pol_measure = -1;                            // >= 0: this call's time per base decides the policy (0 packed, 1 ASCII)
+    {
+        const char *e = std::getenv("RB_HOST_PACK");
+        if (e && e[0] == '0') packed_ok = false;
+        else if (packed_ok && !(e && e[0] == '1') && n_pieces >= kPolicyMinPieces) {
+            std::lock_guard<std::mutex> lock(f->pol_mu);
+            if (f->pol_choice >= 0) packed_ok = f->pol_choice == 0;
+            else {
+                const int c = f->pol_calls++;        // calls 0, 1 packed; 2, 3 ASCII; the first of each kind warms its buffers
+                const int mode = (c & 2) ? 1 : 0;
+                if (c & 1) pol_measure = mode;
+                packed_ok = mode == 0;
+            }
+        }
+    }
 
     // ---- which way out ---------------------------------------------------------------------------------------------------
     uint16_t *m_max = mapped_ptr(max_count);
@@ -778,6 +802,12 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
         return RB_OK;
     };
     int st = body();
+    if (st == RB_OK && pol_measure >= 0 && read_off[n_reads] > read_off[0]) {
+        std::lock_guard<std::mutex> lock(f->pol_mu);
+        f->pol_ns_per_base[pol_measure] = 1e6 * ms_since() / (double)(read_off[n_reads] - read_off[0]);
+        if (f->pol_choice < 0 && f->pol_ns_per_base[0] > 0 && f->pol_ns_per_base[1] > 0)
+            f->pol_choice = f->pol_ns_per_base[1] < kPolicyMargin * f->pol_ns_per_base[0] ? 1 : 0;
+    }
     if (st != RB_OK) {                       // drain whatever was enqueued before the buffers are reused
         const std::string keep = g_last_error;
         for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(ctx->st[s]);
@@ -1312,6 +1342,16 @@ int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_
                              counts_rev, max_count, hit, argmax_bin, read_flag, (cudaStream_t)stream);
     release_ctx(f, ctx);
     return st;
+}
+
+int rb_ibf_transfer_policy(const rb_ibf *f, int *choice, double *ns_per_base_packed, double *ns_per_base_ascii)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "no filter");
+    std::lock_guard<std::mutex> lock(f->pol_mu);
+    if (choice) *choice = f->pol_choice;
+    if (ns_per_base_packed) *ns_per_base_packed = f->pol_ns_per_base[0];
+    if (ns_per_base_ascii) *ns_per_base_ascii = f->pol_ns_per_base[1];
+    return RB_OK;
 }
 
 int rb_transfer_bytes(uint64_t *h2d, uint64_t *d2h)

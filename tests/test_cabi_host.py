@@ -134,6 +134,13 @@ def test_bit_transpose_matches_definition(tmp_path):
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_postings_list_order_is_a_bijection_and_spreads_banks(tmp_path):
+    """rb::list_position (order of the bin ids inside a postings list) for every list length up to 3 000."""
+    exe = _compile(os.path.join(ROOT, "tests", "cpp", "test_postings_layout.cpp"), str(tmp_path / "test_postings_layout"), link=False)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("isa", ["5", "2", "0"])
 def test_host_packer_matches_restatement(tmp_path, isa):
     """Bit planes of the host packer (AVX-512 / AVX2 / scalar paths, thread pool) against a plain loop."""

@@ -292,6 +292,67 @@ def test_host_buffer_pipeline_packed_pieces_and_rounds(monkeypatch):
     assert xfer[("1", None)] < xfer[("1", "0.25")] < xfer[("1", "0.5")] < xfer[("0", None)]
 
 
+@pytest.mark.parametrize("order", ["1", "0"])
+@pytest.mark.parametrize("n_blocks", [2600, 3700, 6000, 9000])
+def test_postings_long_lists(n_blocks, order, monkeypatch):
+    """Postings lists of ~610 / ~380 / ~160 / ~70 bins per k-mer (an over-full 1 100-bin filter: 56 % .. 6 % false positives
+    per bin), so that the lookup kernel walks full rounds, further rounds and every tail width (ibf_postings_layout.cuh),
+    with the ids dealt over the groups (default) and ascending (RB_POSTINGS_ORDER=0)."""
+    monkeypatch.setenv("RB_POSTINGS_ORDER", order)
+    k, n_hash = 11, 3
+    ref = [synth.random_bases(1500, 300 + i) for i in range(1100)]
+    plan = synth.build_plan(ref, 2000, k, n_hash=n_hash)
+    assert plan["n_bins"] == 1100
+    n_bits = n_blocks * 64 * 18
+    of = oracle.OracleIBF.create(1100, n_hash, k, n_bits)
+    of.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"], n_threads=4)
+    gf = rb.IBF.create(1100, n_hash, k, n_bits)
+    gf.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+    assert np.array_equal(gf.download(), of.words()[:n_bits // 64])
+    gf.enable_kmer_table(0)
+    assert gf.kmer_table_kind() == 2
+    mean_ids = (gf.kmer_table_bytes() - 4 ** k * 4) / 2 / 4 ** k
+    fp = (1 - np.exp(-n_hash * (1500 - k + 1) / n_blocks)) ** n_hash
+    assert 0.8 * 1100 * fp < mean_ids < 1.2 * 1100 * fp + 8
+    lut = rb.threshold_lut(0.1, k)
+    short = [250] * 40 + [0, 1, k - 1, k, k + 1, 31, 64, 100, 249, 251, 254 + k]
+    sb, so = synth.ragged_reads(plan["bases"], short, seed=21, frac_from_ref=0.7, n_frac=0.004, lower_frac=0.1)
+    sexp = of.count_batch(sb, so, lut, n_threads=8)
+    assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)                 # 8-bit counters
+    assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+    longer = [250] * 8 + [255 + k, 400, 700, 1500]
+    lb, lo = synth.ragged_reads(plan["bases"], longer, seed=22, frac_from_ref=0.7, n_frac=0.003, lower_frac=0.1)
+    assert_same_results(gf.count_batch(lb, lo, lut, dense=True), of.count_batch(lb, lo, lut, n_threads=8))   # 16-bit counters
+
+
+def test_transfer_policy_times_both_ways(monkeypatch):
+    """Large host-buffer batches with RB_HOST_PACK unset: two packed calls, two ASCII calls, then the faster way for good;
+    every call returns the oracle's answers."""
+    plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
+    bases, off, _ = synth.sample_reads(plan["bases"], 40000, 250, seed=31)
+    lut = rb.threshold_lut(0.1, 13)
+    exp = of.count_batch(bases, off, lut, n_threads=8)
+    gf.enable_kmer_table(0)
+    monkeypatch.setenv("RB_PIECE_MB", "1")                  # ~10 pieces: a "large" batch
+    monkeypatch.setenv("RB_HOST_PACK", "1")                 # pinned choice: no measurement; uploads the thresholds once
+    assert_same_results(gf.count_batch(bases, off, lut), exp, dense=False)
+    monkeypatch.delenv("RB_HOST_PACK", raising=False)
+    assert gf.transfer_policy()["choice"] == "undecided"
+    x = [rb.transfer_bytes()[0]]
+    for call in range(6):
+        assert_same_results(gf.count_batch(bases, off, lut), exp, dense=False)
+        x.append(rb.transfer_bytes()[0])
+    moved = np.diff(x)
+    assert moved[0] == moved[1] < moved[2] == moved[3]      # packed, packed, ASCII, ASCII
+    pol = gf.transfer_policy()
+    assert pol["choice"] in ("packed", "ascii") and pol["ns_per_base_packed"] > 0 and pol["ns_per_base_ascii"] > 0
+    assert moved[4] == moved[5] == (moved[0] if pol["choice"] == "packed" else moved[2])
+    monkeypatch.setenv("RB_PIECE_MB", "64")                 # one piece: small batches are always packed
+    x0 = rb.transfer_bytes()[0]
+    assert_same_results(gf.count_batch(bases, off, lut), exp, dense=False)
+    assert rb.transfer_bytes()[0] - x0 == moved[0]
+
+
 def test_two_threshold_tables_in_one_pass():
     plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
     bases, off, _ = synth.sample_reads(plan["bases"], 3000, 250, seed=5, error_rate=0.12)
