@@ -268,7 +268,7 @@ template <int CB>
 __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return CB == 8 ? __vmaxu4(a, b) : __vmaxu2(a, b); }
 
 template <int CB>
-__global__ void __launch_bounds__(kPostThreads)
+__global__ void __launch_bounds__(kPostThreads, CB == 8 ? 3 : 1)      // 8-bit counters of 31 K bins: 3 CTAs of shared memory
 count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const uint4 *__restrict__ ids, const uint32_t cnt_words)
 {
     constexpr int PER = 32 / CB;
@@ -278,7 +278,6 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
     uint32_t *const s_x = s_mem + 2 * cnt_words;                         // [kPostPiece] packed k-mer or ~0u (not ACGT)
     uint8_t *const s_dig = reinterpret_cast<uint8_t *>(s_x + kPostPiece); // [kPostPiece + 32] Dna5 ranks
     __shared__ uint32_t s_red[kPostWarps];
-    __shared__ uint32_t s_best;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t k = a.fv.hp.k;
@@ -314,12 +313,14 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                 }
                 __syncthreads();
                 // (position, strand) pairs: 32 per warp round, list bounds fetched by the lanes, lists walked by the warp
+                // every warp takes an equal, contiguous share of the pairs (even, so that strands alternate from its start) in
+                // rounds of 32; the list bounds of the next round are requested before the current one is walked
                 const uint32_t n_pairs = 2 * cn;
-                for (uint32_t q0 = warp * 32; q0 < n_pairs; q0 += kPostWarps * 32) {
-                    const uint32_t q = q0 + lane;
-                    uint32_t p0 = 0, p1 = 0;
-                    bool hashed = false;
-                    if (q < n_pairs) {
+                const uint32_t share = 2u * ((cn + kPostWarps - 1) / kPostWarps);
+                const uint32_t q_end = min(n_pairs, (warp + 1) * share);
+                auto list_bounds = [&](const uint32_t q, uint32_t &p0, uint32_t &p1, bool &hashed) {
+                    p0 = 0; p1 = 0; hashed = false;
+                    if (q < q_end) {
                         const uint32_t x = s_x[q >> 1];
                         if (x == ~0u) hashed = true;
                         else {
@@ -333,8 +334,14 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                             p1 = __ldg(ptr + idx + 1);
                         }
                     }
+                };
+                uint32_t p0, p1, np0 = 0, np1 = 0;
+                bool hashed, nhashed = false;
+                list_bounds(warp * share + lane, p0, p1, hashed);
+                for (uint32_t q0 = warp * share; q0 < q_end; q0 += 32) {
+                    if (q0 + 32 < q_end) list_bounds(q0 + 32 + lane, np0, np1, nhashed);
                     const uint32_t any_hashed = __ballot_sync(0xffffffffu, hashed);
-                    const uint32_t n_here = min(32u, n_pairs - q0);
+                    const uint32_t n_here = min(32u, q_end - q0);
                     for (uint32_t t = 0; t < n_here; t += kPostInFlight) {  // kPostInFlight lists in flight
                         ListRegs lr[kPostInFlight];
 #pragma unroll
@@ -352,6 +359,7 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                             if ((any_hashed >> t) & 1u)
                                 add_hashed<CB>(a.fv, s_dig + ((q0 + t) >> 1), (q0 + t) & 1u, ((q0 + t) & 1u) ? cntR : cntF, lane);
                     }
+                    p0 = np0; p1 = np1; hashed = nhashed;
                 }
             }
         }
@@ -359,48 +367,47 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
 
         // ---- epilogue: M = max over bins of max(fwd, rev), its lowest bin; counters back to zero ----------------
         // the sentinel's counter (index nbl) is not a bin
-        if (tid == 0) {
-            const uint32_t sw = (uint32_t)nbl / PER, sb = ((uint32_t)nbl % PER) * CB;
-            cntF[sw] &= ~(CMASK << sb);
-            cntR[sw] &= ~(CMASK << sb);
-        }
-        __syncthreads();
-        uint32_t mx = 0;
-        for (uint32_t w = tid; w < cnt_words; w += kPostThreads) mx = vmax<CB>(mx, vmax<CB>(cntF[w], cntR[w]));
-        uint32_t m1 = 0;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) m1 = max(m1, (mx >> (i * CB)) & CMASK);
-        m1 = __reduce_max_sync(0xffffffffu, m1);
-        if (lane == 0) s_red[warp] = m1;
-        if (tid == 0) s_best = 0xFFFFFFFFu;
-        __syncthreads();
-        uint32_t M = 0;
-#pragma unroll
-        for (int i = 0; i < kPostWarps; ++i) M = max(M, s_red[i]);
-        // second pass: lowest bin attaining M, dense counts, and zero the counters for the next read
-        uint32_t best = 0xFFFFFFFFu;
+        const uint32_t sent_w = (uint32_t)nbl / PER, sent_keep = ~(CMASK << (((uint32_t)nbl % PER) * CB));
+        // one pass: every thread keeps the largest count it has seen and the first bin that had it (its bins ascend),
+        // a word is unpacked only when one of its counters beats that; counters go back to zero on the way
+        uint32_t cur = 0, cur_bin = 0, cur_v = 0;                          // cur_v = cur in every counter lane
+        const bool dense = a.counts_fwd || a.counts_rev;
         for (uint32_t w = tid; w < cnt_words; w += kPostThreads) {
-            const uint32_t f = cntF[w], r = cntR[w];
+            uint32_t f = cntF[w], r = cntR[w];
             cntF[w] = 0; cntR[w] = 0;
+            if (w == sent_w) { f &= sent_keep; r &= sent_keep; }
             const uint32_t m = vmax<CB>(f, r);
+            if (CB == 8 ? __vcmpgtu4(m, cur_v) : __vcmpgtu2(m, cur_v)) {
 #pragma unroll
-            for (int i = PER - 1; i >= 0; --i) {
-                const uint32_t bin = w * PER + i;
-                if (bin < nbl) {
-                    if (((m >> (i * CB)) & CMASK) == M) best = min(best, bin);
-                    if (a.counts_fwd) a.counts_fwd[read * nbl + bin] = (uint16_t)((f >> (i * CB)) & CMASK);
-                    if (a.counts_rev) a.counts_rev[read * nbl + bin] = (uint16_t)((r >> (i * CB)) & CMASK);
+                for (int i = 0; i < PER; ++i) {
+                    const uint32_t v = (m >> (i * CB)) & CMASK;
+                    if (v > cur) { cur = v; cur_bin = w * PER + i; }
+                }
+                cur_v = cur * (CB == 8 ? 0x01010101u : 0x00010001u);
+            }
+            if (dense) {
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const uint32_t bin = w * PER + i;
+                    if (bin < nbl) {
+                        if (a.counts_fwd) a.counts_fwd[read * nbl + bin] = (uint16_t)((f >> (i * CB)) & CMASK);
+                        if (a.counts_rev) a.counts_rev[read * nbl + bin] = (uint16_t)((r >> (i * CB)) & CMASK);
+                    }
                 }
             }
         }
-        best = __reduce_min_sync(0xffffffffu, best);
-        if (lane == 0 && best != 0xFFFFFFFFu) atomicMin(&s_best, best);
+        // (count, lowest bin) as one key: larger count wins, then the smaller bin (bins < 65 535)
+        uint32_t best_key = __reduce_max_sync(0xffffffffu, (cur << 16) | (0xFFFFu - cur_bin));
+        if (lane == 0) s_red[warp] = best_key;
         __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kPostWarps; ++i) best_key = max(best_key, s_red[i]);
+        const uint32_t M = best_key >> 16, best_bin = 0xFFFFu - (best_key & 0xFFFFu);
         if (tid < (int)a.n_lut) {
             uint64_t key = 0;
             if (flag == 0) {
                 const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)tid * kLutSize + len);
-                if (M >= thr) key = pack_key(M, (uint32_t)(a.fv.bin_begin + s_best));
+                if (M >= thr) key = pack_key(M, (uint32_t)(a.fv.bin_begin + best_bin));
             }
             a.keys[(size_t)tid * a.n_reads + read] = key;
         }

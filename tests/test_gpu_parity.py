@@ -350,7 +350,7 @@ def test_transfer_policy_times_both_ways(monkeypatch):
     monkeypatch.setenv("RB_PIECE_MB", "64")                 # one piece: small batches are always packed
     x0 = rb.transfer_bytes()[0]
     assert_same_results(gf.count_batch(bases, off, lut), exp, dense=False)
-    assert rb.transfer_bytes()[0] - x0 == moved[0]
+    assert abs(int(rb.transfer_bytes()[0] - x0) - int(moved[0])) < moved[0] // 100      # planes, fewer per-piece paddings
 
 
 def test_two_threshold_tables_in_one_pass():
