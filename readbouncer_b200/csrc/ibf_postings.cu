@@ -8,7 +8,8 @@
 // (k = 13); as postings -- the sorted list of set bins per k-mer, 2 bytes each -- it needs ~50 GB and fits HBM.
 //
 //   ptr[x], ptr[x+1]   list of k-mer x in units of 8 ids (16 bytes), x = sum rank_j * 4^(k-1-j), ranks A0 C1 G2 T3
-//   ids[8 * u + i]     local bin indices; lists are padded to a multiple of 8 with the sentinel n_bins_local.  Inside a
+//   ids[8 * u + i]     local bin indices; lists are padded to a multiple of 8 with a sentinel (n_bins_local rounded up to
+//                      a multiple of 16: its counter lies behind the quads of counter words that hold bins).  Inside a
 //                      list the ids are dealt over the groups one ATOMS instruction serves so that few of them share a
 //                      shared-memory bank (ibf_postings_layout.cuh); RB_POSTINGS_ORDER=0 keeps them ascending
 //
@@ -77,6 +78,10 @@ __global__ void __launch_bounds__(256) postings_count_kernel(const FilterView fv
     }
 }
 
+// Padding id of the lists: the first id whose counter lies in the 16-byte quad of counter words AFTER the quads that hold
+// bins, for 8-bit (4 per word) and 16-bit (2 per word) counters alike, so the epilogue scans whole quads of bins only.
+__host__ __device__ inline uint32_t postings_sentinel(uint64_t n_bins_local) { return (uint32_t)((n_bins_local + 15) / 16 * 16); }
+
 constexpr int kFillStage = 2048;              // ids of one list staged per warp for the reordering (longer lists stay ascending)
 
 __global__ void __launch_bounds__(256) postings_fill_kernel(const FilterView fv, uint64_t n_kmers, const uint32_t *__restrict__ ptr,
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(256) postings_fill_kernel(const FilterView fv,
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint16_t sentinel = (uint16_t)fv.n_bins_local;
+    const uint16_t sentinel = (uint16_t)postings_sentinel(fv.n_bins_local);
     uint16_t *const stage = s_stage[wib];
     uint32_t *const off = s_off[wib];
     for (uint64_t x = warp0; x < n_kmers; x += n_warps) {
@@ -225,7 +230,8 @@ __device__ __forceinline__ void count_list(const ListRegs &r, uint32_t *cnt, con
     const uint32_t n_u = r.n_u;
     if (n_u >= 32u) {
         add_ids<CB>(cnt, r.full);
-        for (uint32_t rr = 1; rr < (n_u >> 5); ++rr) add_ids<CB>(cnt, __ldg(ids + r.u0 + 32u * rr + lane));     // long lists
+#pragma unroll 1
+        for (uint32_t rr = 1; rr < (n_u >> 5); ++rr) add_ids<CB>(cnt, __ldg(ids + r.u0 + 32u * rr + lane));     // > 511 ids
     }
     const uint32_t tu = n_u & 31u;
     if (tu > 16u) { if ((uint32_t)lane < tu) add_ids<CB>(cnt, r.tail); }
@@ -284,6 +290,7 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
     const uint32_t kbits = 2 * k;
     const uint32_t kmask = kbits >= 32 ? ~0u : ((1u << kbits) - 1u);
     const uint64_t nbl = a.fv.n_bins_local;
+    const uint32_t sentinel = postings_sentinel(nbl);
 
     for (uint32_t w = tid; w < 2 * cnt_words; w += kPostThreads) s_mem[w] = 0;
 
@@ -352,7 +359,7 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                         }
 #pragma unroll
                         for (int j = 0; j < kPostInFlight; ++j)         // q0 and t are even: list j is strand j & 1
-                            count_list<CB>(lr[j], (j & 1) ? cntR : cntF, ids, lane, (uint32_t)nbl);
+                            count_list<CB>(lr[j], (j & 1) ? cntR : cntF, ids, lane, sentinel);
                     }
                     if (any_hashed) {
                         for (uint32_t t = 0; t < n_here; ++t)
@@ -366,26 +373,13 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
         __syncthreads();
 
         // ---- epilogue: M = max over bins of max(fwd, rev), its lowest bin; counters back to zero ----------------
-        // the sentinel's counter (index nbl) is not a bin
-        const uint32_t sent_w = (uint32_t)nbl / PER, sent_keep = ~(CMASK << (((uint32_t)nbl % PER) * CB));
-        // one pass: every thread keeps the largest count it has seen and the first bin that had it (its bins ascend),
-        // a word is unpacked only when one of its counters beats that; counters go back to zero on the way
-        uint32_t cur = 0, cur_bin = 0, cur_v = 0;                          // cur_v = cur in every counter lane
-        const bool dense = a.counts_fwd || a.counts_rev;
-        for (uint32_t w = tid; w < cnt_words; w += kPostThreads) {
-            uint32_t f = cntF[w], r = cntR[w];
-            cntF[w] = 0; cntR[w] = 0;
-            if (w == sent_w) { f &= sent_keep; r &= sent_keep; }
-            const uint32_t m = vmax<CB>(f, r);
-            if (CB == 8 ? __vcmpgtu4(m, cur_v) : __vcmpgtu2(m, cur_v)) {
-#pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    const uint32_t v = (m >> (i * CB)) & CMASK;
-                    if (v > cur) { cur = v; cur_bin = w * PER + i; }
-                }
-                cur_v = cur * (CB == 8 ? 0x01010101u : 0x00010001u);
-            }
-            if (dense) {
+        // The sentinel's counter lies in the quad of words after the bins: it is not scanned, only cleared.
+        const uint32_t sent_word = postings_sentinel(nbl) / PER;
+        const uint32_t scan_quads = ((uint32_t)nbl + 4u * PER - 1u) / (4u * PER);
+        if (tid == 0) { cntF[sent_word] = 0; cntR[sent_word] = 0; }
+        if (a.counts_fwd || a.counts_rev) {                                 // dense counts on request (tests, tools)
+            for (uint32_t w = tid; w * PER < nbl; w += kPostThreads) {
+                const uint32_t f = cntF[w], r = cntR[w];
 #pragma unroll
                 for (int i = 0; i < PER; ++i) {
                     const uint32_t bin = w * PER + i;
@@ -394,6 +388,38 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                         if (a.counts_rev) a.counts_rev[read * nbl + bin] = (uint16_t)((r >> (i * CB)) & CMASK);
                     }
                 }
+            }
+            __syncthreads();
+        }
+        // One pass over quads of counter words (LDS.128 / STS.128): every thread keeps the largest count it has seen and
+        // the first bin that had it (its bins ascend); a quad is unpacked only when the SWAR test says that one of its
+        // counters may beat that.  A maximum below every threshold of the read yields key 0 whatever it is, so the search
+        // starts at min(thr) - 1 and the unpacking is rare (random reads: never).
+        constexpr uint32_t LOW = CB == 8 ? 0x7F7F7F7Fu : 0x7FFF7FFFu, ONES = CB == 8 ? 0x01010101u : 0x00010001u;
+        constexpr uint32_t HALF = (CMASK + 1u) / 2u;                        // 128 or 32 768
+        uint32_t thr_min = CMASK + 1u;                                      // not classified: nothing to find
+        if (flag == 0)
+            for (uint32_t t = 0; t < a.n_lut; ++t) thr_min = min(thr_min, (uint32_t)__ldg(a.lut + (size_t)t * kLutSize + len));
+        uint32_t cur = min(thr_min, CMASK + 1u) - (thr_min ? 1u : 0u), cur_bin = 0;
+        // counter c > cur  =>  c >= HALF, or (c & LOW) + (HALF - 1 - cur) carries into the top bit (cur < HALF);
+        // for cur >= HALF only the first test is left: necessary, not sufficient -- the unpacking decides
+        uint32_t add = (HALF - 1u - min(cur, HALF - 1u)) * ONES;
+        uint4 *const qF = reinterpret_cast<uint4 *>(cntF), *const qR = reinterpret_cast<uint4 *>(cntR);
+        for (uint32_t qd = tid; qd < scan_quads; qd += kPostThreads) {
+            const uint4 f = qF[qd], r = qR[qd];
+            qF[qd] = make_uint4(0, 0, 0, 0); qR[qd] = make_uint4(0, 0, 0, 0);
+            const uint32_t gx = f.x | r.x, gy = f.y | r.y, gz = f.z | r.z, gw = f.w | r.w;
+            const uint32_t h = (((gx & LOW) + add) | gx) | (((gy & LOW) + add) | gy) | (((gz & LOW) + add) | gz) | (((gw & LOW) + add) | gw);
+            if (h & ~LOW) {
+                const uint32_t m[4] = {vmax<CB>(f.x, r.x), vmax<CB>(f.y, r.y), vmax<CB>(f.z, r.z), vmax<CB>(f.w, r.w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        const uint32_t v = (m[j] >> (i * CB)) & CMASK;
+                        if (v > cur) { cur = v; cur_bin = (4u * qd + j) * PER + i; }
+                    }
+                add = (HALF - 1u - min(cur, HALF - 1u)) * ONES;
             }
         }
         // (count, lowest bin) as one key: larger count wins, then the smaller bin (bins < 65 535)
@@ -417,7 +443,7 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
 size_t postings_smem_bytes(uint64_t n_bins_local, int counter_bits, uint32_t *cnt_words)
 {
     const uint32_t per = 32 / counter_bits;
-    const uint32_t words = (uint32_t)((n_bins_local + 1 + per - 1) / per + 1);     // + the sentinel's counter
+    const uint32_t words = postings_sentinel(n_bins_local) / per + 4;     // whole quads of bins + the sentinel's quad
     if (cnt_words) *cnt_words = words;
     return (size_t)2 * words * 4 + kPostPiece * 4 + kPostPiece + 32;
 }
@@ -427,7 +453,7 @@ size_t postings_smem_bytes(uint64_t n_bins_local, int counter_bits, uint32_t *cn
 // Applicable: wide row, k-mer index fits 32 bits, bin ids fit 16 bits with the sentinel, 8-bit counters fit shared memory.
 bool postings_applicable(const FilterView &fv)
 {
-    return fv.stride > 4 && fv.hp.k <= 15 && fv.n_bins_local < 65535 && fv.hp.n_blocks > 0 &&
+    return fv.stride > 4 && fv.hp.k <= 15 && fv.n_bins_local <= 65520 && fv.hp.n_blocks > 0 &&
            postings_smem_bytes(fv.n_bins_local, 8, nullptr) <= 200u * 1024u;
 }
 

@@ -1171,7 +1171,7 @@ int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stre
     drop_table(f);
     f->table_budget = max_table_bytes;
     if (!ensure_table(f, (cudaStream_t)stream, true))
-        return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable (k > 16, bins >= 65535 for postings) or over the memory budget");
+        return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable (k > 16, more than 65520 bins for postings) or over the memory budget");
     return RB_OK;
 }
 
