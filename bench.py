@@ -37,6 +37,13 @@ WORKLOADS = {
     "cfg3_3.1Gb_31kbins": dict(n_seqs=24, seq_len=129_166_667, fragment=100_000, k=13, chunk=250, reads=65_536),
     "w1_50x4Mb_50bins": dict(n_seqs=50, seq_len=4_000_000, fragment=4_200_000, k=13, chunk=250, reads=1_000_000),
     "mini_100x60kb_100bins": dict(n_seqs=100, seq_len=60_000, fragment=61_000, k=13, chunk=250, reads=65_536),
+    # BASELINE config #5 (30 Gb, ~300 k bins, 8 bin shards), one eighth per GPU: every rank generates ITS OWN 3.74 Gb genome
+    # group, builds ITS OWN column slice (37 440 bins = 585 row words, 5.8 GB) and never sees the rest of the filter;
+    # N ranks = an N x 37 440-bin filter over N x 3.74 Gb.  Needs --mode bin_sharded semantics (implied).
+    "cfg5_3.7Gb_37kbins_per_gpu": dict(per_rank=True, seq_len=3_743_950_001, window=64_000_000, fragment=100_000, k=13, chunk=250,
+                                       reads=65_536, bins_per_rank=37_440),
+    "mini5_40Mb_512bins_per_gpu": dict(per_rank=True, seq_len=51_150_001, window=8_000_000, fragment=100_000, k=13, chunk=250,
+                                       reads=16_384, bins_per_rank=512),
 }
 DEFAULT_WORKLOAD = "cfg2_100x4Mb_100bins"
 ERROR_RATE = 0.1
@@ -196,13 +203,31 @@ def run_ours(args, w, n_reads):
     if args.l2_gran:
         rb.set_l2_fetch_granularity(args.l2_gran, device=local)
     stream = torch.cuda.current_stream()
-    bin_sharded = args.mode == "bin_sharded" and world > 1
+    per_rank = bool(w.get("per_rank"))
+    bin_sharded = (args.mode == "bin_sharded" and world > 1) or per_rank
 
     # ---- build the IBF on the GPU (insert kernel) ------------------------------------------------------
-    ref = make_reference(w)
-    plan = synth.build_plan(ref, w["fragment"], w["k"])
-    del ref
-    gf_full = rb.IBF.create(plan["n_bins"], 3, w["k"], plan["n_bits"], device=local)
+    if per_rank:
+        # the first `window` bases of every rank's genome group are known to all ranks (the reads are sampled there, so
+        # all ranks classify the same batch); the rest is generated by its owner only
+        windows = [synth.random_bases(w["window"], 5000 + g) for g in range(world)]
+        seq = np.concatenate([windows[rank], synth.random_bases(w["seq_len"] - w["window"], 6000 + rank)])
+        bases_own = seq[:-1]                 # cutOutNNNs drops the last base of a sequence without trailing N (quirk Q1)
+        del seq
+        fb, fe = rb.capi.fragment_schedule(len(bases_own), w["fragment"], w["k"])
+        per_bins = len(bases_own) // w["fragment"] + 1              # IBFBuild.cpp:90
+        assert per_bins == w["bins_per_rank"] == len(fb) and per_bins % 64 == 0
+        n_bins = world * per_bins
+        plan = {"bases": bases_own, "frag_begin": fb, "frag_end": fe,
+                "frag_bin": np.arange(rank * per_bins, (rank + 1) * per_bins, dtype=np.uint64), "n_bins": n_bins,
+                "n_bits": rb.ibf_size_bits(w["fragment"], w["k"], 3, 0.01, n_bins)}
+        gf_full = rb.IBF.create_shard(n_bins, 3, w["k"], plan["n_bits"], rank, world, device=local)
+        assert gf_full.bin_begin == rank * per_bins and gf_full.n_bins_local >= per_bins
+    else:
+        ref = make_reference(w)
+        plan = synth.build_plan(ref, w["fragment"], w["k"])
+        del ref
+        gf_full = rb.IBF.create(plan["n_bins"], 3, w["k"], plan["n_bits"], device=local)
     d_ref = torch.from_numpy(plan["bases"]).to(dev)
     d_fb = torch.from_numpy(plan["frag_begin"].astype(np.int64)).to(dev)
     d_fe = torch.from_numpy(plan["frag_end"].astype(np.int64)).to(dev)
@@ -225,7 +250,10 @@ def run_ours(args, w, n_reads):
     del d_ref, d_fb, d_fe, d_fbin
     gf = gf_full
     full_keys_check = None
-    if bin_sharded:
+    if per_rank:
+        plan["bases"] = np.concatenate(windows)       # what the reads are sampled from (same on all ranks)
+        del windows, bases_own
+    elif bin_sharded:
         full_keys_check = True
         words = gf_full.download()
         gf = rb.IBF.from_words(words, plan["n_bins"], 3, w["k"], plan["n_bits"], device=local, shard=rank, n_shards=world)
@@ -254,7 +282,7 @@ def run_ours(args, w, n_reads):
 
     def step():
         gf.count_batch_dev(d_bases, d_off, n_reads, d_lut, n_lut, d_keys, max_read_len=w["chunk"], stream=stream)
-        if bin_sharded:
+        if bin_sharded and world > 1:
             dist.all_reduce(d_keys, op=dist.ReduceOp.MAX)       # keys < 2^49: int64 MAX == uint64 MAX
         rb.capi._check(lib.rb_keys_decode_dev(rb.capi._dev_ptr(d_keys), n_lut * n_reads, rb.capi._dev_ptr(d_max),
                                               rb.capi._dev_ptr(d_hit), rb.capi._dev_ptr(d_amax), local,
@@ -280,7 +308,15 @@ def run_ours(args, w, n_reads):
             gf.count_batch_dev(d_bases, d_off, n_reads, d_lut, n_lut, d_keys, max_read_len=w["chunk"], stream=stream)
             torch.cuda.synchronize()              # no collective here: the other ranks wait at the barrier below
     barrier()
-    if bin_sharded:
+    if per_rank:
+        # nobody holds the whole filter: the combined answer of a reference-derived chunk must name a bin of the sampling
+        # windows (the first window/fragment + 1 bins of a rank's range; 1.7 % of the bins by chance)
+        amax = d_amax[:n_reads].cpu().numpy().astype(np.int64)
+        hit = d_hit[:n_reads].cpu().numpy() > 0
+        sel = hit & from_ref
+        in_window = (amax[sel] % w["bins_per_rank"]) <= w["window"] // w["fragment"] + 1
+        assert sel.sum() > 0.9 * from_ref.sum() and in_window.mean() > 0.99, (sel.sum(), from_ref.sum(), in_window.mean())
+    elif bin_sharded:
         # the all-reduced shard keys must equal the keys of the whole (replicated) filter
         d_full = torch.zeros_like(d_keys)
         gf_full.count_batch_dev(d_bases, d_off, n_reads, d_lut, n_lut, d_full, max_read_len=w["chunk"], stream=stream)
@@ -297,7 +333,7 @@ def run_ours(args, w, n_reads):
         k_ev[i][0].record(stream)
         gf.count_batch_dev(d_bases, d_off, n_reads, d_lut, n_lut, d_keys, max_read_len=w["chunk"], stream=stream)
         k_ev[i][1].record(stream)
-        if bin_sharded:
+        if bin_sharded and world > 1:
             dist.all_reduce(d_keys, op=dist.ReduceOp.MAX)
         rb.capi._check(lib.rb_keys_decode_dev(rb.capi._dev_ptr(d_keys), n_lut * n_reads, rb.capi._dev_ptr(d_max),
                                               rb.capi._dev_ptr(d_hit), rb.capi._dev_ptr(d_amax), local,
@@ -315,7 +351,7 @@ def run_ours(args, w, n_reads):
 
     # ---- end-to-end timing through the host-buffer C ABI (H2D + kernels + D2H every step) ------------------
     e2e = None
-    if not args.no_e2e and not bin_sharded:
+    if not args.no_e2e and not bin_sharded:       # (bin shards: the host call returns decoded arrays, the combine needs keys)
         hb, ho = h_bases.numpy(), h_off.numpy().view(np.uint64)
         res_max = torch.empty(n_lut * n_reads, dtype=torch.int16, pin_memory=True).numpy().view(np.uint16)
         res_hit = torch.empty(n_lut * n_reads, dtype=torch.uint8, pin_memory=True).numpy()
@@ -473,9 +509,11 @@ def run_ours(args, w, n_reads):
     value = units * args.steps / (total_ms * 1e-3)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak" if not bin_sharded else "strong",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak" if (not bin_sharded or per_rank) else "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": args.workload, "mode": args.mode if world > 1 else "single_gpu",
+        "config": {"workload": args.workload,
+                   "mode": ("bin_sharded, one genome group and one column slice per GPU, whole filter never in one place: %d bins / %.1f Gb"
+                            % (plan["n_bins"], world * w["seq_len"] / 1e9)) if per_rank else args.mode if world > 1 else "single_gpu",
                    "chunks_per_gpu_per_step": n_reads, "chunk_length": w["chunk"], "kmer_size": w["k"],
                    "bins": plan["n_bins"], "row_bytes": int(gf.bin_width * 8), "filter_bytes": plan["n_bits"] // 8,
                    "thresholds_per_pass": n_lut, "l2_fetch_granularity": rb.get_l2_fetch_granularity(local), "error_rate": ERROR_RATE, "read_mix": "%g%% reference-derived @10%% errors, %g%% iid" % (100 * args.from_ref, 100 - 100 * args.from_ref),

@@ -107,6 +107,11 @@ RB_API uint64_t rb_fragment_schedule(uint64_t seqlen, uint64_t fragment_length, 
 /* TIbf(bins, hashes, k, bits) ctor, src/IBF/IBFBuild.cpp:465: zero-filled matrix in HBM */
 RB_API rb_ibf *rb_ibf_create(uint64_t n_bins, uint32_t n_hash, uint32_t kmer_size, uint64_t n_bits,
                              int device, int *status);
+/* The same ctor for ONE bin shard of a filter that is never held in one place (BASELINE config #5): a zero-filled
+ * column slice [shard*W/n_shards, (shard+1)*W/n_shards) of every row of the (n_bins, n_bits) filter.  Inserts take
+ * global bin ids and skip the bins of other shards. */
+RB_API rb_ibf *rb_ibf_create_shard(uint64_t n_bins, uint32_t n_hash, uint32_t kmer_size, uint64_t n_bits,
+                                   int device, int shard, int n_shards, int *status);
 /* seqan::retrieve, src/IBF/IBFBuild.cpp:343,360 and src/config/configReader.cpp:216.
  * Validates the sdsl header and metadata tail; a FASTA or truncated file fails
  * with RB_ERR_PARSE_IBF_FILE, a missing one with RB_ERR_MISSING_IBF_FILE. */

@@ -25,7 +25,7 @@ LUT_SIZE = 65536
 EXPORTS = [
     "rb_status_string", "rb_last_error", "rb_device_count", "rb_ibf_size_bits", "rb_calculate_ci",
     "rb_threshold_lut", "rb_cut_out_nnns", "rb_fragment_schedule", "rb_ibf_create", "rb_ibf_load",
-    "rb_ibf_load_shard", "rb_ibf_from_words", "rb_ibf_store", "rb_ibf_download", "rb_ibf_free", "rb_ibf_info",
+    "rb_ibf_load_shard", "rb_ibf_create_shard", "rb_ibf_from_words", "rb_ibf_store", "rb_ibf_download", "rb_ibf_free", "rb_ibf_info",
     "rb_ibf_device_words", "rb_ibf_device_kmer_table", "rb_ibf_insert_batch", "rb_ibf_insert_batch_dev", "rb_ibf_count_batch",
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_set_insert_kernel", "rb_kernel_launches",
     "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
@@ -88,6 +88,7 @@ def lib():
         "rb_ibf_create": (vp, [u64, u32, u32, u64, i32, ip]),
         "rb_ibf_load": (vp, [C.c_char_p, i32, ip]),
         "rb_ibf_load_shard": (vp, [C.c_char_p, i32, i32, i32, ip]),
+        "rb_ibf_create_shard": (vp, [u64, u32, u32, u64, i32, i32, i32, ip]),
         "rb_ibf_from_words": (vp, [vp, u64, u32, u32, u64, i32, i32, i32, ip]),
         "rb_ibf_store": (i32, [vp, C.c_char_p]),
         "rb_ibf_download": (i32, [vp, vp, u64]),
@@ -262,6 +263,12 @@ class IBF:
     def create(cls, n_bins, n_hash, kmer_size, n_bits, device=0):
         st = C.c_int(0)
         return cls._wrap(lib().rb_ibf_create(n_bins, n_hash, kmer_size, n_bits, device, C.byref(st)), st)
+
+    @classmethod
+    def create_shard(cls, n_bins, n_hash, kmer_size, n_bits, shard, n_shards, device=0):
+        """Zero-filled bin shard of a filter that is never held in one place (rb_ibf_create_shard)."""
+        st = C.c_int(0)
+        return cls._wrap(lib().rb_ibf_create_shard(n_bins, n_hash, kmer_size, n_bits, device, shard, n_shards, C.byref(st)), st)
 
     @classmethod
     def load(cls, path, device=0, shard=0, n_shards=1):

@@ -22,6 +22,7 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
@@ -29,8 +30,9 @@ namespace rb {
 
 namespace {
 
-constexpr int kPostThreads = 256;
-constexpr int kPostWarps = kPostThreads / 32;
+// threads per CTA by how many CTAs of counters fit the shared memory of an SM: 3 x 256, 2 x 384 or 1 x 768, always 24
+// warps per SM under the 85-register ceiling of that many threads
+constexpr int kPostThreadsMax = 768;
 constexpr int kPostPiece = 512;               // k-mer positions staged per pass over a read
 constexpr int kPostInFlight = 4;              // lists a warp loads before it counts them (even: strands alternate)
 
@@ -273,12 +275,13 @@ __device__ __noinline__ void add_hashed(const FilterView &fv, const uint8_t *dig
 template <int CB>
 __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return CB == 8 ? __vmaxu4(a, b) : __vmaxu2(a, b); }
 
-template <int CB>
-__global__ void __launch_bounds__(kPostThreads, CB == 8 ? 3 : 1)      // 8-bit counters of 31 K bins: 3 CTAs of shared memory
+template <int CB, int kPostThreads>
+__global__ void __launch_bounds__(kPostThreads, 768 / kPostThreads)
 count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const uint4 *__restrict__ ids, const uint32_t cnt_words)
 {
     constexpr int PER = 32 / CB;
     constexpr uint32_t CMASK = (CB == 8) ? 0xFFu : 0xFFFFu;
+    constexpr int kPostWarps = kPostThreads / 32;
     extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t *const cntF = s_mem, *const cntR = s_mem + cnt_words;
     uint32_t *const s_x = s_mem + 2 * cnt_words;                         // [kPostPiece] packed k-mer or ~0u (not ACGT)
@@ -514,19 +517,26 @@ int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint1
     const size_t smem = postings_smem_bytes(a.fv.n_bins_local, narrow ? 8 : 16, &cnt_words);
     if (smem > 220u * 1024u) return -2;
     const uint4 *ids = reinterpret_cast<const uint4 *>(d_ids);
-    int occ = 1;
+    // CTAs of this much shared memory per SM (227 KB usable, 1 KB reserved per CTA) -> threads per CTA
+    const int fit = (int)std::min<size_t>(3, (227u * 1024u) / (smem + 1024u));
+    auto launch = [&](auto kernel, int threads) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+        if (occ < 1) occ = 1;
+        const uint64_t cap = (uint64_t)sm_count * occ;
+        const uint32_t gx = (uint32_t)(a.n_reads < cap ? a.n_reads : cap);
+        kernel<<<gx, threads, smem, st>>>(a, d_ptr, ids, cnt_words);
+    };
     if (narrow) {
-        cudaFuncSetAttribute(count_postings_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_postings_kernel<8>, kPostThreads, smem);
+        if (fit >= 3) launch(count_postings_kernel<8, 256>, 256);
+        else if (fit == 2) launch(count_postings_kernel<8, 384>, 384);
+        else launch(count_postings_kernel<8, 768>, 768);
     } else {
-        cudaFuncSetAttribute(count_postings_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_postings_kernel<16>, kPostThreads, smem);
+        if (fit >= 3) launch(count_postings_kernel<16, 256>, 256);
+        else if (fit == 2) launch(count_postings_kernel<16, 384>, 384);
+        else launch(count_postings_kernel<16, 768>, 768);
     }
-    if (occ < 1) occ = 1;
-    const uint64_t cap = (uint64_t)sm_count * occ;
-    const uint32_t gx = (uint32_t)(a.n_reads < cap ? a.n_reads : cap);
-    if (narrow) count_postings_kernel<8><<<gx, kPostThreads, smem, st>>>(a, d_ptr, ids, cnt_words);
-    else count_postings_kernel<16><<<gx, kPostThreads, smem, st>>>(a, d_ptr, ids, cnt_words);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

@@ -980,6 +980,24 @@ rb_ibf *rb_ibf_create(uint64_t n_bins, uint32_t n_hash, uint32_t kmer_size, uint
     return f;
 }
 
+rb_ibf *rb_ibf_create_shard(uint64_t n_bins, uint32_t n_hash, uint32_t kmer_size, uint64_t n_bits, int device, int shard,
+                            int n_shards, int *status)
+{
+    int st = check_device(device);
+    rb_ibf *f = nullptr;
+    if (st == RB_OK) {
+        f = new rb_ibf();
+        f->device = device;
+        f->n_bins = n_bins; f->n_hash = n_hash; f->k = kmer_size; f->n_bits = n_bits;
+        DeviceGuard g(device);
+        st = derive_geometry(f, shard, n_shards);
+        if (st == RB_OK) st = alloc_device(f, true);
+        if (st != RB_OK) { destroy(f); f = nullptr; }
+    }
+    if (status) *status = st;
+    return f;
+}
+
 rb_ibf *rb_ibf_from_words(const uint64_t *words, uint64_t n_bins, uint32_t n_hash, uint32_t kmer_size, uint64_t n_bits,
                           int device, int shard, int n_shards, int *status)
 {

@@ -353,6 +353,29 @@ def test_transfer_policy_times_both_ways(monkeypatch):
     assert abs(int(rb.transfer_bytes()[0] - x0) - int(moved[0])) < moved[0] // 100      # planes, fewer per-piece paddings
 
 
+def test_create_shard_builds_a_column_slice_in_place():
+    """rb_ibf_create_shard + inserts with global bin ids (bins of other shards are skipped) == the column slice of the
+    whole filter, for every shard; the shards' keys combine (MAX) to the whole filter's keys."""
+    plan, of, gf = make_filter_pair(1, 700 * 2000 + 7, 2000, 13)            # 701 bins, 11 row words
+    whole = gf.download()
+    bases, off = synth.ragged_reads(plan["bases"], [250] * 300 + [0, 5, 1000], seed=9, frac_from_ref=0.7, n_frac=0.002)
+    lut = rb.threshold_lut(0.1, 13)
+    exp = of.count_batch(bases, off, lut, n_threads=4)
+    combined = None
+    for s_ in range(3):
+        sh = rb.IBF.create_shard(plan["n_bins"], 3, 13, plan["n_bits"], s_, 3)
+        sh.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+        ref = rb.IBF.from_words(whole, plan["n_bins"], 3, 13, plan["n_bits"], shard=s_, n_shards=3)
+        assert (sh.col_begin, sh.col_words, sh.bin_begin, sh.n_bins_local) == (ref.col_begin, ref.col_words, ref.bin_begin, ref.n_bins_local)
+        assert np.array_equal(sh.download(), ref.download())
+        got = sh.count_batch(bases, off, lut)
+        k_s = (got["hit"].astype(np.uint64) << np.uint64(48)) | (got["max_count"].astype(np.uint64) << np.uint64(32)) | \
+              np.where(got["hit"] > 0, (~got["argmax_bin"]).astype(np.uint64) & np.uint64(0xFFFFFFFF), np.uint64(0))
+        combined = k_s if combined is None else np.maximum(combined, k_s)
+    mx, hit, am = rb.keys_decode(combined)
+    assert np.array_equal(mx, exp["max_count"]) and np.array_equal(hit, exp["hit"]) and np.array_equal(am, exp["argmax_bin"])
+
+
 def test_two_threshold_tables_in_one_pass():
     plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
     bases, off, _ = synth.sample_reads(plan["bases"], 3000, 250, seed=5, error_rate=0.12)
