@@ -414,6 +414,11 @@ def run_ours(args, w, n_reads):
                 "traffic": traffic, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_chunk": bytes_per_chunk, "peak_source": peak_src,
                 "kmer_lookups_per_s": (n_reads if bin_sharded else world * n_reads) * lookups / (total_ms * 1e-3 / args.steps)}
+    if traffic:     # what the kernel really moves (table entries / postings lists, not the reference's row probes) against HBM peak
+        roofline["dram"] = {"bytes_per_launch": traffic, "bytes_per_chunk": traffic / n_reads,
+                            "achieved": traffic / (kernel_ms * 1e-3) / 1e9, "unit": "GB/s",
+                            "frac": traffic / (kernel_ms * 1e-3) / 1e9 / peak,
+                            "how": "ncu dram bytes of one launch (profiles/traffic.json) / this run's kernel time"}
     # Narrow rows are bound by memory REQUESTS, not bytes: measure the box's random-gather ceiling
     # over the very buffer the kernel reads, with the kernel's request shape, and report requests/s against it.
     row_bytes = int(gf.col_words * 8)
