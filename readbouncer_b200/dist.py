@@ -26,6 +26,21 @@ def bin_shard_columns(bin_width, rank, world):
     return b, e - b
 
 
+def per_rank_bin_ranges(bins_per_rank, world):
+    """Bin ranges [lo, hi) of the column slices when every rank contributes `bins_per_rank` bins (a multiple of 64) to ONE
+    filter that is built slice by slice (rb_ibf_create_shard): the filter has world * bins_per_rank bins and
+    world * bins_per_rank / 64 + 1 row words (IBFBuild.cpp:404-413 reserves one more 64-bin word); slice r starts exactly at
+    bin r * bins_per_rank, and the last slice also holds the spare word."""
+    assert bins_per_rank % 64 == 0 and bins_per_rank > 0
+    n_bins = bins_per_rank * world
+    bin_width = n_bins // 64 + 1
+    out = []
+    for r in range(world):
+        b, w = bin_shard_columns(bin_width, r, world)
+        out.append((64 * b, min(n_bins, 64 * (b + w))))
+    return out
+
+
 def combine_keys(keys, group=None):
     """In-place elementwise MAX of packed summary keys across ranks (int64 tensor; keys are < 2^49)."""
     assert keys.dtype == torch.int64

@@ -105,3 +105,15 @@ def test_shard_arithmetic():
             if W >= w:
                 assert sum(c for _, c in cols) == W and cols[0][0] == 0
                 assert all(cols[i][0] + cols[i][1] == cols[i + 1][0] for i in range(w - 1))
+
+
+def test_per_rank_built_slices_start_at_their_own_bins():
+    """BASELINE config #5 built slice by slice: with a multiple of 64 bins per rank, rank r's slice holds exactly its bins."""
+    from readbouncer_b200 import dist as rbdist
+    for per in (64, 512, 37440):
+        for world in (1, 2, 3, 4, 8):
+            rng = rbdist.per_rank_bin_ranges(per, world)
+            assert [lo for lo, _ in rng] == [r * per for r in range(world)]
+            assert [hi for _, hi in rng] == [(r + 1) * per for r in range(world)]
+    # 8 x 37 440 bins = the 30 Gb filter of config #5: 4 681 row words, 585 (the last 586) per GPU
+    assert rbdist.bin_shard_columns(8 * 37440 // 64 + 1, 7, 8) == (4095, 586)
