@@ -222,7 +222,7 @@ RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_ma
  * (re)builds it now under the given byte budget (0 = automatic); UINT64_MAX disables the table for
  * this handle.
  * Wide filters (rows > 4 words, <= 65520 local bins, k <= 15) get a POSTINGS table instead: the AND of
- * the probed rows is ~1 % dense by the reference's own sizing, so the sorted list of set bins of every
+ * the probed rows is ~1 % dense by the reference's own sizing, so the list of set bins of every
  * k-mer (2 bytes each, ~50 GB for a human-genome filter at k=13) replaces streaming 2*h rows of
  * thousands of bytes per position; same policy, budget and env switches. */
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);

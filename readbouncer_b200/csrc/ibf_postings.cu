@@ -5,7 +5,7 @@
 // thousands of bits -- 3 880 bytes for the 31 008 bins of a human reference -- but it is SPARSE: a bin's bit
 // survives the AND only if the bin holds the k-mer or all h probes are false positives, about 1 % by the
 // reference's own sizing (max_fp = 0.01, IBFBuild.cpp:404-413).  Tabulated densely the function needs 260 GB
-// (k = 13); as postings -- the sorted list of set bins per k-mer, 2 bytes each -- it needs ~50 GB and fits HBM.
+// (k = 13); as postings -- the list of set bins per k-mer, 2 bytes each -- it needs ~50 GB and fits HBM.
 //
 //   ptr[x], ptr[x+1]   list of k-mer x in units of 8 ids (16 bytes), x = sum rank_j * 4^(k-1-j), ranks A0 C1 G2 T3
 //   ids[8 * u + i]     local bin indices; lists are padded to a multiple of 8 with a sentinel (n_bins_local rounded up to
