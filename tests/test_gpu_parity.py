@@ -669,3 +669,29 @@ def test_resize_bins_and_append_equals_oracle(old_seqs, new_seqs):
     assert (exp["argmax_bin"][exp["hit"] > 0] >= old_seqs).any() and (exp["argmax_bin"][exp["hit"] > 0] < old_seqs).any()
     with pytest.raises(rb.RBError):
         gf.resize_bins(total - 1)
+
+
+@pytest.mark.parametrize("workload,extra", [
+    ("mini_100x60kb_100bins", []),
+    ("mini5_40Mb_512bins_per_gpu", []),            # config #5 shape: own genome group, own column slice (rb_ibf_create_shard)
+])
+def test_bench_line_on_mini_workloads(workload, extra):
+    """bench.py end to end on small workloads: one JSON line with the contract's keys; its own asserts (GPU == oracle on
+    the batch, host-API == device-API, argmax bins inside the sampling windows) must hold."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", workload, "--steps", "3", "--warmup", "3"] + extra,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["roofline"]["frac"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    if "per_gpu" not in workload:
+        assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
