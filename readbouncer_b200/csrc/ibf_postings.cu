@@ -30,9 +30,8 @@ namespace rb {
 
 namespace {
 
-// threads per CTA by how many CTAs of counters fit the shared memory of an SM: 3 x 256, 2 x 384 or 1 x 768, always 24
-// warps per SM under the 85-register ceiling of that many threads
-constexpr int kPostThreadsMax = 768;
+// Threads per CTA (template parameter of the lookup kernel) follow from how many CTAs of counters fit the shared memory
+// of an SM: 3 x 256, 2 x 384 or 1 x 768 -- always 24 warps per SM under the 85-register ceiling of 768 threads.
 constexpr int kPostPiece = 512;               // k-mer positions staged per pass over a read
 constexpr int kPostInFlight = 4;              // lists a warp loads before it counts them (even: strands alternate)
 
