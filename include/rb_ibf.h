@@ -148,7 +148,10 @@ RB_API int rb_ibf_resize_bins(rb_ibf *f, uint64_t new_n_bins, rb_stream stream);
 RB_API int rb_ibf_insert_batch(rb_ibf *f, const char *bases, uint64_t n_bases,
                                const uint64_t *frag_begin, const uint64_t *frag_end,
                                const uint64_t *frag_bin, uint64_t n_frags, rb_stream stream);
-/* device-pointer variant; max_frag_len is a launch-shape hint (0 = unknown) */
+/* device-pointer variant; max_frag_len is a launch-shape hint (0 = unknown).
+ * Device base buffers (here and in rb_ibf_count_batch_dev) are fetched as aligned 16-byte blocks: they must be readable from
+ * the 16-byte boundary at or below their first byte to the one at or above their last byte -- true of every cudaMalloc /
+ * torch allocation and of any sub-range of one; the bytes outside the fragments / reads are never interpreted. */
 RB_API int rb_ibf_insert_batch_dev(rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_frag_begin,
                                    const uint64_t *d_frag_end, const uint64_t *d_frag_bin,
                                    uint64_t n_frags, uint64_t max_frag_len, rb_stream stream);

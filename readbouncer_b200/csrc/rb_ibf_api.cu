@@ -1272,7 +1272,8 @@ int rb_ibf_insert_batch(rb_ibf *f, const char *bases, uint64_t n_bases, const ui
     uint8_t *d_bases = nullptr;
     uint64_t *d_frag = nullptr;
     auto body = [&]() -> int {
-        RB_CUDA(cudaMallocAsync(&d_bases, n_bases ? n_bases : 1, st));
+        // the kernels fetch bases as aligned 16-byte blocks: the copy may be over-read up to the next 16-byte boundary
+        RB_CUDA(cudaMallocAsync(&d_bases, n_bases + 32, st));
         RB_CUDA(cudaMallocAsync(&d_frag, 3 * n_frags * 8, st));
         RB_CUDA(cudaMemcpyAsync(d_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
         RB_CUDA(cudaMemcpyAsync(d_frag, frag_begin, n_frags * 8, cudaMemcpyHostToDevice, st));
