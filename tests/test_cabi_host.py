@@ -169,3 +169,24 @@ def test_cpp_shim_on_gpu(tmp_path, golden_ibf_paths, known):
                           data_path("lib_test.fasta"), str(tmp_path), known["known"]["read354"]["seq"]],
                          capture_output=True, text=True)
     assert out.returncode == 0 and "gpu OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU oracle port on all host cores) on a small workload: one JSON line with the
+    contract's keys, no GPU work, and -- under a multi-rank launch -- nothing from ranks other than 0."""
+    import json
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "mini_100x60kb_100bins",
+           "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "classified_250b_read_chunks_per_sec" and d["unit"] == "chunks/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
