@@ -190,3 +190,14 @@ def test_reference_arm_prints_the_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_bench_refuses_to_run_without_a_gpu():
+    """No CPU fallback anywhere: on a box without a CUDA device the product arm of bench.py stops with an error."""
+    import sys
+    if rb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "mini_100x60kb_100bins", "--steps", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
+    assert not any(ln.startswith("{") for ln in out.stdout.splitlines())
