@@ -263,6 +263,23 @@ RB_API int rb_microbench_gather_coop(const void *d_buf, uint64_t n_rows, uint32_
                                      uint64_t probes_per_group, uint32_t n_blocks, uint64_t *d_sink,
                                      rb_stream stream);
 
+/* Measurement aid: what one rb_ibf_count_batch_dev launch over this batch has to fetch from HBM, derived from the table
+ * geometry of the handle as it is now (k-mer window table, postings, or hashed row probes when no table is built):
+ *   table_bytes     bytes of table data at 128-byte line granularity (HBM delivers whole lines; nothing assumed in L2)
+ *   table_requests  table accesses (entries, lists + list bounds, or row probes)
+ *   io_bytes        read bases + offsets in, keys out
+ * bench.py divides their sum by the kernel's measured time for roofline.frac; profiles/ holds the ncu dram__bytes check.
+ * Synchronises the stream. */
+RB_API int rb_ibf_count_traffic_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                                    uint32_t n_lut, uint64_t *table_bytes, uint64_t *table_requests, uint64_t *io_bytes,
+                                    rb_stream stream);
+
+/* Test / benchmark aid (not on the product path): n synthetic ACGT bases, positions [start, start + n) of the stream
+ * `seed`, written to d_out (device).  base(i) = "ACGT"[(mix64(seed * 0xD1342543DE82EF95 + (i >> 5)) >> 2 (i & 31)) & 3]
+ * with the splitmix64 finaliser, so a host regenerates any window without holding the sequence: multi-Gb references
+ * (BASELINE configs #3-#5) are generated where they are inserted. */
+RB_API int rb_synth_bases_dev(uint8_t *d_out, uint64_t n, uint64_t seed, uint64_t start, rb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,7 @@ EXPORTS = [
     "rb_ibf_count_batch_dev", "rb_keys_decode_dev", "rb_set_count_kernel", "rb_set_insert_kernel", "rb_kernel_launches",
     "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
     "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins", "rb_host_pack_info", "rb_transfer_bytes",
-    "rb_ibf_transfer_policy",
+    "rb_ibf_transfer_policy", "rb_ibf_count_traffic_dev", "rb_synth_bases_dev",
 ]
 
 
@@ -53,9 +53,9 @@ def lib_path():
 
 def build_library(force=False):
     """Compile librb_ibf.so in-tree with nvcc for sm_100a (see csrc/Makefile)."""
-    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", "Makefile"))]
+    srcs = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".hpp", "Makefile"))]
     root = os.path.dirname(_HERE)
-    srcs += [os.path.join(root, "include", f) for f in ("rb_ibf.h", "rb_interleave.hpp", "rb_drivers.hpp")]
+    srcs += [os.path.join(root, "include", f) for f in os.listdir(os.path.join(root, "include")) if f.endswith((".h", ".hpp"))]
     srcs.append(os.path.join(root, "tools", "rb_readbouncer.cpp"))
     exe = os.path.join(_HERE, "bin", "rb_readbouncer")
     stale = (not os.path.exists(_LIB) or not os.path.exists(exe)
@@ -113,6 +113,8 @@ def lib():
         "rb_host_pack_info": (i32, [vp, vp]),
         "rb_transfer_bytes": (i32, [vp, vp]),
         "rb_ibf_transfer_policy": (i32, [vp, vp, vp, vp]),
+        "rb_ibf_count_traffic_dev": (i32, [vp, vp, vp, u64, u32, vp, vp, vp, vp]),
+        "rb_synth_bases_dev": (i32, [vp, u64, u64, u64, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -175,6 +177,11 @@ def microbench_gather(d_buf, n_rows, row_bytes, probes_per_thread, n_blocks, d_s
 def microbench_gather_coop(d_buf, n_rows, row_bytes, lane_bytes, probes_per_group, n_blocks, d_sink, stream=None):
     _check(lib().rb_microbench_gather_coop(_dev_ptr(d_buf), n_rows, row_bytes, lane_bytes, probes_per_group, n_blocks,
                                            _dev_ptr(d_sink), _stream_ptr(stream)))
+
+
+def synth_bases_dev(d_out, n, seed, start=0, stream=None):
+    """n synthetic bases of stream `seed` from position `start` into a device buffer (see synth.hash_bases for the host twin)."""
+    _check(lib().rb_synth_bases_dev(_dev_ptr(d_out), int(n), int(seed), int(start), _stream_ptr(stream)))
 
 
 def host_pack_info():
@@ -374,6 +381,13 @@ class IBF:
         _check(lib().rb_ibf_count_batch_dev(self._h, _dev_ptr(d_bases), _dev_ptr(d_read_off), n_reads, max_read_len,
                                             _dev_ptr(d_thr_lut), n_lut, _dev_ptr(d_keys), _dev_ptr(d_counts_fwd),
                                             _dev_ptr(d_counts_rev), _dev_ptr(d_read_flag), _stream_ptr(stream)))
+
+    def count_traffic_dev(self, d_bases, d_read_off, n_reads, n_lut=1, stream=None):
+        """(table_bytes at 128-byte line granularity, table_requests, io_bytes) of one count launch over this batch."""
+        tb, tr, io = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().rb_ibf_count_traffic_dev(self._h, _dev_ptr(d_bases), _dev_ptr(d_read_off), n_reads, n_lut,
+                                              C.byref(tb), C.byref(tr), C.byref(io), _stream_ptr(stream)))
+        return int(tb.value), int(tr.value), int(io.value)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -78,4 +78,8 @@ int launch_keys_decode_piece(const uint64_t *keys, const uint8_t *flag_in, uint6
                              uint64_t out_off, uint16_t *max_count, uint8_t *hit, uint32_t *argmax_bin, uint8_t *flag_out,
                              cudaStream_t st);
 
+// measurement aid (ibf_traffic.cu): DRAM bytes at 128-byte line granularity, table accesses and base bytes of one count launch
+int launch_traffic(const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads, uint32_t k, uint32_t n_hash, int kind, int span,
+                   uint32_t entry_bytes, const uint32_t *ptr, unsigned long long *d_out, int sm_count, cudaStream_t st);
+
 }  // namespace rb

@@ -86,7 +86,48 @@ __global__ void __launch_bounds__(256) gather_coop_kernel(const uint8_t *__restr
     if (acc == 0x123456789ABCDEFULL) sink[0] = acc;
 }
 
+// Synthetic reference generator (test / benchmark aid): base i of the stream `seed` is a pure function of (seed, i), so
+// the host regenerates any window without holding the sequence (readbouncer_b200/synth.py: hash_bases).
+//   h(b) = mix64(seed * 0xD1342543DE82EF95 + b), b = i >> 5;  code = (h >> 2 (i & 31)) & 3;  base = "ACGT"[code]
+__global__ void __launch_bounds__(256) synth_bases_kernel(uint8_t *__restrict__ out, uint64_t n, uint64_t seed, uint64_t start)
+{
+    const uint64_t b_first = start >> 5, b_last = (start + n + 31) >> 5;          // hash blocks [b_first, b_last)
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t b = b_first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < b_last; b += stride) {
+        const uint64_t h = mix64(seed * 0xD1342543DE82EF95ULL + b);
+        const uint64_t p0 = b << 5;
+        uint32_t wds[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x |= ((0x54474341u >> (8 * (uint32_t)((h >> (2 * (4 * w + j))) & 3u))) & 0xFFu) << (8 * j);
+            wds[w] = x;
+        }
+        uint8_t *dst = out + (p0 - start);                                       // may lie before `out` for the first block
+        if (p0 >= start && p0 + 32 <= start + n && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+            reinterpret_cast<uint4 *>(dst)[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+            reinterpret_cast<uint4 *>(dst)[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint64_t p = p0 + j;
+                if (p >= start && p < start + n) out[p - start] = (uint8_t)(wds[j >> 2] >> (8 * (j & 3)));
+            }
+        }
+    }
+}
+
 }  // namespace rb
+
+extern "C" RB_API int rb_synth_bases_dev(uint8_t *d_out, uint64_t n, uint64_t seed, uint64_t start, rb_stream stream)
+{
+    if (n == 0) return RB_OK;
+    if (!d_out) return RB_ERR_INVALID_ARG;
+    const uint64_t blocks = ((n + 31) / 32 + 1 + 255) / 256;
+    rb::synth_bases_kernel<<<(unsigned)(blocks < 148u * 32u ? blocks : 148u * 32u), 256, 0, (cudaStream_t)stream>>>(d_out, n, seed, start);
+    return cudaGetLastError() == cudaSuccess ? RB_OK : RB_ERR_CUDA;
+}
 
 extern "C" RB_API int rb_microbench_gather(const void *d_buf, uint64_t n_rows, uint32_t row_bytes,
                                            uint64_t probes_per_thread, uint32_t n_blocks, uint64_t *d_sink,

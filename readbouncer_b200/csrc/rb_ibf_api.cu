@@ -1363,6 +1363,38 @@ int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_
     return st;
 }
 
+int rb_ibf_count_traffic_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads, uint32_t n_lut,
+                             uint64_t *table_bytes, uint64_t *table_requests, uint64_t *io_bytes, rb_stream stream)
+{
+    if (!f) return fail(RB_ERR_NULL_FILTER, "no filter");
+    if (!d_bases || !d_read_off) return fail(RB_ERR_INVALID_ARG, "null device pointer");
+    DeviceGuard g(f->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int kind, span;
+    uint32_t entry_bytes;
+    const uint32_t *ptr = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(f->table_mu);
+        kind = f->table_kind; span = f->table_span;
+        if (kind == 1) entry_bytes = (uint32_t)(span == 1 ? 16 * f->col_words : (span == 2 ? 2 : 4) * 16 * f->col_words);
+        else if (kind == 2) { entry_bytes = 16; ptr = f->d_post_ptr; }
+        else entry_bytes = (uint32_t)(8 * f->col_words);
+    }
+    unsigned long long *d_out = nullptr, h_out[3] = {0, 0, 0};
+    RB_CUDA(cudaMalloc(&d_out, sizeof(h_out)));
+    int n = rb::launch_traffic(d_bases, d_read_off, n_reads, (uint32_t)f->k, (uint32_t)f->n_hash, kind, span, entry_bytes, ptr, d_out,
+                               f->sm_count, st);
+    cudaError_t e = n < 0 ? cudaErrorUnknown : cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(RB_ERR_CUDA, "traffic kernel failed"); }
+    g_launches += 1;
+    if (table_bytes) *table_bytes = h_out[0];
+    if (table_requests) *table_requests = h_out[1];
+    if (io_bytes) *io_bytes = h_out[2] + n_reads * 8 + 8 + (uint64_t)n_lut * n_reads * 8;    // bases + offsets in, keys out
+    return RB_OK;
+}
+
 int rb_ibf_transfer_policy(const rb_ibf *f, int *choice, double *ns_per_base_packed, double *ns_per_base_ascii)
 {
     if (!f) return fail(RB_ERR_NULL_FILTER, "no filter");

@@ -21,6 +21,94 @@ def random_bases(n, seed):
     return ACGT[rng.integers(0, 4, size=int(n), dtype=np.uint8)]
 
 
+_M64 = (1 << 64) - 1
+
+
+def _mix64(z):
+    """splitmix64 finaliser on a uint64 array (same as mix64 in csrc/ibf_microbench.cu)."""
+    with np.errstate(over="ignore"):
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def hash_bases(start, n, seed):
+    """Bases [start, start + n) of the synthetic stream `seed`: the host twin of rb_synth_bases_dev (a pure function of
+    (seed, position), so multi-Gb references are generated on the GPU and only the windows reads are sampled from are
+    regenerated here)."""
+    start, n = int(start), int(n)
+    b0, b1 = start >> 5, (start + n + 31) >> 5
+    base = np.uint64((int(seed) * 0xD1342543DE82EF95) & _M64)
+    with np.errstate(over="ignore"):
+        h = _mix64(np.arange(b0, b1, dtype=np.uint64) + base)
+    codes = ((h[:, None] >> (np.uint64(2) * np.arange(32, dtype=np.uint64))[None, :]) & np.uint64(3)).astype(np.uint8)
+    return ACGT[codes].reshape(-1)[start - 32 * b0: start - 32 * b0 + n]
+
+
+class HashReference:
+    """A synthetic reference of several sequences, sequence i = hash_bases(0, lengths[i], seed0 + i) -- what is left of a
+    raw record of lengths[i] + 1 bases after cutOutNNNs dropped its last base (IBFBuild.cpp:121-125, quirk Q1).  Never
+    materialised on the host at full size: `to_device` generates it in HBM, `windows` regenerates what reads are sampled
+    from, `plan` is IBF::create_filter's host logic on the lengths alone."""
+
+    def __init__(self, lengths, seed0):
+        self.lengths = [int(x) for x in lengths]
+        self.seeds = [int(seed0) + i for i in range(len(self.lengths))]
+        self.offsets = np.concatenate([[0], np.cumsum(self.lengths)]).astype(np.int64)
+
+    def __len__(self):
+        return int(self.offsets[-1])
+
+    def host(self, end=None):
+        """The concatenated bases on the host, or their first `end`."""
+        end = len(self) if end is None else int(end)
+        parts = []
+        for o, n, s in zip(self.offsets[:-1], self.lengths, self.seeds):
+            if o >= end:
+                break
+            parts.append(hash_bases(0, min(n, end - int(o)), s))
+        return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+
+    def to_device(self, device, stream=None):
+        import torch
+        d = torch.empty(len(self) + 32, dtype=torch.uint8, device=device)     # kernels fetch aligned 16-byte blocks
+        for o, n, s in zip(self.offsets[:-1], self.lengths, self.seeds):
+            capi.synth_bases_dev(d.data_ptr() + int(o), n, s, 0, stream)
+        return d
+
+    def windows(self, pos, win):
+        """(len(pos), win) bases starting at the global positions `pos` of the concatenated reference; a window that
+        would run over the end of its sequence is moved back to end there."""
+        pos = np.asarray(pos, dtype=np.int64)
+        win = int(win)
+        seq = np.searchsorted(self.offsets, pos, side="right") - 1
+        lens = np.asarray(self.lengths, dtype=np.int64)[seq]
+        assert (lens >= win).all()
+        local0 = np.minimum(pos - self.offsets[seq], lens - win)
+        nblk = win // 32 + 2
+        base = np.array([(s * 0xD1342543DE82EF95) & _M64 for s in self.seeds], dtype=np.uint64)[seq]
+        with np.errstate(over="ignore"):
+            h = _mix64((local0 >> 5).astype(np.uint64)[:, None] + np.arange(nblk, dtype=np.uint64)[None, :] + base[:, None])
+        codes = ((h[:, :, None] >> (np.uint64(2) * np.arange(32, dtype=np.uint64))[None, None, :]) & np.uint64(3)).astype(np.uint8)
+        idx = (local0 & 31)[:, None] + np.arange(win, dtype=np.int64)[None, :]
+        return ACGT[np.take_along_axis(codes.reshape(len(pos), nblk * 32), idx, axis=1)]
+
+    def plan(self, fragment_length, kmer_size=13, n_hash=3, max_fp=0.01, bin0=0, n_bins=None):
+        total_bins = sum(n // fragment_length + 1 for n in self.lengths)        # IBFBuild.cpp:90
+        fb, fe = [], []
+        for o, n in zip(self.offsets[:-1], self.lengths):
+            b, e = capi.fragment_schedule(n, fragment_length, kmer_size)
+            fb.append(b + np.uint64(o))
+            fe.append(e + np.uint64(o))
+        fb, fe = np.concatenate(fb), np.concatenate(fe)
+        nb = int(n_bins if n_bins is not None else total_bins)
+        return {"frag_begin": fb, "frag_end": fe, "frag_bin": np.arange(bin0, bin0 + len(fb), dtype=np.uint64),
+                "n_bins": nb, "n_bits": int(capi.ibf_size_bits(fragment_length, kmer_size, n_hash, max_fp, nb)),
+                "sum_seq_len": len(self), "bin_ids_consumed": int(len(fb)), "bins_own": int(total_bins),
+                "kmer_size": kmer_size, "n_hash": n_hash}
+
+
 def revcomp(a):
     return _COMP[a[::-1]]
 
@@ -81,7 +169,7 @@ def sample_reads(ref, n_reads, read_len, seed, frac_from_ref=0.5, error_rate=0.1
         idx = np.nonzero(from_ref[b0:b1])[0]
         if idx.size and len(ref) > win:
             pos = rng.integers(0, len(ref) - win, size=idx.size)
-            w = ref[pos[:, None] + np.arange(win)[None, :]]
+            w = ref.windows(pos, win) if hasattr(ref, "windows") else ref[pos[:, None] + np.arange(win)[None, :]]
             strand = rng.random(idx.size) < 0.5
             w[strand] = _COMP[w[strand][:, ::-1]]
             u = rng.random((idx.size, win))
