@@ -237,6 +237,7 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
     Conf.significance = 0.95;                                  // classify.hpp:173
     Conf.error_rate = config.IBF_Parsed.error_rate;
     const int cl = config.IBF_Parsed.chunk_length;
+    enable_kmer_tables(DepletionFilters, TargetFilters);      // one plan for all filters, before the first read
     ClassificationResults res;
     std::filesystem::create_directories(config.output_dir);
 
@@ -278,7 +279,7 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
                     BatchCounts c = count_matches_batch(f.filter, bases.data(), off.data(), m, Conf, deplete && target);
                     cnt.emplace_back(c.max_count.begin(), c.max_count.begin() + m);
                     if (deplete && target) cnt_s.emplace_back(c.max_count.begin() + m, c.max_count.begin() + 2 * m);
-                    for (uint64_t j = 0; j < m; ++j) flag[j] |= c.read_flag[j];
+                    for (uint64_t j = 0; j < m; ++j) flag[j] = std::max(flag[j], c.read_flag[j]);
                 }
             };
             std::vector<std::vector<uint16_t>> tc, tcs, dc, dcs;
@@ -296,6 +297,7 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
                 int ti = -1, di = -1, tmp = -1;
                 bool classified = false;
                 if (deplete && target) {                        // classify_deplete_target, classify.hpp:58-111
+                    if (tflag[j] >= 2 || dflag[j] >= 2) { res.failed++; res.assignment[r] = -3; continue; }   // chunk > 65 535 bases
                     const uint64_t t0 = best_of(tc, j, ti), d0 = best_of(dc, j, di);
                     if (t0 > 0) {
                         if (d0 > 0) {

@@ -230,6 +230,20 @@ RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_ma
  * thousands of bytes per position; same policy, budget and env switches. */
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);
 
+/* The same for ALL filters a caller classifies against (the reference holds every target and depletion filter at
+ * once: classify.hpp:142, adaptive_sampling.hpp:555): one joint plan per device under total_bytes (0 = 85 % of the
+ * free HBM, counting what these handles' old tables held as free).  Every filter first gets its smallest table
+ * (span 1 / postings), then the filter with the narrowest span is widened while the sum fits; a filter whose table
+ * does not fit gets none and is marked so that no count call tries to build one later.  Call it once after loading /
+ * building the filters (rb_drivers.hpp and rb_live.hpp do): no classify call then stalls on a table build. */
+RB_API int rb_ibf_enable_kmer_tables(rb_ibf *const *filters, uint32_t n_filters, uint64_t total_bytes, rb_stream stream);
+
+/* Threshold table WITHOUT the range check of rb_threshold_lut: whatever the reference's FP64 arithmetic gives for this
+ * rate.  check_unblock / classify_deplete_target retry at error_rate - 0.02 without validating it
+ * (adaptive_sampling.hpp:55-59, classify.hpp:75-80); for rates <= 0 the interval bound is NaN, which the uint16 cast
+ * turns into 0 on x86-64, i.e. threshold = number of k-mers (every k-mer must match). */
+RB_API int rb_threshold_lut_raw(double error_rate, double significance, uint32_t kmer_size, uint16_t *lut65536);
+
 /* Kernel selection override for tests/benchmarks: 0 auto, 1 warp-per-read tile kernel,
  * 2 CTA-per-read streaming kernel, 3 direct k-mer table kernel (fails if not applicable; bit-sliced
  * register counters for rows <= 2 words), 4 k-mer table kernel with shared-memory counters,

@@ -169,6 +169,20 @@ struct IBFMeta {
     uint64_t classified = 0;
 };
 
+// One joint k-mer table plan for every filter a caller classifies against (rb_ibf_enable_kmer_tables): called once by
+// classify_reads and LiveClassifier before the first read, so that no classify call stalls on a multi-GB table build
+// and the first filter does not take the HBM the others need.
+inline void enable_kmer_tables(const std::vector<IBFMeta> &a, const std::vector<IBFMeta> &b = {}, uint64_t total_bytes = 0)
+{
+    std::vector<rb_ibf *> hs;
+    for (const std::vector<IBFMeta> *v : {&a, &b})
+        for (const IBFMeta &f : *v)
+            if (f.filter) hs.push_back(f.filter.get());
+    if (hs.empty()) return;
+    int st = rb_ibf_enable_kmer_tables(hs.data(), (uint32_t)hs.size(), total_bytes, nullptr);
+    if (st != RB_OK) throw_status(st, "enable_kmer_tables");
+}
+
 typedef std::pair<uint16_t, uint16_t> TInterval;
 
 // calculateCI (src/IBF/IBF.hpp:320-338)
@@ -342,16 +356,19 @@ private:
 };
 
 // ---- threshold tables, cached per (error_rate, significance, k) ---------------------------------------------------
-inline const std::vector<uint16_t> &threshold_lut(double error_rate, double significance, uint32_t k)
+// raw: no range check on the rate -- the retry of check_unblock / classify_deplete_target at error_rate - 0.02 is never
+// validated by the reference (adaptive_sampling.hpp:55-59), so a configured rate <= 0.02 must not make a batch throw
+inline const std::vector<uint16_t> &threshold_lut(double error_rate, double significance, uint32_t k, bool raw = false)
 {
     static std::mutex mu;
-    static std::map<std::tuple<double, double, uint32_t>, std::vector<uint16_t>> cache;
+    static std::map<std::tuple<double, double, uint32_t, bool>, std::vector<uint16_t>> cache;
     std::lock_guard<std::mutex> lock(mu);
-    auto key = std::make_tuple(error_rate, significance, k);
+    auto key = std::make_tuple(error_rate, significance, k, raw);
     auto it = cache.find(key);
     if (it == cache.end()) {
         std::vector<uint16_t> lut(65536);
-        int st = rb_threshold_lut(error_rate, significance, k, lut.data());
+        int st = raw ? rb_threshold_lut_raw(error_rate, significance, k, lut.data())
+                     : rb_threshold_lut(error_rate, significance, k, lut.data());
         if (st != RB_OK) throw_status(st, "threshold");
         it = cache.emplace(key, std::move(lut)).first;
     }
@@ -377,7 +394,7 @@ inline BatchCounts count_matches_batch(const TIbf &filter, const char *bases, co
     out.n_lut = with_retry_threshold ? 2 : 1;
     std::vector<uint16_t> luts(threshold_lut(config.error_rate, config.significance, filter.kmerSize));
     if (with_retry_threshold) {
-        const std::vector<uint16_t> &l2 = threshold_lut(config.error_rate - 0.02, config.significance, filter.kmerSize);
+        const std::vector<uint16_t> &l2 = threshold_lut(config.error_rate - 0.02, config.significance, filter.kmerSize, true);
         luts.insert(luts.end(), l2.begin(), l2.end());
     }
     out.max_count.resize(out.n_lut * n_reads);
@@ -480,7 +497,8 @@ inline uint8_t check_unblock(interleave::Read &read, interleave::ClassifyConfig 
 // Batch form of check_unblock: one GPU pass per filter evaluates both thresholds (error_rate and
 // error_rate - 0.02), then the decision table above is applied per read on the host.
 // Reads shorter than k follow the reference: the pair overload skips the filter (count 0); the single-list
-// overloads throw ShortReadException per read, reported here as decision 255.
+// overloads throw ShortReadException per read, reported here as decision 255.  Reads longer than 65 535 bases
+// (read_flag 2) are decision 255 in every mode.
 inline std::vector<uint8_t> check_unblock_batch(const char *bases, const uint64_t *read_off, uint64_t n_reads,
                                                 const interleave::ClassifyConfig &conf,
                                                 std::vector<interleave::IBFMeta> &DepletionFilters,
@@ -498,7 +516,7 @@ inline std::vector<uint8_t> check_unblock_batch(const char *bases, const uint64_
             for (uint64_t i = 0; i < n_reads; ++i) {
                 best[i] = std::max(best[i], c.max_count[i]);
                 if (both) best_strict[i] = std::max(best_strict[i], c.max_count[n_reads + i]);
-                flag[i] |= c.read_flag[i];
+                flag[i] = std::max(flag[i], c.read_flag[i]);
             }
         }
     };
@@ -509,6 +527,9 @@ inline std::vector<uint8_t> check_unblock_batch(const char *bases, const uint64_
     if (withTarget) best_of(TargetFilters, tgt, tgt_s, ft);
     for (uint64_t i = 0; i < n_reads; ++i) {
         if (both) {
+            // reads shorter than k are skipped per filter by the pair overload (count 0); a read the engine cannot
+            // classify at all (longer than 65 535 bases: the reference's uint16 readlen) is reported, not kept silently
+            if (fd[i] >= 2 || ft[i] >= 2) { out[i] = 255; continue; }
             if (dep[i] > 0) {
                 if (tgt[i] > 0) out[i] = (dep_s[i] > 0 && tgt_s[i] == 0) ? 1 : 0;
                 else out[i] = 1;

@@ -44,6 +44,7 @@ public:
         : dep_(std::move(depletion)), tgt_(std::move(target)), conf_(conf), give_up_(give_up_length)
     {
         if (dep_.empty() && tgt_.empty()) throw interleave::NullFilterException("No IBF provided to classify the read!");
+        interleave::enable_kmer_tables(dep_, tgt_);       // up front: a micro-batch must never wait for a table build
     }
 
     size_t pending() const { return once_seen_.size(); }

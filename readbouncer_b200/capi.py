@@ -31,6 +31,7 @@ EXPORTS = [
     "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
     "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins", "rb_host_pack_info", "rb_transfer_bytes",
     "rb_ibf_transfer_policy", "rb_ibf_count_traffic_dev", "rb_synth_bases_dev",
+    "rb_ibf_enable_kmer_tables", "rb_threshold_lut_raw",
 ]
 
 
@@ -115,6 +116,8 @@ def lib():
         "rb_ibf_transfer_policy": (i32, [vp, vp, vp, vp]),
         "rb_ibf_count_traffic_dev": (i32, [vp, vp, vp, u64, u32, vp, vp, vp, vp]),
         "rb_synth_bases_dev": (i32, [vp, u64, u64, u64, vp]),
+        "rb_ibf_enable_kmer_tables": (i32, [vp, u32, u64, vp]),
+        "rb_threshold_lut_raw": (i32, [dbl, dbl, u32, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -216,10 +219,18 @@ def calculate_ci(error_rate, kmer_size, readlen, significance=0.95):
     return lo.value, hi.value
 
 
-def threshold_lut(error_rate, kmer_size, significance=0.95):
+def threshold_lut(error_rate, kmer_size, significance=0.95, raw=False):
+    """uint16[65536] thresholds by read length; raw=True skips the (0, 1) range check (the reference's retry rate)."""
     out = np.zeros(LUT_SIZE, np.uint16)
-    _check(lib().rb_threshold_lut(error_rate, significance, kmer_size, _np_ptr(out)))
+    fn = lib().rb_threshold_lut_raw if raw else lib().rb_threshold_lut
+    _check(fn(error_rate, significance, kmer_size, _np_ptr(out)))
     return out
+
+
+def enable_kmer_tables(filters, total_bytes=0, stream=None):
+    """Joint k-mer table plan for all filters a caller classifies against (rb_ibf_enable_kmer_tables)."""
+    arr = (C.c_void_p * len(filters))(*[f._h for f in filters])
+    _check(lib().rb_ibf_enable_kmer_tables(arr, len(filters), int(total_bytes), _stream_ptr(stream)))
 
 
 def cut_out_nnns(seq):

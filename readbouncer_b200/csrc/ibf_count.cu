@@ -200,7 +200,9 @@ count_stream_kernel(const CountArgs a)
     const uint64_t stride = a.fv.stride;
     const uint64_t off = a.read_off[read];
     const uint64_t len = a.read_off[read + 1] - off;
-    const uint32_t flag = read_flag_of(len, k);
+    uint32_t flag = read_flag_of(len, k);
+    // a read longer than the caller's max_read_len promised does not fit this variant's NP-bit counters: flag 3, not classified
+    if (flag == 0 && NP < 16 && len - k + 1 > (1u << NP) - 1u) flag = 3;
     if (tid == 0 && blockIdx.y == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
 
     const uint64_t cb0 = (uint64_t)blockIdx.y * kStreamCB;

@@ -210,7 +210,9 @@ count_table_bs_kernel(const CountArgs a, const uint64_t *__restrict__ table)
     for (uint64_t read = (uint64_t)blockIdx.x * kTileWarps + warp; read < a.n_reads; read += total_warps) {
         const uint64_t off = a.read_off[read];
         const uint64_t len = a.read_off[read + 1] - off;
-        const uint32_t flag = read_flag_of(len, k);
+        uint32_t flag = read_flag_of(len, k);
+        // a read longer than the caller's max_read_len promised does not fit the NPA-bit accumulator: flag 3, not classified
+        if (flag == 0 && NPA < 16 && len - k + 1 > (1u << NPA) - 1u) flag = 3;
         if (lane == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
 
         uint32_t acc[NPA];

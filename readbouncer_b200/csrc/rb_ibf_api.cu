@@ -108,7 +108,8 @@ double normal_cdf_inverse(double p)
                    : rational_approx(std::sqrt(-2.0 * std::log(1.0 - p)));
 }
 
-uint16_t cast_u16(double x) { return (uint16_t)(int64_t)x; }
+// double -> uint16 as x86-64 does it for the reference (cvttsd2si, low 16 bits); NaN / out of range give 0 there
+uint16_t cast_u16(double x) { return (x >= -9.2e18 && x <= 9.2e18) ? (uint16_t)(int64_t)x : (uint16_t)0; }
 
 // calculateCI, src/IBF/IBF.hpp:320-338 (kmer_size arrives as uint8_t there)
 void calculate_ci(double r, uint32_t kmer_size, uint32_t readlen, double confidence, uint16_t *lo, uint16_t *hi)
@@ -179,7 +180,10 @@ int alloc_device(rb_ibf *f, bool zero)
     const size_t bytes = f->n_local_words * 8;
     if (prop.persistingL2CacheMaxSize > 0 && bytes <= (size_t)prop.persistingL2CacheMaxSize &&
         bytes <= (size_t)prop.accessPolicyMaxWindowSize) {
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) == cudaSuccess) f->l2_persist = true;
+        // device-wide limit shared by all filters of the device: only ever raised (the largest small filter decides)
+        size_t cur = 0;
+        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess) { cudaGetLastError(); cur = 0; }
+        if (cur >= bytes || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes) == cudaSuccess) f->l2_persist = true;
         else cudaGetLastError();
     }
     return RB_OK;
@@ -274,6 +278,22 @@ uint64_t table_bytes_needed(const rb_ibf *f, int span)
     uint64_t n_entries = 0;
     if (!rb::wtable_geometry(f->col_words, (uint32_t)f->k, span, &lanes, nullptr, &n_entries)) return 0;
     return n_entries * (uint64_t)lanes * 2 * f->col_words * 8;
+}
+
+// Expected size of the postings table of a wide filter (0: not applicable), from a sample of 65 536 k-mers.
+uint64_t postings_estimate_bytes(const rb_ibf *f, cudaStream_t st)
+{
+    const rb::FilterView fv = view_of(f);
+    if (!rb::postings_applicable(fv)) return 0;
+    const uint64_t n_kmers = 1ull << (2 * f->k);
+    const uint32_t n_sample = (uint32_t)std::min<uint64_t>(65536, n_kmers);
+    uint32_t *d_tmp = nullptr;
+    if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); return 0; }
+    double mean_units = 0;
+    const int r = rb::postings_sample_units(fv, d_tmp, n_sample, &mean_units, f->sm_count, st);
+    cudaFree(d_tmp);
+    if (r < 0) { cudaGetLastError(); return 0; }
+    return (uint64_t)(mean_units * (double)n_kmers * 16.0) + (n_kmers + 1) * 4;
 }
 
 // Builds the table on `st` if the policy allows it; returns the device pointer or null.
@@ -916,6 +936,12 @@ int rb_threshold_lut(double error_rate, double significance, uint32_t kmer_size,
     if (!lut65536) return fail(RB_ERR_INVALID_ARG, "null lut");
     if (!(error_rate > 0.0 && error_rate < 1.0) || !(significance > 0.0 && significance < 1.0))
         return fail(RB_ERR_INVALID_CONFIG, "error rate and significance must be in (0, 1)");
+    return rb_threshold_lut_raw(error_rate, significance, kmer_size, lut65536);
+}
+
+int rb_threshold_lut_raw(double error_rate, double significance, uint32_t kmer_size, uint16_t *lut65536)
+{
+    if (!lut65536) return fail(RB_ERR_INVALID_ARG, "null lut");
     for (uint32_t len = 0; len < 65536; ++len) {
         // src/IBF/IBFClassify.cpp:154-159: uint16 readlen, int16 threshold, used as uint16
         uint16_t hi = 0;
@@ -1190,6 +1216,71 @@ int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stre
     f->table_budget = max_table_bytes;
     if (!ensure_table(f, (cudaStream_t)stream, true))
         return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable (k > 16, more than 65520 bins for postings) or over the memory budget");
+    return RB_OK;
+}
+
+// Joint table plan for several filters (the reference classifies every read against ALL target and depletion filters:
+// classify.hpp:142, adaptive_sampling.hpp:555), so that the first filter does not take the HBM the others need.
+int rb_ibf_enable_kmer_tables(rb_ibf *const *filters, uint32_t n_filters, uint64_t total_bytes, rb_stream stream)
+{
+    if (!filters && n_filters) return fail(RB_ERR_INVALID_ARG, "null filter list");
+    for (uint32_t i = 0; i < n_filters; ++i)
+        if (!filters[i]) return fail(RB_ERR_NULL_FILTER, "null filter in the list");
+    std::vector<int> devices;
+    for (uint32_t i = 0; i < n_filters; ++i)
+        if (std::find(devices.begin(), devices.end(), filters[i]->device) == devices.end()) devices.push_back(filters[i]->device);
+    for (int dev : devices) {
+        DeviceGuard g(dev);
+        std::vector<rb_ibf *> fs;
+        for (uint32_t i = 0; i < n_filters; ++i)
+            if (filters[i]->device == dev && std::find(fs.begin(), fs.end(), filters[i]) == fs.end()) fs.push_back(filters[i]);
+        for (rb_ibf *f : fs) {                                    // their old tables and build scratch count as free
+            drop_table(f);
+            if (f->build_scratch.p) { cudaFree(f->build_scratch.p); f->build_scratch = rb::ScratchBuf{}; }
+        }
+        size_t free_b = 0, total_b = 0;
+        RB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t budget = total_bytes ? total_bytes : (uint64_t)(free_b * 0.85);
+        struct Opt { uint64_t bytes; int span; };
+        std::vector<std::vector<Opt>> opts(fs.size());
+        for (size_t i = 0; i < fs.size(); ++i) {
+            rb_ibf *f = fs[i];
+            if (f->col_words > 4) {
+                const uint64_t est = postings_estimate_bytes(f, (cudaStream_t)stream);
+                if (est) opts[i].push_back({est + est / 16, 1});  // the estimate comes from a sample: leave a margin
+            } else {
+                for (int sp = 1; sp <= (f->col_words <= 2 ? 4 : 1); ++sp) {
+                    const uint64_t b = table_bytes_needed(f, sp);
+                    if (b) opts[i].push_back({b, sp});
+                }
+            }
+        }
+        std::vector<int> chosen(fs.size(), -1);
+        uint64_t used = 0;
+        for (size_t i = 0; i < fs.size(); ++i)                    // everybody gets the smallest table first ...
+            if (!opts[i].empty() && used + opts[i][0].bytes <= budget) { chosen[i] = 0; used += opts[i][0].bytes; }
+        for (;;) {                                                // ... then the narrowest span is widened while it fits
+            int best = -1;
+            for (size_t i = 0; i < fs.size(); ++i) {
+                if (chosen[i] < 0 || chosen[i] + 1 >= (int)opts[i].size()) continue;
+                const uint64_t delta = opts[i][chosen[i] + 1].bytes - opts[i][chosen[i]].bytes;
+                if (used + delta > budget) continue;
+                if (best < 0 || opts[i][chosen[i]].span < opts[best][chosen[best]].span ||
+                    (opts[i][chosen[i]].span == opts[best][chosen[best]].span &&
+                     delta < opts[best][chosen[best] + 1].bytes - opts[best][chosen[best]].bytes))
+                    best = (int)i;
+            }
+            if (best < 0) break;
+            used += opts[best][chosen[best] + 1].bytes - opts[best][chosen[best]].bytes;
+            chosen[best] += 1;
+        }
+        for (size_t i = 0; i < fs.size(); ++i) {
+            rb_ibf *f = fs[i];
+            if (chosen[i] < 0) { f->table_tried = true; continue; }      // no table: hashed probes / streaming, never a lazy build
+            f->table_budget = opts[i][chosen[i]].bytes;
+            if (!ensure_table(f, (cudaStream_t)stream, true)) f->table_tried = true;
+        }
+    }
     return RB_OK;
 }
 
