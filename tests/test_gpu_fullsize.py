@@ -173,7 +173,7 @@ def test_many_host_threads_one_handle(shape):
         ref = [synth.random_bases(60_000, 40 + i) for i in range(100)]
         plan = synth.build_plan(ref, 61_000, 13)                          # 100 bins: window-table kernels
     else:
-        ref = [synth.random_bases(700_000, 70 + i) for i in range(3)]
+        ref = [synth.random_bases(700_500, 70 + i) for i in range(3)]
         plan = synth.build_plan(ref, 2_000, 13)                           # ~1 050 bins: postings kernel
     gf = rb.IBF.create(plan["n_bins"], 3, 13, plan["n_bits"])
     gf.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
