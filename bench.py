@@ -571,7 +571,7 @@ def run_workload(env, args, name, n_reads, steps, warmup, role):
     span = gf.kmer_table_span()
     kind = gf.kmer_table_kind()
     group_ok = span >= 2 and chunk - k + 1 <= 127 * span and chunk <= 545   # ibf_wtable.cu: wgroup_applicable
-    kernel_name = ("count_postings_kernel" if kind == 2 else "count_wgroup_kernel" if group_ok else "count_wtable_kernel" if span >= 2
+    kernel_name = ("count_slots_kernel" if kind == 3 else "count_postings_kernel" if kind == 2 else "count_wgroup_kernel" if group_ok else "count_wtable_kernel" if span >= 2
                    else "count_table_kernel" if span == 1 else
                    "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel")
     streamed = kernel_name == "count_stream_kernel"
@@ -614,7 +614,7 @@ def run_workload(env, args, name, n_reads, steps, warmup, role):
         return ev0.elapsed_time(ev1) / 2
 
     npos = chunk - k + 1
-    if kind == 2:
+    if kind in (2, 3):
         pass                # postings lists are streamed: the HBM-bandwidth roofline above applies
     elif span >= 2:     # window table: one request per entry of `lanes` slots, adjacent lanes
         lanes = 2 if span == 2 else 4

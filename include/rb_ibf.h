@@ -81,7 +81,8 @@ typedef struct rb_ibf_info_t {
     int32_t shard, n_shards;
     int32_t kmer_table_span;   /* consecutive k-mers per table entry (1..4), 0 if not built */
     uint64_t kmer_table_bytes; /* bytes of the k-mer table, 0 if not built */
-    int32_t kmer_table_kind;   /* 0 none, 1 dense k-mer / window table (rows <= 4 words), 2 postings (wider rows) */
+    int32_t kmer_table_kind;   /* 0 none, 1 dense k-mer / window table (rows <= 4 words), wider rows: 3 postings in fixed
+                                  slots per k-mer (default), 2 postings as pointer + lists (RB_POSTINGS_LAYOUT=lists) */
 } rb_ibf_info_t;
 
 /* ---- host-side scalar helpers (FP64, bit-exact with the reference) ------- */
@@ -224,10 +225,20 @@ RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_ma
  * cap, RB_KMER_TABLE_SPAN the widest span tried); dropped by rb_ibf_insert_batch*.  This call
  * (re)builds it now under the given byte budget (0 = automatic); UINT64_MAX disables the table for
  * this handle.
- * Wide filters (rows > 4 words, <= 65520 local bins, k <= 15) get a POSTINGS table instead: the AND of
+ * Wide filters (rows > 4 words, <= 65280 local bins, k <= 15) get a POSTINGS table instead: the AND of
  * the probed rows is ~1 % dense by the reference's own sizing, so the list of set bins of every
  * k-mer (2 bytes each, ~50 GB for a human-genome filter at k=13) replaces streaming 2*h rows of
- * thousands of bytes per position; same policy, budget and env switches. */
+ * thousands of bytes per position; same policy, budget and env switches.  Every k-mer owns a fixed,
+ * 128-byte-aligned slot (its size chosen from the sampled list lengths; the few longer lists go to an
+ * overflow area), which the lookup kernel fetches with one bulk copy into a shared-memory ring.
+ *
+ * SUPPORTED ENVELOPE of the table paths (outside it results are the same, from the hashed / streaming kernels):
+ *   rows <= 2 words (<= 128 bins): window tables for k + span - 1 <= 16, i.e. span 3 up to k = 14, span 2 up to k = 15,
+ *                                   span 1 up to k = 16; k >= 17: hashed probes (count_tile_kernel)
+ *   rows of 3-4 words:             span 1 up to k = 16
+ *   rows > 4 words:                postings up to k = 15 while 4^k slots fit the HBM budget (k = 13 for a human-sized
+ *                                   filter); else count_stream_kernel
+ * bench.py's `secondary` reports k = 13, 15 and 17 on the BASELINE config #2 shape so the steps are visible. */
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);
 
 /* The same for ALL filters a caller classifies against (the reference holds every target and depletion filter at

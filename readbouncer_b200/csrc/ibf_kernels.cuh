@@ -3,6 +3,8 @@
 
 #include "ibf_common.cuh"
 
+#include <vector>
+
 namespace rb {
 
 // View of one handle's slice of the bit matrix, as the kernels see it.
@@ -63,6 +65,16 @@ int postings_build_ptr(const FilterView &fv, uint32_t *d_ptr, uint64_t *total_un
 int postings_fill(const FilterView &fv, const uint32_t *d_ptr, uint16_t *d_ids, int sm_count, cudaStream_t st);
 int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint16_t *d_ids, uint32_t max_read_len, int sm_count,
                           cudaStream_t st);
+// the same lists as fixed, 128-byte-aligned slots per k-mer, fetched by bulk copies into shared-memory rings (ibf_postings.cu)
+bool slots_applicable(const FilterView &fv);
+int slots_sample_lengths(const FilterView &fv, uint32_t *d_scratch, uint32_t n_sample, std::vector<uint32_t> *lengths, int sm_count,
+                         cudaStream_t st);
+bool slots_choose(const std::vector<uint32_t> &lengths, uint32_t k, uint64_t budget, uint32_t *slot_bytes, uint64_t *ovf_units,
+                  uint64_t *total_bytes);
+int slots_fill(const FilterView &fv, uint8_t *d_slots, uint32_t slot_bytes, uint16_t *d_ovf, uint64_t ovf_units, unsigned int *d_ctr,
+               int sm_count, cudaStream_t st);
+int launch_count_slots(const CountArgs &a, const uint8_t *d_slots, uint32_t slot_bytes, const uint16_t *d_ovf, uint32_t max_read_len,
+                       int sm_count, unsigned int *d_err, cudaStream_t st);
 bool wgroup_applicable(uint32_t k, int span, uint32_t max_read_len);
 int get_wtable_variant();
 void set_wtable_variant(int v);   // 0 auto (group-per-read kernel for short reads), 1 always warp-per-read

@@ -52,8 +52,9 @@ __device__ __forceinline__ void kmer_hashes(uint64_t x, uint32_t k, uint64_t &Hf
 // build: pass 1 counts, pass 2 fills; one warp per k-mer, lanes stride over the row words
 // ------------------------------------------------------------------------------------------
 // x = first + i * step for i < n (step > 1: a sample to estimate the table size)
+// raw: write the number of ids instead of the number of 8-id units
 __global__ void __launch_bounds__(256) postings_count_kernel(const FilterView fv, uint64_t first, uint64_t step, uint64_t n,
-                                                             uint32_t *__restrict__ units)
+                                                             uint32_t *__restrict__ units, const int raw = 0)
 {
     const HashParams &hp = fv.hp;
     const int lane = threadIdx.x & 31;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) postings_count_kernel(const FilterView fv
             c += (uint32_t)__popcll(m);
         }
         c = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0) units[i] = (c + 7u) >> 3;
+        if (lane == 0) units[i] = raw ? c : (c + 7u) >> 3;
     }
 }
 
@@ -442,6 +443,383 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
     }
 }
 
+// ==========================================================================================================
+// SLOT layout: every k-mer owns a fixed, 128-byte-aligned slot of slot_bytes (ibf_postings_layout.cuh)
+// ==========================================================================================================
+// Why: the list layout above costs a dependent pointer fetch (a whole 128-byte line for 8 useful bytes) before every list
+// and lists start at random 16-byte offsets (a 720-byte list touches 6.5 lines): ncu measured 469 KB per chunk for 343 KB
+// of ids, and 27 % of the warps' time waiting for list data with the register file capping the lists in flight
+// (profiles/r1_m_postings_cfg3_ncu_full.json).  With a slot per k-mer the address is a multiplication, a list is ONE
+// aligned bulk copy (cp.async.bulk global -> shared, completion on an mbarrier), and the lists in flight live in a
+// shared-memory ring per warp instead of registers.  Lists longer than a slot go to an overflow area (the slot then
+// holds its offset); the slot size is chosen from the sampled list-length distribution so that this is rare.
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// one bulk copy global -> shared (async proxy); bytes is a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Waits for the phase with the given parity; gives up after ~1 s of polling (a copy that never lands is a bug, not a
+// reason to hang the device) and reports through *err.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, unsigned int *err)
+{
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+        if (!ok && spin > (1u << 22)) { if (err) atomicExch(err, 1u); return false; }
+    }
+    return true;
+}
+
+// ---- build ------------------------------------------------------------------------------------------------
+struct SlotTable {
+    uint8_t *slots;            // [4^k][slot_bytes]
+    uint16_t *ovf;             // overflow lists, 16-byte units of 8 ids, ascending, padded with the plain sentinel
+    uint32_t slot_bytes;
+    uint32_t ovf_cap_units;
+    unsigned int *ovf_used;    // units handed out (device counter)
+    unsigned int *err;         // set when the overflow area is exhausted
+};
+
+__global__ void __launch_bounds__(256) slots_fill_kernel(const FilterView fv, const uint64_t n_kmers, const SlotTable tb, const int deal)
+{
+    __shared__ uint16_t s_stage[8][kFillStage];
+    __shared__ uint32_t s_off[8][32];
+    const HashParams &hp = fv.hp;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t sentinel = postings_sentinel(fv.n_bins_local);
+    const uint32_t cap = slot_capacity(tb.slot_bytes);
+    uint16_t *const stage = s_stage[wib];
+    uint32_t *const off = s_off[wib];
+    for (uint64_t x = warp0; x < n_kmers; x += n_warps) {
+        uint64_t Hf, Hr;
+        kmer_hashes(x, hp.k, Hf, Hr);
+        const uint64_t *rows[kMaxHash];
+#pragma unroll
+        for (int h = 0; h < kMaxHash; ++h)
+            rows[h] = (uint32_t)h < hp.n_hash ? fv.words + hash_row(Hf, hp.pre[h], hp.n_blocks, hp.magic) * fv.stride : nullptr;
+        // ascending ids into the stage (as many as it holds), n = all of them
+        auto scan = [&](uint16_t *dst, uint64_t dst_cap) -> uint32_t {
+            uint64_t run = 0;
+            for (uint64_t w0 = 0; w0 < fv.stride; w0 += 32) {
+                const uint64_t w = w0 + lane;
+                uint64_t m = 0;
+                if (w < fv.stride) {
+                    m = ~0ULL;
+#pragma unroll
+                    for (int h = 0; h < kMaxHash; ++h)
+                        if ((uint32_t)h < hp.n_hash) m &= __ldg(rows[h] + w);
+                }
+                const uint32_t c = (uint32_t)__popcll(m);
+                uint32_t incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                uint64_t pos = run + incl - c;
+                while (m) {
+                    const int b = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    if (pos < dst_cap) dst[pos] = (uint16_t)(w * 64 + b);
+                    ++pos;
+                }
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            return (uint32_t)run;
+        };
+        const uint32_t n = scan(stage, kFillStage);
+        __syncwarp();
+        uint8_t *const slot = tb.slots + x * tb.slot_bytes;
+        uint16_t *const out = reinterpret_cast<uint16_t *>(slot + kSlotHeaderBytes);
+        if (n > cap) {
+            // ---- overflow: the whole list, ascending, in units of 8 ids ---------------------------------------
+            const uint32_t units = (n + 7u) >> 3;
+            uint32_t u0 = 0;
+            if (lane == 0) u0 = atomicAdd(tb.ovf_used, units);
+            u0 = __shfl_sync(0xffffffffu, u0, 0);
+            const bool fits = (uint64_t)u0 + units <= tb.ovf_cap_units;
+            if (lane == 0) {
+                if (!fits) atomicExch(tb.err, 1u);
+                reinterpret_cast<uint32_t *>(slot)[0] = fits ? kSlotOverflow : 0u;   // not fits: an empty list (the build is void anyway)
+                reinterpret_cast<uint32_t *>(slot)[1] = u0;
+                reinterpret_cast<uint32_t *>(slot)[2] = units;
+            }
+            if (fits) {
+                uint16_t *const dst = tb.ovf + (uint64_t)u0 * 8;
+                if (n <= (uint32_t)kFillStage) for (uint32_t i = lane; i < n; i += 32) dst[i] = stage[i];
+                else scan(dst, n);
+                for (uint32_t i = n + lane; i < 8u * units; i += 32) dst[i] = (uint16_t)sentinel;
+            }
+            __syncwarp();
+            continue;
+        }
+        if (lane == 0) { reinterpret_cast<uint32_t *>(slot)[0] = n; reinterpret_cast<uint32_t *>(slot)[1] = 0u; }
+        // pads up to the end of the last round the lookup walks (never past the slot)
+        const uint32_t lim = min(cap, (n + 127u) & ~127u);
+        for (uint32_t p = n + lane; p < lim; p += 32) out[p] = (uint16_t)slot_pad_id(sentinel, p);
+        if (!deal) {
+            for (uint32_t i = lane; i < n; i += 32) out[i] = stage[i];
+            __syncwarp();
+            continue;
+        }
+        // ---- deal the ascending ids over the groups of the slot, bank by bank ------------------------------------
+        off[lane] = 0;
+        __syncwarp();
+        for (uint32_t i = lane; i < n; i += 32) atomicAdd(&off[counter_bank(stage[i])], 1u);
+        __syncwarp();
+        {
+            const uint32_t load = off[lane];
+            uint32_t incl = load;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            __syncwarp();
+            off[lane] = incl - load;
+        }
+        __syncwarp();
+        const SlotShape shape = slot_shape(n);
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            const bool valid = i < n;
+            const uint32_t id = valid ? stage[i] : 0u;
+            const uint32_t b = counter_bank(id);
+            const uint32_t same = __match_any_sync(0xffffffffu, valid ? b : 32u + lane);
+            const uint32_t before = __popc(same & ((1u << lane) - 1u));
+            const uint32_t c = valid ? off[b] + before : 0u;
+            __syncwarp();
+            if (valid && before == 0) off[b] += __popc(same);
+            __syncwarp();
+            if (valid) out[slot_position(shape, c)] = (uint16_t)id;
+        }
+        __syncwarp();
+    }
+}
+
+// ---- lookup -------------------------------------------------------------------------------------------------
+template <int CB>
+__device__ __forceinline__ void bump_checked(uint32_t *cnt, const uint32_t v, const uint32_t sentinel)
+{
+    if ((v & 0xFFFFu) != sentinel) bump<CB>(cnt, v);
+}
+
+// CB: counter bits.  THREADS per CTA: 256, 384 or 768 by how many CTAs of counters + rings fit an SM.
+// Dynamic shared memory: [2 * cnt_words counters][kPostPiece packed k-mers][digits][pad to 128][warps * ring slots][warps * ring mbarriers]
+template <int CB, int THREADS>
+__global__ void __launch_bounds__(THREADS, 768 / THREADS)
+count_slots_kernel(const CountArgs a, const uint8_t *__restrict__ slots, const uint32_t slot_bytes, const uint4 *__restrict__ ovf,
+                   const uint32_t cnt_words, const uint32_t ring, const uint32_t ring_off, unsigned int *err)
+{
+    constexpr int PER = 32 / CB;
+    constexpr uint32_t CMASK = (CB == 8) ? 0xFFu : 0xFFFFu;
+    constexpr int kWarps = THREADS / 32;
+    extern __shared__ __align__(128) uint32_t s_slot_mem[];
+    uint32_t *const s_mem = s_slot_mem;
+    uint32_t *const cntF = s_mem, *const cntR = s_mem + cnt_words;
+    uint32_t *const s_x = s_mem + 2 * cnt_words;
+    uint8_t *const s_dig = reinterpret_cast<uint8_t *>(s_x + kPostPiece);
+    __shared__ uint32_t s_red[kWarps];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *const my_ring = reinterpret_cast<uint8_t *>(s_mem) + ring_off + (size_t)warp * ring * slot_bytes;
+    uint64_t *const my_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_mem) + ring_off + (size_t)kWarps * ring * slot_bytes) + warp * ring;
+    const uint32_t k = a.fv.hp.k;
+    const uint32_t kbits = 2 * k;
+    const uint32_t kmask = kbits >= 32 ? ~0u : ((1u << kbits) - 1u);
+    const uint64_t nbl = a.fv.n_bins_local;
+    const uint32_t sentinel = postings_sentinel(nbl);
+    const uint32_t cap = slot_capacity(slot_bytes);
+
+    for (uint32_t w = tid; w < 2 * cnt_words; w += THREADS) s_mem[w] = 0;
+    if (lane == 0)
+        for (uint32_t j = 0; j < ring; ++j) mbar_init(my_bar + j, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t phase_bits = 0;                                               // expected parity of each of this warp's slots
+
+    bool dead = false;                                                     // a copy never landed: stop waiting, wind down
+
+    for (uint64_t read = blockIdx.x; read < a.n_reads; read += gridDim.x) {
+        if (*reinterpret_cast<volatile unsigned int *>(err)) break;        // some warp of the grid gave up (reported by the host call)
+        const uint64_t off = a.read_off[read];
+        const uint64_t len = a.read_off[read + 1] - off;
+        uint32_t flag = read_flag_of(len, k);
+        if (flag == 0 && CB == 8 && len - k + 1 > 255) flag = 3;         // longer than the caller's max_read_len promised
+        if (tid == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
+        __syncthreads();                                                   // counters are zero and visible
+
+        if (flag == 0) {
+            const uint32_t npos = (uint32_t)len - k + 1;
+            for (uint32_t cs = 0; cs < npos; cs += kPostPiece) {
+                const uint32_t cn = min((uint32_t)kPostPiece, npos - cs);
+                __syncthreads();
+                for (uint32_t i = tid; i < cn + k - 1; i += THREADS) s_dig[i] = (uint8_t)dna5(a.bases[off + cs + i]);
+                __syncthreads();
+                for (uint32_t j = tid; j < cn; j += THREADS) {
+                    uint32_t x = 0, bad = 0;
+                    for (uint32_t u = 0; u < k; ++u) {
+                        const uint32_t d = s_dig[j + u];
+                        x = (x << 2) | (d & 3u);
+                        bad |= d >> 2;
+                    }
+                    s_x[j] = bad ? ~0u : (x & kmask);
+                }
+                __syncthreads();
+                // every warp takes an equal, contiguous share of the (position, strand) pairs -- pair q = position q >> 1,
+                // strand q & 1 -- and keeps `ring` slots in flight: the copy of pair q + ring is issued when pair q is counted
+                const uint32_t n_pairs = 2 * cn;
+                const uint32_t share = 2u * ((cn + kWarps - 1) / kWarps);
+                const uint32_t q_begin = min(n_pairs, warp * share), q_end = min(n_pairs, q_begin + share);
+                auto issue = [&](const uint32_t q, const uint32_t slot) {
+                    const uint32_t x = s_x[q >> 1];
+                    if (x == ~0u) return;                                  // hashed pair: no copy, its slot stays idle
+                    uint32_t idx = x;
+                    if (q & 1u) {                                          // reverse strand: the slot of revcomp(x)
+                        uint32_t v = __brev(~x);
+                        v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+                        idx = v >> (32 - kbits);
+                    }
+                    if (lane == 0) {
+                        mbar_expect_tx(my_bar + slot, slot_bytes);
+                        bulk_g2s(my_ring + (size_t)slot * slot_bytes, slots + (uint64_t)idx * slot_bytes, slot_bytes, my_bar + slot);
+                    }
+                };
+                for (uint32_t j = 0; j < ring && q_begin + j < q_end; ++j) issue(q_begin + j, j);
+                uint32_t slot = 0;
+                for (uint32_t q = q_begin; q < q_end; ++q) {
+                    uint32_t *const cnt = (q & 1u) ? cntR : cntF;
+                    if (s_x[q >> 1] == ~0u) {
+                        add_hashed<CB>(a.fv, s_dig + (q >> 1), q & 1u, cnt, lane);
+                    } else if (!dead && !__all_sync(0xffffffffu, mbar_wait(my_bar + slot, (phase_bits >> slot) & 1u, err))) {
+                        dead = true;                                       // warp-uniform: nobody waits or counts any more
+                    } else if (!dead) {
+                        phase_bits ^= 1u << slot;
+                        const uint8_t *const sp = my_ring + (size_t)slot * slot_bytes;
+                        const uint2 hdr = *reinterpret_cast<const uint2 *>(sp);
+                        const uint32_t n = hdr.x & 0xFFFFu;
+                        if (n != kSlotOverflow) {
+                            const uint32_t lim = min(cap, (n + 127u) & ~127u);
+                            const uint8_t *const ip = sp + kSlotHeaderBytes + 8u * lane;
+#pragma unroll 4
+                            for (uint32_t p0 = 0; p0 < lim; p0 += 128u) {
+                                if (p0 + 4u * lane < lim) {
+                                    const uint2 v = *reinterpret_cast<const uint2 *>(ip + 2u * p0);
+                                    bump_pair<CB>(cnt, v.x);
+                                    bump_pair<CB>(cnt, v.y);
+                                }
+                            }
+                        } else {                                           // rare: the list lives in the overflow area
+                            const uint32_t units = *reinterpret_cast<const uint32_t *>(sp + 8);
+                            for (uint32_t u = lane; u < units; u += 32) {
+                                const uint4 v = __ldg(ovf + hdr.y + u);
+                                bump_checked<CB>(cnt, v.x, sentinel); bump_checked<CB>(cnt, v.x >> 16, sentinel);
+                                bump_checked<CB>(cnt, v.y, sentinel); bump_checked<CB>(cnt, v.y >> 16, sentinel);
+                                bump_checked<CB>(cnt, v.z, sentinel); bump_checked<CB>(cnt, v.z >> 16, sentinel);
+                                bump_checked<CB>(cnt, v.w, sentinel); bump_checked<CB>(cnt, v.w >> 16, sentinel);
+                            }
+                        }
+                    }
+                    // the slot's ids are in registers / counted: its next copy may land (all lanes are past their loads)
+                    __syncwarp();
+                    if (q + ring < q_end) issue(q + ring, slot);
+                    if (++slot == ring) slot = 0;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- epilogue: M = max over bins of max(fwd, rev), its lowest bin; counters back to zero ----------------
+        // The pads' counters (32 words for 8-bit, 64 for 16-bit counters) lie behind the quads of words that hold bins: they
+        // are not scanned, only cleared.
+        const uint32_t sent_word = sentinel / PER;
+        const uint32_t scan_quads = ((uint32_t)nbl + 4u * PER - 1u) / (4u * PER);
+        for (uint32_t w = tid; w < 128u / PER; w += THREADS) { cntF[sent_word + w] = 0; cntR[sent_word + w] = 0; }
+        if (a.counts_fwd || a.counts_rev) {                                 // dense counts on request (tests, tools)
+            for (uint32_t w = tid; w * PER < nbl; w += THREADS) {
+                const uint32_t f = cntF[w], r = cntR[w];
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const uint32_t bin = w * PER + i;
+                    if (bin < nbl) {
+                        if (a.counts_fwd) a.counts_fwd[read * nbl + bin] = (uint16_t)((f >> (i * CB)) & CMASK);
+                        if (a.counts_rev) a.counts_rev[read * nbl + bin] = (uint16_t)((r >> (i * CB)) & CMASK);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        constexpr uint32_t LOW = CB == 8 ? 0x7F7F7F7Fu : 0x7FFF7FFFu, ONES = CB == 8 ? 0x01010101u : 0x00010001u;
+        constexpr uint32_t HALF = (CMASK + 1u) / 2u;
+        uint32_t thr_min = CMASK + 1u;
+        if (flag == 0)
+            for (uint32_t t = 0; t < a.n_lut; ++t) thr_min = min(thr_min, (uint32_t)__ldg(a.lut + (size_t)t * kLutSize + len));
+        uint32_t cur = min(thr_min, CMASK + 1u) - (thr_min ? 1u : 0u), cur_bin = 0;
+        uint32_t add = (HALF - 1u - min(cur, HALF - 1u)) * ONES;
+        uint4 *const qF = reinterpret_cast<uint4 *>(cntF), *const qR = reinterpret_cast<uint4 *>(cntR);
+        for (uint32_t qd = tid; qd < scan_quads; qd += THREADS) {
+            const uint4 f = qF[qd], r = qR[qd];
+            qF[qd] = make_uint4(0, 0, 0, 0); qR[qd] = make_uint4(0, 0, 0, 0);
+            const uint32_t gx = f.x | r.x, gy = f.y | r.y, gz = f.z | r.z, gw = f.w | r.w;
+            const uint32_t h = (((gx & LOW) + add) | gx) | (((gy & LOW) + add) | gy) | (((gz & LOW) + add) | gz) | (((gw & LOW) + add) | gw);
+            if (h & ~LOW) {
+                const uint32_t m[4] = {vmax<CB>(f.x, r.x), vmax<CB>(f.y, r.y), vmax<CB>(f.z, r.z), vmax<CB>(f.w, r.w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) {
+                        const uint32_t v = (m[j] >> (i * CB)) & CMASK;
+                        if (v > cur) { cur = v; cur_bin = (4u * qd + j) * PER + i; }
+                    }
+                add = (HALF - 1u - min(cur, HALF - 1u)) * ONES;
+            }
+        }
+        uint32_t best_key = __reduce_max_sync(0xffffffffu, (cur << 16) | (0xFFFFu - cur_bin));
+        if (lane == 0) s_red[warp] = best_key;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kWarps; ++i) best_key = max(best_key, s_red[i]);
+        const uint32_t M = best_key >> 16, best_bin = 0xFFFFu - (best_key & 0xFFFFu);
+        if (tid < (int)a.n_lut) {
+            uint64_t key = 0;
+            if (flag == 0) {
+                const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)tid * kLutSize + len);
+                if (M >= thr) key = pack_key(M, (uint32_t)(a.fv.bin_begin + best_bin));
+            }
+            a.keys[(size_t)tid * a.n_reads + read] = key;
+        }
+    }
+}
+
+// counters: whole quads of bins + the 128 pad ids' words (+ slack to a quad)
+size_t slots_counter_words(uint64_t n_bins_local, int counter_bits)
+{
+    const uint32_t per = 32 / counter_bits;
+    return (size_t)postings_sentinel(n_bins_local) / per + 128u / per + 4;
+}
+
 size_t postings_smem_bytes(uint64_t n_bins_local, int counter_bits, uint32_t *cnt_words)
 {
     const uint32_t per = 32 / counter_bits;
@@ -501,6 +879,123 @@ int postings_fill(const FilterView &fv, const uint32_t *d_ptr, uint16_t *d_ids, 
     int deal = 1;                                               // RB_POSTINGS_ORDER=0: ascending ids (A/B measurements)
     if (const char *e = std::getenv("RB_POSTINGS_ORDER")) deal = e[0] != '0';
     postings_fill_kernel<<<sm_count * 16, 256, 0, st>>>(fv, 1ull << (2 * fv.hp.k), d_ptr, d_ids, deal);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ---- slot table: host side ------------------------------------------------------------------------------------
+bool slots_applicable(const FilterView &fv)
+{
+    return fv.stride > 4 && fv.hp.k <= 15 && fv.n_bins_local <= 65280 && fv.hp.n_blocks > 0 &&
+           slots_counter_words(fv.n_bins_local, 8) * 8 + kPostPiece * 5 + 160 + 768 * 128 / 32 <= 200u * 1024u;
+}
+
+// List lengths (ids) of n_sample k-mers spread over all 4^k; d_scratch: n_sample uint32.  Synchronises the stream.
+int slots_sample_lengths(const FilterView &fv, uint32_t *d_scratch, uint32_t n_sample, std::vector<uint32_t> *lengths, int sm_count,
+                         cudaStream_t st)
+{
+    const uint64_t n_kmers = 1ull << (2 * fv.hp.k);
+    // an odd step visits k-mers of every suffix (a power-of-two stride would fix the low bases of all samples)
+    uint64_t step = n_kmers / n_sample ? n_kmers / n_sample : 1;
+    if (step > 2) step |= 1;
+    postings_count_kernel<<<sm_count * 8, 256, 0, st>>>(fv, step / 2, step, n_sample, d_scratch, 1);
+    lengths->resize(n_sample);
+    if (cudaMemcpyAsync(lengths->data(), d_scratch, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    return 1;
+}
+
+// Slot size that minimises the expected bytes fetched per list -- slot + P(overflow) x (overflow lines + 1) -- among those whose
+// table fits the budget; also the overflow area to reserve.  Returns false if nothing fits.
+bool slots_choose(const std::vector<uint32_t> &lengths, uint32_t k, uint64_t budget, uint32_t *slot_bytes, uint64_t *ovf_units,
+                  uint64_t *total_bytes)
+{
+    const double n_kmers = (double)(1ull << (2 * k));
+    double best_cost = 0;
+    bool found = false;
+    for (uint32_t sb = 128; sb <= kSlotMaxBytes; sb += 128) {
+        const uint32_t cap = slot_capacity(sb);
+        double over = 0, over_units = 0, over_lines = 0;
+        for (uint32_t n : lengths)
+            if (n > cap) { over += 1; over_units += (n + 7) / 8; over_lines += ((n + 7) / 8 * 16 + 127) / 128 + 1; }
+        const double p = over / (double)lengths.size();
+        const double cost = sb + 128.0 * over_lines / (double)lengths.size();
+        // reserve twice the sampled overflow (+ 1 M units): the sample is 65 536 k-mers
+        const uint64_t units = (uint64_t)(2.0 * over_units / (double)lengths.size() * n_kmers) + (1u << 20);
+        const uint64_t bytes = (uint64_t)(n_kmers * sb) + units * 16;
+        if (bytes > budget || units > 0xFFFFFFF0ull) continue;
+        (void)p;
+        if (!found || cost < best_cost) { found = true; best_cost = cost; *slot_bytes = sb; *ovf_units = units; *total_bytes = bytes; }
+    }
+    return found;
+}
+
+// Fills the table; returns launches (1) or -1 (CUDA error) / -3 (overflow area exhausted: reserve more and retry).
+int slots_fill(const FilterView &fv, uint8_t *d_slots, uint32_t slot_bytes, uint16_t *d_ovf, uint64_t ovf_units, unsigned int *d_ctr,
+               int sm_count, cudaStream_t st)
+{
+    int deal = 1;
+    if (const char *e = std::getenv("RB_POSTINGS_ORDER")) deal = e[0] != '0';
+    if (cudaMemsetAsync(d_ctr, 0, 2 * sizeof(unsigned int), st) != cudaSuccess) return -1;
+    SlotTable tb{};
+    tb.slots = d_slots; tb.ovf = d_ovf; tb.slot_bytes = slot_bytes; tb.ovf_cap_units = (uint32_t)ovf_units;
+    tb.ovf_used = d_ctr; tb.err = d_ctr + 1;
+    slots_fill_kernel<<<sm_count * 16, 256, 0, st>>>(fv, 1ull << (2 * fv.hp.k), tb, deal);
+    unsigned int h[2] = {0, 0};
+    if (cudaMemcpyAsync(h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return h[1] ? -3 : 1;
+}
+
+// returns launches, -1 on error, -2 if this launch's reads need more shared memory than an SM has
+int launch_count_slots(const CountArgs &a, const uint8_t *d_slots, uint32_t slot_bytes, const uint16_t *d_ovf, uint32_t max_read_len,
+                       int sm_count, unsigned int *d_err, cudaStream_t st)
+{
+    if (a.n_reads == 0) return 0;
+    if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut) return -1;
+    const uint32_t k = a.fv.hp.k;
+    const bool narrow = max_read_len != 0 && (max_read_len < k || max_read_len - k + 1 <= 255);
+    const uint32_t cnt_words = (uint32_t)slots_counter_words(a.fv.n_bins_local, narrow ? 8 : 16);
+    const size_t fixed = ((size_t)2 * cnt_words * 4 + kPostPiece * 4 + kPostPiece + 32 + 127) / 128 * 128;
+    // CTAs per SM x threads: 3 x 256, 2 x 384 or 1 x 768 (always 24 warps per SM); take the shape that keeps the most
+    // bytes in flight per SM (ring slots x 24 warps, at most 8 slots per warp), preferring more CTAs on a tie
+    int ring_env = 0;
+    if (const char *e = std::getenv("RB_SLOT_RING")) ring_env = std::atoi(e);
+    int ctas_env = 0;
+    if (const char *e = std::getenv("RB_SLOT_CTAS")) ctas_env = std::atoi(e);
+    int best_ctas = 0, best_ring = 0;
+    for (int ctas = 3; ctas >= 1; --ctas) {
+        if (ctas_env && ctas != ctas_env) continue;
+        const int warps = 24 / ctas;
+        const size_t avail = (227u * 1024u) / ctas - 1024u;
+        if (fixed + (size_t)warps * (slot_bytes + 8) > avail) continue;
+        int ring = (int)std::min<size_t>(8, (avail - fixed) / ((size_t)warps * (slot_bytes + 8)));
+        if (ring_env > 0) ring = std::min(ring, ring_env);
+        if (ring > best_ring || (ring == best_ring && best_ctas == 0)) { best_ring = ring; best_ctas = ctas; }
+        if (ring >= 4) break;                                     // four slots of a warp in flight cover the latency
+    }
+    if (!best_ctas) return -2;
+    const int warps = 24 / best_ctas;
+    const size_t smem = fixed + (size_t)warps * best_ring * (slot_bytes + 8);
+    const uint4 *ovf = reinterpret_cast<const uint4 *>(d_ovf);
+    auto launch = [&](auto kernel, int threads) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+        if (occ < 1) occ = 1;
+        const uint64_t capb = (uint64_t)sm_count * occ;
+        const uint32_t gx = (uint32_t)(a.n_reads < capb ? a.n_reads : capb);
+        kernel<<<gx, threads, smem, st>>>(a, d_slots, slot_bytes, ovf, cnt_words, (uint32_t)best_ring, (uint32_t)fixed, d_err);
+    };
+    if (narrow) {
+        if (best_ctas == 3) launch(count_slots_kernel<8, 256>, 256);
+        else if (best_ctas == 2) launch(count_slots_kernel<8, 384>, 384);
+        else launch(count_slots_kernel<8, 768>, 768);
+    } else {
+        if (best_ctas == 3) launch(count_slots_kernel<16, 256>, 256);
+        else if (best_ctas == 2) launch(count_slots_kernel<16, 384>, 384);
+        else launch(count_slots_kernel<16, 768>, 768);
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

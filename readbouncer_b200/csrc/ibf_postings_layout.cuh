@@ -62,4 +62,51 @@ RB_HD uint32_t list_position(const ListShape &s, uint32_t c)
 
 RB_HD uint32_t counter_bank(uint32_t id) { return (id >> 2) & 31u; }
 
+// ---- slot layout (count_slots_kernel): every k-mer owns a fixed, 128-byte-aligned slot ------------------------------
+// A slot is fetched whole by ONE bulk copy into shared memory, then walked by the warp in rounds: in round r lane l
+// takes the four ids at positions 128 r + 4 l + e (one LDS.64), so one ATOMS instruction serves group (r, e) = the
+// positions {128 r + 4 l + e : l < 32}.  The n real ids occupy positions [0, n); as above the build deals them, sorted
+// by bank, round-robin over the groups, level by level (level t = lane t of every group that has one).
+struct SlotShape {
+    uint32_t n_big;      // groups of the full rounds (4 per round), 32 positions each
+    uint32_t n_all;      // + the 4 groups of the last, partial round
+    uint32_t q;          // every tail group has at least q positions
+    uint32_t n_a;        // ids dealt over all groups (levels < q)
+    uint32_t n_b;        // ids of level q: the full rounds' groups + the (n mod 4) tail groups that have one more
+    uint32_t tail0;      // first position of the partial round
+};
+
+RB_HD SlotShape slot_shape(uint32_t n)
+{
+    SlotShape s;
+    const uint32_t R = n >> 7, m = n & 127u;
+    s.n_big = 4u * R;
+    s.n_all = s.n_big + 4u;
+    s.tail0 = 128u * R;
+    s.q = m >> 2;
+    s.n_a = s.q * s.n_all;
+    s.n_b = s.n_big + (m & 3u);
+    return s;
+}
+
+// position of the c-th id in dealing order, c < n
+RB_HD uint32_t slot_position(const SlotShape &s, uint32_t c)
+{
+    uint32_t t, g;
+    if (c < s.n_a) { t = c / s.n_all; g = c % s.n_all; }
+    else if (c < s.n_a + s.n_b) { t = s.q; g = c - s.n_a; }
+    else { const uint32_t c2 = c - s.n_a - s.n_b; t = s.q + 1u + c2 / s.n_big; g = c2 % s.n_big; }
+    return g < s.n_big ? (g >> 2) * 128u + 4u * t + (g & 3u) : s.tail0 + 4u * t + (g - s.n_big);
+}
+
+// Padding id for the positions [n, end of the last round): lane l's pads live in their own counter word behind the bins
+// (32 words, one per bank), so a group of pads costs one conflict-free ATOMS instead of a 32-way collision.
+RB_HD uint32_t slot_pad_id(uint32_t sentinel, uint32_t pos) { return sentinel + 4u * ((pos >> 2) & 31u); }
+
+constexpr uint32_t kSlotHeaderBytes = 8;      // u16 n (kSlotOverflow: the list lives in the overflow area), u16 0, u32 first overflow unit;
+                                              // overflow slots: bytes 8..11 = u32 number of 16-byte units
+constexpr uint32_t kSlotOverflow = 0xFFFFu;
+constexpr uint32_t kSlotMaxBytes = 4096;
+RB_HD uint32_t slot_capacity(uint32_t slot_bytes) { return (slot_bytes - kSlotHeaderBytes) / 2u; }
+
 }  // namespace rb

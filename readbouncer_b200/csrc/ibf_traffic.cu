@@ -14,12 +14,10 @@ struct TrafficArgs {
     const uint64_t *read_off;
     uint64_t n_reads;
     uint32_t k, n_hash;
-    int kind;                  // 0 hashed row probes, 1 dense k-mer / window table, 2 postings (ptr + lists), 3 postings slots
+    int kind;                  // 0 hashed row probes, 1 dense k-mer / window table, 2 postings (ptr + lists), 3 postings in slots
     int span;                  // positions per table entry (kind 1)
     uint32_t entry_bytes;      // kind 1: bytes per entry; kind 0: bytes per row; kind 3: bytes per slot
-    const uint32_t *ptr;       // kind 2
-    const uint8_t *slots;      // kind 3: u16 count at the start of every slot
-    uint32_t slot_cap;         // kind 3: ids a slot holds
+    const uint32_t *ptr;       // kind 2: list bounds; kind 3: the slots (header words)
     unsigned long long *out;   // [0] table bytes at line granularity, [1] table accesses (requests), [2] bases read
 };
 
@@ -63,8 +61,11 @@ __global__ void __launch_bounds__(256) traffic_kernel(const TrafficArgs a)
                         bytes += 128ull * (lines_of(4ull * idx[s], 8) + lines_of(16ull * p0, 16ull * (p1 - p0)));
                         reqs += 2;
                     } else {
-                        bytes += a.entry_bytes;                     // slots are line-aligned multiples of 128 bytes
+                        // slots are line-aligned multiples of 128 bytes; a list that overflowed its slot costs its units too
+                        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(a.ptr) + (uint64_t)idx[s] * a.entry_bytes);
+                        bytes += a.entry_bytes;
                         reqs += 1;
+                        if ((hdr[0] & 0xFFFFu) == 0xFFFFu) { bytes += 128ull * lines_of(16ull * hdr[1], 16ull * hdr[2]); reqs += 1; }
                     }
                 }
             }

@@ -75,6 +75,10 @@ struct rb_ibf {
     mutable int table_kind = 0;             // 0 none, 1 dense k-mer / window table, 2 postings
     mutable uint32_t *d_post_ptr = nullptr;
     mutable uint16_t *d_post_ids = nullptr;
+    // ... or, by default, the same lists as one fixed slot per k-mer + an overflow area (table_kind 3)
+    mutable uint8_t *d_slots = nullptr;
+    mutable uint16_t *d_slot_ovf = nullptr;
+    mutable uint32_t slot_bytes = 0;
     mutable bool table_tried = false;
     // working memory of the column build (ibf_insert.cu), kept between insert calls; released when the k-mer table is built
     mutable rb::ScratchBuf build_scratch;
@@ -165,8 +169,9 @@ int alloc_device(rb_ibf *f, bool zero)
     RB_CUDA(cudaGetDeviceProperties(&prop, f->device));
     f->sm_count = prop.multiProcessorCount;
     RB_CUDA(cudaMalloc(&f->d_words, f->n_local_words * 8));
-    RB_CUDA(cudaMalloc(&f->d_err, sizeof(unsigned int)));
-    RB_CUDA(cudaMemset(f->d_err, 0, sizeof(unsigned int)));
+    // [0] insert error (bin >= n_bins), [1] count kernel gave up waiting for a bulk copy, [2..3] counters of the slot-table build
+    RB_CUDA(cudaMalloc(&f->d_err, 4 * sizeof(unsigned int)));
+    RB_CUDA(cudaMemset(f->d_err, 0, 4 * sizeof(unsigned int)));
     if (zero) RB_CUDA(cudaMemset(f->d_words, 0, f->n_local_words * 8));
     // host-buffer calls take their staging buffers from the stream-ordered pool; keep freed blocks
     // cached instead of returning them to the driver at every synchronisation
@@ -195,7 +200,7 @@ void destroy(rb_ibf *f)
 {
     if (!f) return;
     free_call_contexts(f);
-    if (f->d_words || f->d_err || f->d_table || f->d_post_ptr || f->d_post_ids || f->build_scratch.p) {
+    if (f->d_words || f->d_err || f->d_table || f->d_post_ptr || f->d_post_ids || f->d_slots || f->d_slot_ovf || f->build_scratch.p) {
         DeviceGuard g(f->device);
         if (f->build_scratch.p) cudaFree(f->build_scratch.p);
         if (f->d_words) cudaFree(f->d_words);
@@ -203,6 +208,8 @@ void destroy(rb_ibf *f)
         if (f->d_table) cudaFree(f->d_table);
         if (f->d_post_ptr) cudaFree(f->d_post_ptr);
         if (f->d_post_ids) cudaFree(f->d_post_ids);
+        if (f->d_slots) cudaFree(f->d_slots);
+        if (f->d_slot_ovf) cudaFree(f->d_slot_ovf);
     }
     delete f;
 }
@@ -284,10 +291,21 @@ uint64_t table_bytes_needed(const rb_ibf *f, int span)
 uint64_t postings_estimate_bytes(const rb_ibf *f, cudaStream_t st)
 {
     const rb::FilterView fv = view_of(f);
-    if (!rb::postings_applicable(fv)) return 0;
     const uint64_t n_kmers = 1ull << (2 * f->k);
     const uint32_t n_sample = (uint32_t)std::min<uint64_t>(65536, n_kmers);
     uint32_t *d_tmp = nullptr;
+    const char *lay = std::getenv("RB_POSTINGS_LAYOUT");
+    if (!(lay && lay[0] == 'l') && rb::slots_applicable(fv)) {
+        if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); return 0; }
+        std::vector<uint32_t> lengths;
+        const int r0 = rb::slots_sample_lengths(fv, d_tmp, n_sample, &lengths, f->sm_count, st);
+        cudaFree(d_tmp);
+        uint32_t sb = 0;
+        uint64_t ou = 0, total = 0;
+        if (r0 < 0 || !rb::slots_choose(lengths, (uint32_t)f->k, ~0ull, &sb, &ou, &total)) { cudaGetLastError(); return 0; }
+        return total;
+    }
+    if (!rb::postings_applicable(fv)) return 0;
     if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); return 0; }
     double mean_units = 0;
     const int r = rb::postings_sample_units(fv, d_tmp, n_sample, &mean_units, f->sm_count, st);
@@ -303,6 +321,7 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     std::lock_guard<std::mutex> lock(f->table_mu);
     if (f->d_table) return f->d_table;
     if (f->table_kind == 2) return reinterpret_cast<const uint64_t *>(f->d_post_ptr);
+    if (f->table_kind == 3) return reinterpret_cast<const uint64_t *>(f->d_slots);
     if (f->table_tried && !force) return nullptr;
     if (!force && n_reads < kTableMinReads) return nullptr;     // not "tried": a later large batch builds it
     f->table_tried = true;
@@ -321,8 +340,52 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     if (const char *gb = std::getenv("RB_KMER_TABLE_MAX_GB")) cap = (uint64_t)std::max(0, std::atoi(gb)) << 30;
     const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>((uint64_t)(free_b * 0.6), cap);
     if (f->col_words > 4) {
-        // wide rows: postings.  Size known only after counting: sample first, then count everything, then fill.
         const rb::FilterView fv = view_of(f);
+        // wide rows: postings.  Default layout: one fixed slot per k-mer (bulk copies into shared-memory rings);
+        // RB_POSTINGS_LAYOUT=lists keeps the pointer + variable-length lists of round 1 (A/B measurements).
+        const char *lay = std::getenv("RB_POSTINGS_LAYOUT");
+        const bool want_slots = !(lay && lay[0] == 'l');
+        if (want_slots && rb::slots_applicable(fv)) {
+            const uint64_t n_kmers = 1ull << (2 * f->k);
+            const uint32_t n_sample = (uint32_t)std::min<uint64_t>(65536, n_kmers);
+            uint32_t *d_tmp = nullptr;
+            if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            std::vector<uint32_t> lengths;
+            const int r0 = rb::slots_sample_lengths(fv, d_tmp, n_sample, &lengths, f->sm_count, st);
+            cudaFree(d_tmp);
+            if (r0 < 0) { cudaGetLastError(); return nullptr; }
+            uint32_t slot_bytes = 0;
+            uint64_t ovf_units = 0, total = 0;
+            if (const char *sb = std::getenv("RB_SLOT_BYTES")) {          // tests / tuning: force the slot size
+                std::vector<uint32_t> none;
+                slot_bytes = (uint32_t)std::max(128, std::min(4096, std::atoi(sb) / 128 * 128));
+                double over_units = 0;
+                for (uint32_t n : lengths) if (n > (slot_bytes - 8) / 2) over_units += (n + 7) / 8;
+                ovf_units = (uint64_t)(2.0 * over_units / (double)lengths.size() * (double)n_kmers) + (1u << 20);
+                total = n_kmers * slot_bytes + ovf_units * 16;
+                if (total > budget || ovf_units > 0xFFFFFFF0ull) return nullptr;
+            } else if (!rb::slots_choose(lengths, (uint32_t)f->k, budget, &slot_bytes, &ovf_units, &total)) return nullptr;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                uint8_t *d_slots = nullptr;
+                uint16_t *d_ovf = nullptr;
+                if (cudaMalloc(&d_slots, n_kmers * slot_bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+                if (cudaMalloc(&d_ovf, ovf_units * 16) != cudaSuccess) { cudaFree(d_slots); cudaGetLastError(); return nullptr; }
+                const int r1 = rb::slots_fill(fv, d_slots, slot_bytes, d_ovf, ovf_units, f->d_err + 2, f->sm_count, st);
+                if (r1 == 1) {
+                    g_launches += 2;
+                    f->d_slots = d_slots; f->d_slot_ovf = d_ovf; f->slot_bytes = slot_bytes;
+                    f->table_kind = 3; f->table_span = 1; f->table_entries = n_kmers;
+                    f->table_bytes = n_kmers * slot_bytes + ovf_units * 16;
+                    return reinterpret_cast<const uint64_t *>(d_slots);
+                }
+                cudaFree(d_slots); cudaFree(d_ovf); cudaGetLastError();
+                if (r1 != -3) return nullptr;
+                ovf_units *= 4;                                            // the sample underestimated the long lists: once more
+                if (n_kmers * slot_bytes + ovf_units * 16 > budget || ovf_units > 0xFFFFFFF0ull) return nullptr;
+            }
+            return nullptr;
+        }
+        // pointer + lists.  Size known only after counting: sample first, then count everything, then fill.
         if (!rb::postings_applicable(fv)) return nullptr;
         const uint64_t n_kmers = 1ull << (2 * f->k);
         const uint64_t ptr_bytes = (n_kmers + 1) * 4;
@@ -381,15 +444,20 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
 void drop_table(rb_ibf *f)
 {
     std::lock_guard<std::mutex> lock(f->table_mu);
-    if (f->d_table || f->d_post_ptr || f->d_post_ids) {
+    if (f->d_table || f->d_post_ptr || f->d_post_ids || f->d_slots || f->d_slot_ovf) {
         cudaDeviceSynchronize();
         if (f->d_table) cudaFree(f->d_table);
         if (f->d_post_ptr) cudaFree(f->d_post_ptr);
         if (f->d_post_ids) cudaFree(f->d_post_ids);
+        if (f->d_slots) cudaFree(f->d_slots);
+        if (f->d_slot_ovf) cudaFree(f->d_slot_ovf);
     }
     f->d_table = nullptr;
     f->d_post_ptr = nullptr;
     f->d_post_ids = nullptr;
+    f->d_slots = nullptr;
+    f->d_slot_ovf = nullptr;
+    f->slot_bytes = 0;
     f->table_kind = 0;
     f->table_entries = 0;
     f->table_span = 0;
@@ -1290,7 +1358,8 @@ const uint64_t *rb_ibf_device_kmer_table(const rb_ibf *f)
 {
     if (!f) return nullptr;
     std::lock_guard<std::mutex> lock(f->table_mu);
-    return f->table_kind == 2 ? reinterpret_cast<const uint64_t *>(f->d_post_ids) : f->d_table;
+    return f->table_kind == 3 ? reinterpret_cast<const uint64_t *>(f->d_slots)
+           : f->table_kind == 2 ? reinterpret_cast<const uint64_t *>(f->d_post_ids) : f->d_table;
 }
 
 // filter.resizeBins(n), src/IBF/IBFBuild.cpp:274 (update_filter): the number of rows stays, rows get wider
@@ -1401,6 +1470,12 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     const uint64_t *table = nullptr;
     if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3, n_reads);   // 3..5: table kernels
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
+    if (table && f->table_kind == 3) {
+        int n = rb::launch_count_slots(a, f->d_slots, f->slot_bytes, f->d_slot_ovf, max_read_len, f->sm_count, f->d_err + 1, (cudaStream_t)stream);
+        if (n == -1) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        if (n >= 0) { g_launches += (uint64_t)n; return RB_OK; }
+        table = nullptr;                          // -2: counters + rings of this launch's reads do not fit shared memory
+    }
     if (table && f->table_kind == 2) {
         int n = rb::launch_count_postings(a, f->d_post_ptr, f->d_post_ids, max_read_len, f->sm_count, (cudaStream_t)stream);
         if (n == -1) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -1451,6 +1526,15 @@ int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t *read_
     int st = run_count_batch(f, ctx, reinterpret_cast<const uint8_t *>(bases), read_off, n_reads, thr_lut, n_lut, counts_fwd,
                              counts_rev, max_count, hit, argmax_bin, read_flag, (cudaStream_t)stream);
     release_ctx(f, ctx);
+    if (st == RB_OK && f->table_kind == 3) {
+        // the slot kernel never hangs on a bulk copy that does not land: it gives up and says so here
+        unsigned int gave_up = 0;
+        RB_CUDA(cudaMemcpy(&gave_up, f->d_err + 1, sizeof(gave_up), cudaMemcpyDeviceToHost));
+        if (gave_up) {
+            cudaMemset(f->d_err + 1, 0, sizeof(gave_up));
+            return fail(RB_ERR_COUNT_KMER, "Error counting kmers in IBF bins: a postings slot copy did not complete");
+        }
+    }
     return st;
 }
 
@@ -1469,6 +1553,7 @@ int rb_ibf_count_traffic_dev(const rb_ibf *f, const uint8_t *d_bases, const uint
         kind = f->table_kind; span = f->table_span;
         if (kind == 1) entry_bytes = (uint32_t)(span == 1 ? 16 * f->col_words : (span == 2 ? 2 : 4) * 16 * f->col_words);
         else if (kind == 2) { entry_bytes = 16; ptr = f->d_post_ptr; }
+        else if (kind == 3) { entry_bytes = f->slot_bytes; ptr = reinterpret_cast<const uint32_t *>(f->d_slots); }
         else entry_bytes = (uint32_t)(8 * f->col_words);
     }
     unsigned long long *d_out = nullptr, h_out[3] = {0, 0, 0};

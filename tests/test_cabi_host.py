@@ -141,6 +141,13 @@ def test_postings_list_order_is_a_bijection_and_spreads_banks(tmp_path):
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
 
 
+def test_slot_order_is_a_bijection_and_spreads_banks(tmp_path):
+    """rb::slot_position / slot_pad_id (order of the bin ids inside a postings slot) for every length a slot can hold."""
+    exe = _compile(os.path.join(ROOT, "tests", "cpp", "test_slot_layout.cpp"), str(tmp_path / "test_slot_layout"), link=False)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
 @pytest.mark.parametrize("isa", ["5", "2", "0"])
 def test_host_packer_matches_restatement(tmp_path, isa):
     """Bit planes of the host packer (AVX-512 / AVX2 / scalar paths, thread pool) against a plain loop."""

@@ -156,18 +156,24 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
     if kernel.startswith("table"):
         if gf.bin_width > 4:                             # wide rows: postings table (sorted bin lists per k-mer)
             exp = of.count_batch(bases, off, lut, n_threads=4)
-            gf.enable_kmer_table(0)
-            assert gf.kmer_table_kind() == 2 and gf.kmer_table_bytes() > 4 ** k * 4
-            assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)          # long reads: 16-bit counters
             short = [250] * 70 + [0, 1, k - 1, k, k + 1, 31, 32, 33, 64, 100, 249, 251, 254 + k, 255 + k - 1]
             sb, so = synth.ragged_reads(plan["bases"], short, seed=12, frac_from_ref=0.7, n_frac=0.004, lower_frac=0.1)
             sb[int(so[5]):int(so[6])] = ord("N")
             sb[int(so[7]) + 100] = ord("U")
             sexp = of.count_batch(sb, so, lut, n_threads=4)
-            assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)             # <= 255 positions: 8-bit counters
-            assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
-            gf.disable_kmer_table()
-            assert gf.kmer_table_kind() == 0
+            # slots: one fixed slot per k-mer fetched by bulk copies (default); lists: pointer + variable-length lists
+            for layout, kind in (("slots", 3), ("lists", 2)):
+                os.environ["RB_POSTINGS_LAYOUT"] = layout
+                try:
+                    gf.enable_kmer_table(0)
+                finally:
+                    del os.environ["RB_POSTINGS_LAYOUT"]
+                assert gf.kmer_table_kind() == kind and gf.kmer_table_bytes() > 4 ** k * 4
+                assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)          # long reads: 16-bit counters
+                assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)             # <= 255 positions: 8-bit counters
+                assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+                gf.disable_kmer_table()
+                assert gf.kmer_table_kind() == 0
             return
         exp = of.count_batch(bases, off, lut, n_threads=4)
         span1 = 4 ** k * 16 * gf.bin_width
@@ -294,11 +300,53 @@ def test_host_buffer_pipeline_packed_pieces_and_rounds(monkeypatch):
 
 @pytest.mark.parametrize("order", ["1", "0"])
 @pytest.mark.parametrize("n_blocks", [2600, 3700, 6000, 9000])
+@pytest.mark.parametrize("slot_bytes,ring", [(0, 0), (128, 0), (256, 1), (1024, 2)])
+def test_postings_slots(n_blocks, order, slot_bytes, ring, monkeypatch):
+    """The same over-full filters through the SLOT layout: the sampled slot size (0) and forced ones -- 128 / 256 bytes push most
+    / many lists into the overflow area, 1 024 holds nearly all -- with ring depths 1 and 2 next to the default."""
+    monkeypatch.setenv("RB_POSTINGS_ORDER", order)
+    if slot_bytes:
+        monkeypatch.setenv("RB_SLOT_BYTES", str(slot_bytes))
+    if ring:
+        monkeypatch.setenv("RB_SLOT_RING", str(ring))
+    k, n_hash = 11, 3
+    ref = [synth.random_bases(1500, 300 + i) for i in range(1100)]
+    plan = synth.build_plan(ref, 2000, k, n_hash=n_hash)
+    n_bits = n_blocks * 64 * 18
+    of = oracle.OracleIBF.create(1100, n_hash, k, n_bits)
+    of.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"], n_threads=4)
+    gf = rb.IBF.create(1100, n_hash, k, n_bits)
+    gf.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+    gf.enable_kmer_table(0)
+    assert gf.kmer_table_kind() == 3
+    if slot_bytes:
+        assert gf.kmer_table_bytes() >= 4 ** k * slot_bytes
+    lut = rb.threshold_lut(0.1, k)
+    short = [250] * 40 + [0, 1, k - 1, k, k + 1, 31, 64, 100, 249, 251, 254 + k]
+    sb, so = synth.ragged_reads(plan["bases"], short, seed=21, frac_from_ref=0.7, n_frac=0.004, lower_frac=0.1)
+    sexp = of.count_batch(sb, so, lut, n_threads=8)
+    assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)                 # 8-bit counters
+    assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+    longer = [250] * 8 + [255 + k, 400, 700, 1500]
+    lb, lo = synth.ragged_reads(plan["bases"], longer, seed=22, frac_from_ref=0.7, n_frac=0.003, lower_frac=0.1)
+    assert_same_results(gf.count_batch(lb, lo, lut, dense=True), of.count_batch(lb, lo, lut, n_threads=8))   # 16-bit counters
+    # the measured-geometry traffic of the roofline: a slot per (position, strand) + what overflowed
+    import torch
+    d_b, d_o = torch.from_numpy(sb).cuda(), torch.from_numpy(so.astype(np.int64)).cuda()
+    tb, reqs, io = gf.count_traffic_dev(d_b, d_o, len(so) - 1, 1)
+    pairs = 2 * sum(max(0, x - k + 1) for x in short if x <= 65535)
+    sbytes = (gf.kmer_table_bytes() // 4 ** k) // 128 * 128 if not slot_bytes else slot_bytes
+    assert tb >= 0.95 * pairs * min(sbytes, 128) and reqs >= 0.95 * pairs and io > sb.size
+
+
+@pytest.mark.parametrize("order", ["1", "0"])
+@pytest.mark.parametrize("n_blocks", [2600, 3700, 6000, 9000])
 def test_postings_long_lists(n_blocks, order, monkeypatch):
     """Postings lists of ~610 / ~380 / ~160 / ~70 bins per k-mer (an over-full 1 100-bin filter: 56 % .. 6 % false positives
     per bin), so that the lookup kernel walks full rounds, further rounds and every tail width (ibf_postings_layout.cuh),
     with the ids dealt over the groups (default) and ascending (RB_POSTINGS_ORDER=0)."""
     monkeypatch.setenv("RB_POSTINGS_ORDER", order)
+    monkeypatch.setenv("RB_POSTINGS_LAYOUT", "lists")
     k, n_hash = 11, 3
     ref = [synth.random_bases(1500, 300 + i) for i in range(1100)]
     plan = synth.build_plan(ref, 2000, k, n_hash=n_hash)
