@@ -413,7 +413,8 @@ def run_workload(env, args, name, n_reads, steps, warmup, role):
             nb_local = gf.n_bins_local
             of = oracle.OracleIBF.create(nb_local, 3, k, gf.n_blocks * 64 * gf.col_words)
             assert of.bin_width == gf.col_words and of.n_blocks == gf.n_blocks
-            of.words()[:gf.n_local_words] = gf.download()
+            nw = gf.n_blocks * gf.col_words                  # (an unsharded handle also holds the words behind the last whole row)
+            of.words()[:nw] = gf.download()[:nw]
             exp_keys = np.zeros((n_lut, len(pick)), np.uint64)
             t0 = time.time()
             for t in range(n_lut):

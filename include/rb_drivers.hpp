@@ -13,6 +13,7 @@
 
 #include "rb_interleave.hpp"
 
+#include <chrono>
 #include <cstdio>
 #include <filesystem>
 #include <iostream>
@@ -213,6 +214,9 @@ struct ClassificationResults {          // classify.hpp:127-134
     uint64_t too_short = 0;
     uint64_t readCounter = 0;
     std::vector<int> assignment;         // per read: target index, -2 depleted-mode hit, -1 unclassified, -3 failed, -4 too short
+    double avgClassifyduration = 0;      // seconds per read: chunk loop + decisions + output records (classify.hpp:252-303, :362)
+    double readFileSeconds = 0;          // parsing the read file (outside the reference's per-read timer)
+    double tableSetupSeconds = 0;        // the joint k-mer table plan (one-off, before the first read)
 };
 
 inline std::string to_dna5_string(const std::string &s)
@@ -237,14 +241,22 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
     Conf.significance = 0.95;                                  // classify.hpp:173
     Conf.error_rate = config.IBF_Parsed.error_rate;
     const int cl = config.IBF_Parsed.chunk_length;
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const clk::time_point t_setup = clk::now();
     enable_kmer_tables(DepletionFilters, TargetFilters);      // one plan for all filters, before the first read
+    const double table_setup_s = secs(t_setup, clk::now());
     ClassificationResults res;
     std::filesystem::create_directories(config.output_dir);
 
     for (const std::filesystem::path &read_file : config.IBF_Parsed.read_files) {
         res = ClassificationResults();
+        res.tableSetupSeconds = table_setup_s;
         for (IBFMeta &f : TargetFilters) f.classified = 0;
+        const clk::time_point t_read = clk::now();
         std::vector<SeqRecord> reads = read_sequence_file(read_file.string());
+        const clk::time_point t_classify = clk::now();
+        res.readFileSeconds = secs(t_read, t_classify);
         const size_t n = reads.size();
         res.readCounter = n;
         res.assignment.assign(n, -1);
@@ -336,12 +348,16 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
                 for (size_t p = 0; p < d.size(); p += 70) unclassified << d.substr(p, 70) << "\n";
             }
         }
+        // the reference's per-read timer covers the chunk loop, the decision and the output record of a read; here the same work
+        // is done for all reads of the file at once
+        res.avgClassifyduration = res.readCounter ? secs(t_classify, clk::now()) / (double)res.readCounter : 0.0;
         std::cout << "------------------------------- Final Results -------------------------------" << std::endl;
         std::cout << "Number of classified reads                         :   " << res.found << std::endl;
         std::cout << "Number of of too short reads (len < " << cl << ")           :   " << res.too_short << std::endl;
         std::cout << "Number of all reads                                :   " << res.readCounter << std::endl;
         for (IBFMeta &f : TargetFilters)
             std::cout << f.name << "\t : " << f.classified << "\t\t" << ((float)f.classified) / ((float)res.readCounter) << std::endl;
+        std::cout << "Average Processing Time Read Classification        :   " << res.avgClassifyduration << std::endl;
         std::cout << "-----------------------------------------------------------------------------------" << std::endl;
     }
     return res;

@@ -211,6 +211,25 @@ RB_API int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const
 RB_API int rb_keys_decode_dev(const uint64_t *d_keys, uint64_t n, uint16_t *d_max_count, uint8_t *d_hit,
                               uint32_t *d_argmax_bin, int device, rb_stream stream);
 
+/* ---- bin-sharded filters (BASELINE config #5: a database larger than one GPU's HBM) --------------------------------
+ * Every shard holds a column slice of every row (rb_ibf_load_shard / rb_ibf_create_shard), every shard classifies ALL
+ * reads against its bins, and the per-read keys of the shards combine by elementwise MAX (RB_KEY_* above).
+ *
+ * One host process driving several devices (what a C++ host like ReadBouncer does):
+ * shards[i] lives on its own device; the batch is copied to every device, every device counts, and every count kernel
+ * folds its key straight into ONE key array on shards[0]'s device with a system-scope 64-bit atomicMax over NVLink
+ * peer memory -- the combine is the kernels' own epilogue, there is no separate collective and no host hop; shard 0
+ * decodes.  Outputs as rb_ibf_count_batch (max_count / hit / argmax_bin [n_lut][n_reads], global bin ids; read_flag
+ * [n_reads]); dense counts are per shard and not offered here.  Synchronous. */
+RB_API int rb_ibf_count_batch_sharded(const rb_ibf *const *shards, uint32_t n_shards, const char *bases,
+                                      const uint64_t *read_off, uint64_t n_reads, const uint16_t *thr_lut, uint32_t n_lut,
+                                      uint16_t *max_count, uint8_t *hit, uint32_t *argmax_bin, uint8_t *read_flag);
+/* One process per GPU (MPI / torchrun style): after rb_ibf_count_batch_dev on every rank, ONE in-place
+ * ncclAllReduce(ncclUint64, ncclMax) of the n keys on `stream` (8 bytes per read and threshold table; dense counts are
+ * never exchanged), then rb_keys_decode_dev.  nccl_comm is the caller's ncclComm_t; libnccl.so.2 is looked up at run
+ * time (the copy already loaded in the process, if any), so the library itself does not link NCCL. */
+RB_API int rb_keys_combine_nccl(void *nccl_comm, uint64_t *d_keys, uint64_t n, rb_stream stream);
+
 /* Direct k-mer table for narrow filters (row <= 4 words, k <= 16): the AND of the h probed rows is a
  * pure function of the k-mer, so it is tabulated once for all ACGT k-mers and both strands.  An entry
  * covers a window of `span` consecutive k-mers (k+span-1 bases).  span 1: 4^k entries of 16*col_words

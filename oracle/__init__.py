@@ -292,6 +292,50 @@ def check_unblock(deplete, target, read, error_rate=0.1, significance=0.95):
     return int(r)
 
 
+def classify_reads_serial(reads, dep, tgt, chunk, max_chunks, err):
+    """The serial loop of classify_reads (src/main/classify.hpp:229-303) read by read, chunk by chunk, with the oracle's
+    classify overloads: per read the index of the target filter it is assigned to, -2 a depletion-mode hit, -1 unclassified,
+    -3 failed (ShortReadException), -4 too short (len < chunk_length).  `dep` / `tgt` are lists of OracleIBF."""
+    assign = []
+    for seq in reads:
+        if len(seq) < chunk:
+            assign.append(-4)
+            continue
+        a = -1
+        for i in range(max_chunks):
+            if i * chunk >= len(seq):
+                break
+            frag = seq[i * chunk:min((i + 1) * chunk, len(seq))]
+            if dep and tgt:                                   # classify_deplete_target, classify.hpp:58-111
+                t0, d0 = classify_pair(tgt, dep, frag, err)
+                ok = False
+                if t0 > 0:
+                    if d0 > 0:
+                        t1, d1 = classify_pair(tgt, dep, frag, err - 0.02)
+                        ok = t1 > 0 and d1 == 0
+                    else:
+                        ok = True
+                if ok:
+                    a = classify_best(tgt, frag, err)
+            elif dep:
+                if len(frag) < dep[0].k:
+                    a = -3
+                    break
+                if classify_best(dep, frag, err) > -1:
+                    a = -2
+            else:
+                if len(frag) < tgt[0].k:
+                    a = -3
+                    break
+                b = classify_best(tgt, frag, err)
+                if b != -1:
+                    a = b
+            if a != -1:
+                break
+        assign.append(a)
+    return assign
+
+
 def build_from_sequences(seqs, fragment_length, k=13, n_hash=3, max_fp=0.01, passes=1, n_threads=1):
     """IBF::create_filter restated (src/IBF/IBFBuild.cpp:421-521) on in-memory records.
 

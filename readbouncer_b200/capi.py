@@ -31,7 +31,7 @@ EXPORTS = [
     "rb_microbench_gather", "rb_microbench_gather_coop", "rb_set_l2_fetch_granularity", "rb_get_l2_fetch_granularity",
     "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins", "rb_host_pack_info", "rb_transfer_bytes",
     "rb_ibf_transfer_policy", "rb_ibf_count_traffic_dev", "rb_synth_bases_dev",
-    "rb_ibf_enable_kmer_tables", "rb_threshold_lut_raw",
+    "rb_ibf_enable_kmer_tables", "rb_threshold_lut_raw", "rb_ibf_count_batch_sharded", "rb_keys_combine_nccl",
 ]
 
 
@@ -118,6 +118,8 @@ def lib():
         "rb_synth_bases_dev": (i32, [vp, u64, u64, u64, vp]),
         "rb_ibf_enable_kmer_tables": (i32, [vp, u32, u64, vp]),
         "rb_threshold_lut_raw": (i32, [dbl, dbl, u32, vp]),
+        "rb_ibf_count_batch_sharded": (i32, [vp, u32, vp, vp, u64, vp, u32, vp, vp, vp, vp]),
+        "rb_keys_combine_nccl": (i32, [vp, vp, u64, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -225,6 +227,24 @@ def threshold_lut(error_rate, kmer_size, significance=0.95, raw=False):
     fn = lib().rb_threshold_lut_raw if raw else lib().rb_threshold_lut
     _check(fn(error_rate, significance, kmer_size, _np_ptr(out)))
     return out
+
+
+def count_batch_sharded(shards, bases, read_off, thr_lut):
+    """Bin shards on several devices of this process: one call, keys folded over NVLink (rb_ibf_count_batch_sharded)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    read_off = np.ascontiguousarray(read_off, dtype=np.uint64)
+    lut = np.ascontiguousarray(thr_lut, dtype=np.uint16).reshape(-1, LUT_SIZE)
+    n, n_lut = read_off.size - 1, lut.shape[0]
+    res = {"max_count": np.zeros((n_lut, n), np.uint16), "hit": np.zeros((n_lut, n), np.uint8),
+           "argmax_bin": np.zeros((n_lut, n), np.uint32), "read_flag": np.zeros(n, np.uint8)}
+    arr = (C.c_void_p * len(shards))(*[f._h for f in shards])
+    _check(lib().rb_ibf_count_batch_sharded(arr, len(shards), _np_ptr(bases), _np_ptr(read_off), n, _np_ptr(lut), n_lut,
+                                            _np_ptr(res["max_count"]), _np_ptr(res["hit"]), _np_ptr(res["argmax_bin"]),
+                                            _np_ptr(res["read_flag"])))
+    if n_lut == 1:
+        for key in ("max_count", "hit", "argmax_bin"):
+            res[key] = res[key][0]
+    return res
 
 
 def enable_kmer_tables(filters, total_bytes=0, stream=None):

@@ -20,6 +20,8 @@
 //                       per plane per 64 bins and no shared-memory traffic (configs #3, #5).
 #include "ibf_device.cuh"
 
+#include <cstdlib>
+
 namespace rb {
 
 // ------------------------------------------------------------------------------------------
@@ -327,7 +329,7 @@ count_stream_kernel(const CountArgs a)
         uint64_t bk = 0;
 #pragma unroll
         for (int w = 0; w < kStreamThreads / 32; ++w) bk = s_red[w][tid] > bk ? s_red[w][tid] : bk;
-        if (bk) atomicMax((unsigned long long *)(a.keys + (size_t)tid * a.n_reads + read), (unsigned long long)bk);
+        if (bk) key_max(a.keys + (size_t)tid * a.n_reads + read, bk, a.keys_shared);
     }
 }
 
@@ -378,7 +380,7 @@ static void launch_tile_one(const CountArgs &a, uint32_t c0, uint32_t n_tiles, i
         occ = o > 0 ? o : 1;
     }
     uint64_t blocks_needed = (a.n_reads + kTileWarps - 1) / kTileWarps;
-    uint64_t max_x = (uint64_t)sm_count * occ;
+    uint64_t max_x = (uint64_t)sm_count * occ * grid_waves();
     if (n_tiles > 1) max_x = (max_x + n_tiles - 1) / n_tiles;
     uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
     if (gx == 0) gx = 1;
@@ -447,6 +449,16 @@ static int launch_stream(const CountArgs &a, uint32_t max_read_len, cudaStream_t
     return 1;
 }
 
+int grid_waves()
+{
+    static const int waves = [] {
+        const char *e = std::getenv("RB_GRID_WAVES");
+        const int v = e ? std::atoi(e) : 0;
+        return v > 0 ? (v > 64 ? 64 : v) : 1;
+    }();
+    return waves;
+}
+
 int launch_count(const CountArgs &a, uint32_t max_read_len, int which, int sm_count, cudaStream_t st)
 {
     if (a.n_reads == 0) return 0;
@@ -458,8 +470,8 @@ int launch_count(const CountArgs &a, uint32_t max_read_len, int which, int sm_co
     else if (which == 2) use_stream = stream_ok;
     else use_stream = stream_ok && a.fv.stride > 4;
     int launches = 0;
-    if (use_stream || a.fv.stride > 4) {
-        // both multi-block paths combine their partial summaries with atomicMax
+    if ((use_stream || a.fv.stride > 4) && !a.keys_shared) {
+        // both multi-block paths combine their partial summaries with atomicMax (a shared key array is zeroed by its owner)
         cudaMemsetAsync(a.keys, 0, sizeof(uint64_t) * a.n_lut * a.n_reads, st);
     }
     launches += use_stream ? launch_stream(a, max_read_len, st) : launch_tile(a, sm_count, st);

@@ -18,6 +18,14 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v)
     return v;
 }
 
+// fold a key into a shared key array: device scope for the partial summaries of one launch, system scope when the array
+// is shared by the kernels of several devices (CountArgs::keys_shared; NVLink peer atomics)
+__device__ __forceinline__ void key_max(uint64_t *dst, uint64_t key, int shared_by_devices)
+{
+    if (shared_by_devices) atomicMax_system(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)key);
+    else atomicMax(reinterpret_cast<unsigned long long *>(dst), (unsigned long long)key);
+}
+
 __device__ __forceinline__ uint32_t read_flag_of(uint64_t len, uint32_t k)
 {
     return len < k ? 1u : (len > 65535u ? 2u : 0u);
@@ -96,7 +104,7 @@ __device__ __forceinline__ void tile_epilogue(const CountArgs &a, uint64_t read,
             uint64_t bk = warp_max_u64(best[t]);
             if (lane == 0) {
                 uint64_t *dst = a.keys + (size_t)t * a.n_reads + read;
-                if (multi_tile) { if (bk) atomicMax((unsigned long long *)dst, (unsigned long long)bk); }
+                if (multi_tile || a.keys_shared) { if (bk) key_max(dst, bk, a.keys_shared); }
                 else *dst = bk;
             }
         }

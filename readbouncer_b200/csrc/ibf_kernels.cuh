@@ -31,6 +31,10 @@ struct CountArgs {
     // of the `bases` coordinate system that read_off uses.  Only the group-per-read window-table kernel reads them.
     const uint32_t *pk_lo, *pk_hi, *pk_bad;
     uint64_t pk_base0;
+    // keys_shared: `keys` is ONE array shared by the count kernels of all bin shards (rb_ibf_count_batch_sharded), possibly in
+    // a peer device's memory: every kernel folds its key in with a system-scope 64-bit atomicMax instead of storing it, and
+    // nobody but the owner zeroes it.  Honoured by the kernels wide shards use (slots, postings, streaming, multi-tile).
+    int keys_shared;
 };
 
 struct InsertArgs {
@@ -45,6 +49,11 @@ struct InsertArgs {
     uint64_t n_frags;
     unsigned int *error_flag;  // set to 1 when a fragment names a bin >= n_bins
 };
+
+// Grid size of the grid-stride count kernels in waves of resident CTAs.  One wave (every CTA resident from start to end, equal
+// shares of the reads) leaves the SMs that finish early idle: memory channels are not equally far from every SM.  Several
+// waves of smaller shares let the block scheduler hand out work as SMs become free.  RB_GRID_WAVES overrides (measurements).
+int grid_waves();
 
 // which: 0 auto, 1 tile kernel, 2 streaming kernel.  Returns number of kernel launches or <0.
 int launch_count(const CountArgs &a, uint32_t max_read_len, int which, int sm_count, cudaStream_t st);

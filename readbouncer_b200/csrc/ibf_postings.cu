@@ -438,7 +438,9 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                 const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)tid * kLutSize + len);
                 if (M >= thr) key = pack_key(M, (uint32_t)(a.fv.bin_begin + best_bin));
             }
-            a.keys[(size_t)tid * a.n_reads + read] = key;
+            uint64_t *const dst = a.keys + (size_t)tid * a.n_reads + read;
+            if (a.keys_shared) { if (key) key_max(dst, key, 1); }          // all bin shards fold into one array (NVLink peer atomics)
+            else *dst = key;
         }
     }
 }
@@ -626,8 +628,44 @@ __device__ __forceinline__ void bump_checked(uint32_t *cnt, const uint32_t v, co
     if ((v & 0xFFFFu) != sentinel) bump<CB>(cnt, v);
 }
 
+// One slot, landed in shared memory: its ids into the counters of one strand.  Round r: lane l takes the four ids at
+// positions 128 r + 4 l (one LDS.64); pads fill the last round, so only a slot-filling list ends in a partial one.
+template <int CB>
+__device__ __forceinline__ void consume_slot(const uint8_t *sp, uint32_t *cnt, const uint32_t cap, const int lane,
+                                             const uint4 *__restrict__ ovf, const uint32_t sentinel)
+{
+    const uint2 hdr = *reinterpret_cast<const uint2 *>(sp);
+    const uint32_t n = hdr.x & 0xFFFFu;
+    if (n != kSlotOverflow) {
+        const uint32_t lim = min(cap, (n + 127u) & ~127u);
+        const uint8_t *ip = sp + kSlotHeaderBytes + 8u * lane;
+        const uint32_t full = lim >> 7;
+#pragma unroll 2
+        for (uint32_t r = 0; r < full; ++r, ip += 256) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(ip);
+            bump_pair<CB>(cnt, v.x);
+            bump_pair<CB>(cnt, v.y);
+        }
+        if (4u * lane < (lim & 127u)) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(ip);
+            bump_pair<CB>(cnt, v.x);
+            bump_pair<CB>(cnt, v.y);
+        }
+    } else {                                                               // rare: the list lives in the overflow area
+        const uint32_t units = *reinterpret_cast<const uint32_t *>(sp + 8);
+        for (uint32_t u = lane; u < units; u += 32) {
+            const uint4 v = __ldg(ovf + hdr.y + u);
+            bump_checked<CB>(cnt, v.x, sentinel); bump_checked<CB>(cnt, v.x >> 16, sentinel);
+            bump_checked<CB>(cnt, v.y, sentinel); bump_checked<CB>(cnt, v.y >> 16, sentinel);
+            bump_checked<CB>(cnt, v.z, sentinel); bump_checked<CB>(cnt, v.z >> 16, sentinel);
+            bump_checked<CB>(cnt, v.w, sentinel); bump_checked<CB>(cnt, v.w >> 16, sentinel);
+        }
+    }
+}
+
 // CB: counter bits.  THREADS per CTA: 256, 384 or 768 by how many CTAs of counters + rings fit an SM.
-// Dynamic shared memory: [2 * cnt_words counters][kPostPiece packed k-mers][digits][pad to 128][warps * ring slots][warps * ring mbarriers]
+// Dynamic shared memory: [2 * cnt_words counters][2 * kPostPiece slot indices][digits][pad to 128]
+//                        [warps * ring entries of 2 slots (forward, reverse strand of one position)][warps * ring mbarriers]
 template <int CB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 768 / THREADS)
 count_slots_kernel(const CountArgs a, const uint8_t *__restrict__ slots, const uint32_t slot_bytes, const uint4 *__restrict__ ovf,
@@ -639,13 +677,15 @@ count_slots_kernel(const CountArgs a, const uint8_t *__restrict__ slots, const u
     extern __shared__ __align__(128) uint32_t s_slot_mem[];
     uint32_t *const s_mem = s_slot_mem;
     uint32_t *const cntF = s_mem, *const cntR = s_mem + cnt_words;
-    uint32_t *const s_x = s_mem + 2 * cnt_words;
-    uint8_t *const s_dig = reinterpret_cast<uint8_t *>(s_x + kPostPiece);
+    uint32_t *const s_idx = s_mem + 2 * cnt_words;                         // [2 * kPostPiece]: slot index of (position, strand) or ~0u
+    uint8_t *const s_dig = reinterpret_cast<uint8_t *>(s_idx + 2 * kPostPiece);
     __shared__ uint32_t s_red[kWarps];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint8_t *const my_ring = reinterpret_cast<uint8_t *>(s_mem) + ring_off + (size_t)warp * ring * slot_bytes;
-    uint64_t *const my_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_mem) + ring_off + (size_t)kWarps * ring * slot_bytes) + warp * ring;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);                // the same value, provably warp-uniform
+    const uint32_t entry_bytes = 2 * slot_bytes;
+    uint8_t *const my_ring = reinterpret_cast<uint8_t *>(s_mem) + ring_off + (size_t)warp * ring * entry_bytes;
+    uint64_t *const my_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_mem) + ring_off + (size_t)kWarps * ring * entry_bytes) + warp * ring;
     const uint32_t k = a.fv.hp.k;
     const uint32_t kbits = 2 * k;
     const uint32_t kmask = kbits >= 32 ? ~0u : ((1u << kbits) - 1u);
@@ -658,8 +698,7 @@ count_slots_kernel(const CountArgs a, const uint8_t *__restrict__ slots, const u
         for (uint32_t j = 0; j < ring; ++j) mbar_init(my_bar + j, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    uint32_t phase_bits = 0;                                               // expected parity of each of this warp's slots
-
+    uint32_t phase_bits = 0;                                               // expected parity of each of this warp's ring entries
     bool dead = false;                                                     // a copy never landed: stop waiting, wind down
 
     for (uint64_t read = blockIdx.x; read < a.n_reads; read += gridDim.x) {
@@ -685,67 +724,47 @@ count_slots_kernel(const CountArgs a, const uint8_t *__restrict__ slots, const u
                         x = (x << 2) | (d & 3u);
                         bad |= d >> 2;
                     }
-                    s_x[j] = bad ? ~0u : (x & kmask);
+                    x &= kmask;
+                    uint32_t v = __brev(~x);                               // reverse strand: the slot of revcomp(x)
+                    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+                    *reinterpret_cast<uint2 *>(s_idx + 2 * j) = bad ? make_uint2(~0u, ~0u) : make_uint2(x, v >> (32 - kbits));
                 }
                 __syncthreads();
-                // every warp takes an equal, contiguous share of the (position, strand) pairs -- pair q = position q >> 1,
-                // strand q & 1 -- and keeps `ring` slots in flight: the copy of pair q + ring is issued when pair q is counted
-                const uint32_t n_pairs = 2 * cn;
-                const uint32_t share = 2u * ((cn + kWarps - 1) / kWarps);
-                const uint32_t q_begin = min(n_pairs, warp * share), q_end = min(n_pairs, q_begin + share);
-                auto issue = [&](const uint32_t q, const uint32_t slot) {
-                    const uint32_t x = s_x[q >> 1];
-                    if (x == ~0u) return;                                  // hashed pair: no copy, its slot stays idle
-                    uint32_t idx = x;
-                    if (q & 1u) {                                          // reverse strand: the slot of revcomp(x)
-                        uint32_t v = __brev(~x);
-                        v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
-                        idx = v >> (32 - kbits);
-                    }
+                // every warp takes an equal, contiguous share of the positions and keeps `ring` of them in flight: both strands'
+                // slots of a position land in one ring entry (two bulk copies, one mbarrier); the copies of position p + ring
+                // are issued when position p has been counted
+                const uint32_t share = (cn + kWarps - 1) / kWarps;
+                const uint32_t p_begin = min(cn, warp * share), p_end = min(cn, p_begin + share);
+                auto issue = [&](const uint32_t p, const uint32_t e) {
+                    const uint2 ix = *reinterpret_cast<const uint2 *>(s_idx + 2 * p);
+                    if (ix.x == ~0u) return;                               // window with a non-ACGT base: hashed, the entry stays idle
                     if (lane == 0) {
-                        mbar_expect_tx(my_bar + slot, slot_bytes);
-                        bulk_g2s(my_ring + (size_t)slot * slot_bytes, slots + (uint64_t)idx * slot_bytes, slot_bytes, my_bar + slot);
+                        uint8_t *const dst = my_ring + (size_t)e * entry_bytes;
+                        mbar_expect_tx(my_bar + e, entry_bytes);
+                        bulk_g2s(dst, slots + (uint64_t)ix.x * slot_bytes, slot_bytes, my_bar + e);
+                        bulk_g2s(dst + slot_bytes, slots + (uint64_t)ix.y * slot_bytes, slot_bytes, my_bar + e);
                     }
                 };
-                for (uint32_t j = 0; j < ring && q_begin + j < q_end; ++j) issue(q_begin + j, j);
-                uint32_t slot = 0;
-                for (uint32_t q = q_begin; q < q_end; ++q) {
-                    uint32_t *const cnt = (q & 1u) ? cntR : cntF;
-                    if (s_x[q >> 1] == ~0u) {
-                        add_hashed<CB>(a.fv, s_dig + (q >> 1), q & 1u, cnt, lane);
-                    } else if (!dead && !__all_sync(0xffffffffu, mbar_wait(my_bar + slot, (phase_bits >> slot) & 1u, err))) {
-                        dead = true;                                       // warp-uniform: nobody waits or counts any more
+                for (uint32_t j = 0; j < ring && p_begin + j < p_end; ++j) issue(p_begin + j, j);
+                uint32_t e = 0;
+#pragma unroll 1
+                for (uint32_t p = p_begin; p < p_end; ++p) {
+                    if (s_idx[2 * p] == ~0u) {
+                        add_hashed<CB>(a.fv, s_dig + p, 0u, cntF, lane);
+                        add_hashed<CB>(a.fv, s_dig + p, 1u, cntR, lane);
                     } else if (!dead) {
-                        phase_bits ^= 1u << slot;
-                        const uint8_t *const sp = my_ring + (size_t)slot * slot_bytes;
-                        const uint2 hdr = *reinterpret_cast<const uint2 *>(sp);
-                        const uint32_t n = hdr.x & 0xFFFFu;
-                        if (n != kSlotOverflow) {
-                            const uint32_t lim = min(cap, (n + 127u) & ~127u);
-                            const uint8_t *const ip = sp + kSlotHeaderBytes + 8u * lane;
-#pragma unroll 4
-                            for (uint32_t p0 = 0; p0 < lim; p0 += 128u) {
-                                if (p0 + 4u * lane < lim) {
-                                    const uint2 v = *reinterpret_cast<const uint2 *>(ip + 2u * p0);
-                                    bump_pair<CB>(cnt, v.x);
-                                    bump_pair<CB>(cnt, v.y);
-                                }
-                            }
-                        } else {                                           // rare: the list lives in the overflow area
-                            const uint32_t units = *reinterpret_cast<const uint32_t *>(sp + 8);
-                            for (uint32_t u = lane; u < units; u += 32) {
-                                const uint4 v = __ldg(ovf + hdr.y + u);
-                                bump_checked<CB>(cnt, v.x, sentinel); bump_checked<CB>(cnt, v.x >> 16, sentinel);
-                                bump_checked<CB>(cnt, v.y, sentinel); bump_checked<CB>(cnt, v.y >> 16, sentinel);
-                                bump_checked<CB>(cnt, v.z, sentinel); bump_checked<CB>(cnt, v.z >> 16, sentinel);
-                                bump_checked<CB>(cnt, v.w, sentinel); bump_checked<CB>(cnt, v.w >> 16, sentinel);
-                            }
-                        }
+                        if (mbar_wait(my_bar + e, (phase_bits >> e) & 1u, err)) {
+                            phase_bits ^= 1u << e;
+                            const uint8_t *const sp = my_ring + (size_t)e * entry_bytes;
+                            consume_slot<CB>(sp, cntF, cap, lane, ovf, sentinel);
+                            consume_slot<CB>(sp + slot_bytes, cntR, cap, lane, ovf, sentinel);
+                        } else
+                            dead = true;
                     }
-                    // the slot's ids are in registers / counted: its next copy may land (all lanes are past their loads)
+                    // the entry's ids are counted (every lane is past its loads): its next copies may land
                     __syncwarp();
-                    if (q + ring < q_end) issue(q + ring, slot);
-                    if (++slot == ring) slot = 0;
+                    if (p + ring < p_end) issue(p + ring, e);
+                    if (++e == ring) e = 0;
                 }
             }
         }
@@ -808,7 +827,9 @@ count_slots_kernel(const CountArgs a, const uint8_t *__restrict__ slots, const u
                 const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)tid * kLutSize + len);
                 if (M >= thr) key = pack_key(M, (uint32_t)(a.fv.bin_begin + best_bin));
             }
-            a.keys[(size_t)tid * a.n_reads + read] = key;
+            uint64_t *const dst = a.keys + (size_t)tid * a.n_reads + read;
+            if (a.keys_shared) { if (key) key_max(dst, key, 1); }          // all bin shards fold into one array (NVLink peer atomics)
+            else *dst = key;
         }
     }
 }
@@ -886,7 +907,7 @@ int postings_fill(const FilterView &fv, const uint32_t *d_ptr, uint16_t *d_ids, 
 bool slots_applicable(const FilterView &fv)
 {
     return fv.stride > 4 && fv.hp.k <= 15 && fv.n_bins_local <= 65280 && fv.hp.n_blocks > 0 &&
-           slots_counter_words(fv.n_bins_local, 8) * 8 + kPostPiece * 5 + 160 + 768 * 128 / 32 <= 200u * 1024u;
+           slots_counter_words(fv.n_bins_local, 8) * 8 + kPostPiece * 9 + 160 + 24 * (2 * 128 + 8) <= 200u * 1024u;
 }
 
 // List lengths (ids) of n_sample k-mers spread over all 4^k; d_scratch: n_sample uint32.  Synchronises the stream.
@@ -956,7 +977,8 @@ int launch_count_slots(const CountArgs &a, const uint8_t *d_slots, uint32_t slot
     const uint32_t k = a.fv.hp.k;
     const bool narrow = max_read_len != 0 && (max_read_len < k || max_read_len - k + 1 <= 255);
     const uint32_t cnt_words = (uint32_t)slots_counter_words(a.fv.n_bins_local, narrow ? 8 : 16);
-    const size_t fixed = ((size_t)2 * cnt_words * 4 + kPostPiece * 4 + kPostPiece + 32 + 127) / 128 * 128;
+    const size_t fixed = ((size_t)2 * cnt_words * 4 + kPostPiece * 8 + kPostPiece + 32 + 127) / 128 * 128;
+    const size_t entry = 2 * (size_t)slot_bytes + 8;               // both strands' slots of one position + its mbarrier
     // CTAs per SM x threads: 3 x 256, 2 x 384 or 1 x 768 (always 24 warps per SM); take the shape that keeps the most
     // bytes in flight per SM (ring slots x 24 warps, at most 8 slots per warp), preferring more CTAs on a tie
     int ring_env = 0;
@@ -968,22 +990,22 @@ int launch_count_slots(const CountArgs &a, const uint8_t *d_slots, uint32_t slot
         if (ctas_env && ctas != ctas_env) continue;
         const int warps = 24 / ctas;
         const size_t avail = (227u * 1024u) / ctas - 1024u;
-        if (fixed + (size_t)warps * (slot_bytes + 8) > avail) continue;
-        int ring = (int)std::min<size_t>(8, (avail - fixed) / ((size_t)warps * (slot_bytes + 8)));
+        if (fixed + (size_t)warps * entry > avail) continue;
+        int ring = (int)std::min<size_t>(8, (avail - fixed) / ((size_t)warps * entry));
         if (ring_env > 0) ring = std::min(ring, ring_env);
         if (ring > best_ring || (ring == best_ring && best_ctas == 0)) { best_ring = ring; best_ctas = ctas; }
-        if (ring >= 4) break;                                     // four slots of a warp in flight cover the latency
+        if (ring >= 2) break;                                     // two positions = four slots of a warp in flight cover the latency
     }
     if (!best_ctas) return -2;
     const int warps = 24 / best_ctas;
-    const size_t smem = fixed + (size_t)warps * best_ring * (slot_bytes + 8);
+    const size_t smem = fixed + (size_t)warps * best_ring * entry;
     const uint4 *ovf = reinterpret_cast<const uint4 *>(d_ovf);
     auto launch = [&](auto kernel, int threads) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
         if (occ < 1) occ = 1;
-        const uint64_t capb = (uint64_t)sm_count * occ;
+        const uint64_t capb = (uint64_t)sm_count * occ * grid_waves();
         const uint32_t gx = (uint32_t)(a.n_reads < capb ? a.n_reads : capb);
         kernel<<<gx, threads, smem, st>>>(a, d_slots, slot_bytes, ovf, cnt_words, (uint32_t)best_ring, (uint32_t)fixed, d_err);
     };
@@ -1018,7 +1040,7 @@ int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint1
         int occ = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
         if (occ < 1) occ = 1;
-        const uint64_t cap = (uint64_t)sm_count * occ;
+        const uint64_t cap = (uint64_t)sm_count * occ * grid_waves();
         const uint32_t gx = (uint32_t)(a.n_reads < cap ? a.n_reads : cap);
         kernel<<<gx, threads, smem, st>>>(a, d_ptr, ids, cnt_words);
     };

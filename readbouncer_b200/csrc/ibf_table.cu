@@ -394,7 +394,7 @@ static void launch_table_wt(const CountArgs &a, const uint64_t *table, int sm_co
         occ = o > 0 ? o : 1;
     }
     uint64_t blocks_needed = (a.n_reads + kTileWarps - 1) / kTileWarps;
-    uint64_t max_x = (uint64_t)sm_count * occ;
+    uint64_t max_x = (uint64_t)sm_count * occ * grid_waves();
     uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
     count_table_kernel<WT, U><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }
@@ -409,7 +409,7 @@ static void launch_table_bs(const CountArgs &a, const uint64_t *table, int sm_co
         occ = o > 0 ? o : 1;
     }
     uint64_t blocks_needed = (a.n_reads + kTileWarps - 1) / kTileWarps;
-    uint64_t max_x = (uint64_t)sm_count * occ;
+    uint64_t max_x = (uint64_t)sm_count * occ * grid_waves();
     uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
     count_table_bs_kernel<WT, NPA, S><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }

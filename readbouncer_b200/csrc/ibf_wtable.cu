@@ -737,7 +737,7 @@ void launch_count_one(const CountArgs &a, const uint64_t *table, int sm_count, c
         occ = o > 0 ? o : 1;
     }
     const uint64_t blocks_needed = (a.n_reads + kTileWarps - 1) / kTileWarps;
-    const uint64_t max_x = (uint64_t)sm_count * occ;
+    const uint64_t max_x = (uint64_t)sm_count * occ * grid_waves();
     const uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
     count_wtable_kernel<WT, S, G, CANON, NPA><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }
@@ -753,7 +753,7 @@ void launch_count_group(const CountArgs &a, const uint64_t *table, int sm_count,
     }
     constexpr uint64_t reads_per_cta = (uint64_t)kTileWarps * (32 / G);
     const uint64_t blocks_needed = (a.n_reads + reads_per_cta - 1) / reads_per_cta;
-    const uint64_t max_x = (uint64_t)sm_count * occ;
+    const uint64_t max_x = (uint64_t)sm_count * occ * grid_waves();
     const uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
     count_wgroup_kernel<WT, S, G, CANON, PACKED><<<gx ? gx : 1, kTileWarps * 32, 0, st>>>(a, table);
 }

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <dlfcn.h>
 #include <sys/stat.h>
 #include <vector>
 
@@ -1452,9 +1453,10 @@ int rb_ibf_insert_batch(rb_ibf *f, const char *bases, uint64_t n_bases, const ui
 }
 
 // ---- classify --------------------------------------------------------------------------------------
-int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
-                           uint32_t max_read_len, const uint16_t *d_thr_lut, uint32_t n_lut, uint64_t *d_keys,
-                           uint16_t *d_counts_fwd, uint16_t *d_counts_rev, uint8_t *d_read_flag, rb_stream stream)
+// keys_shared: d_keys is one array shared by the count kernels of all bin shards (see CountArgs::keys_shared)
+static int count_dev_impl(const rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                          uint32_t max_read_len, const uint16_t *d_thr_lut, uint32_t n_lut, uint64_t *d_keys,
+                          uint16_t *d_counts_fwd, uint16_t *d_counts_rev, uint8_t *d_read_flag, rb_stream stream, int keys_shared)
 {
     if (!f) return fail(RB_ERR_NULL_FILTER, "No IBF provided to classify the read!");
     if (n_reads == 0) return RB_OK;
@@ -1466,10 +1468,12 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     a.fv = view_of(f);
     a.bases = d_bases; a.read_off = d_read_off; a.n_reads = n_reads; a.lut = d_thr_lut; a.n_lut = n_lut;
     a.keys = d_keys; a.counts_fwd = d_counts_fwd; a.counts_rev = d_counts_rev; a.read_flag = d_read_flag;
+    a.keys_shared = keys_shared;
     const int which = g_count_kernel.load();
     const uint64_t *table = nullptr;
     if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3, n_reads);   // 3..5: table kernels
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
+    if (keys_shared && table && f->table_kind == 1) table = nullptr;      // the dense-table kernels store their keys: hashed probes fold them
     if (table && f->table_kind == 3) {
         int n = rb::launch_count_slots(a, f->d_slots, f->slot_bytes, f->d_slot_ovf, max_read_len, f->sm_count, f->d_err + 1, (cudaStream_t)stream);
         if (n == -1) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -1495,6 +1499,149 @@ int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64
     int n = rb::launch_count(a, max_read_len, which, f->sm_count, (cudaStream_t)stream);
     if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     g_launches += (uint64_t)n;
+    return RB_OK;
+}
+
+int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_read_off, uint64_t n_reads,
+                           uint32_t max_read_len, const uint16_t *d_thr_lut, uint32_t n_lut, uint64_t *d_keys,
+                           uint16_t *d_counts_fwd, uint16_t *d_counts_rev, uint8_t *d_read_flag, rb_stream stream)
+{
+    return count_dev_impl(f, d_bases, d_read_off, n_reads, max_read_len, d_thr_lut, n_lut, d_keys, d_counts_fwd, d_counts_rev,
+                          d_read_flag, stream, 0);
+}
+
+// ---- bin shards driven by ONE host process: count on every device, keys folded over NVLink into shard 0's array ----------
+int rb_ibf_count_batch_sharded(const rb_ibf *const *shards, uint32_t n_shards, const char *bases, const uint64_t *read_off,
+                               uint64_t n_reads, const uint16_t *thr_lut, uint32_t n_lut, uint16_t *max_count, uint8_t *hit,
+                               uint32_t *argmax_bin, uint8_t *read_flag)
+{
+    if (!shards || n_shards == 0) return fail(RB_ERR_NULL_FILTER, "No IBF provided to classify the read!");
+    if (n_shards > 64) return fail(RB_ERR_INVALID_ARG, "more than 64 shards");
+    for (uint32_t i = 0; i < n_shards; ++i) {
+        if (!shards[i]) return fail(RB_ERR_NULL_FILTER, "No IBF provided to classify the read!");
+        const rb_ibf *a = shards[0], *b = shards[i];
+        if (b->n_bins != a->n_bins || b->n_bits != a->n_bits || b->k != a->k || b->n_hash != a->n_hash)
+            return fail(RB_ERR_INVALID_ARG, "the handles are not shards of one filter");
+    }
+    if (n_reads == 0) return RB_OK;
+    if (!bases || !read_off || !thr_lut) return fail(RB_ERR_INVALID_ARG, "null pointer");
+    if (n_lut == 0 || n_lut > (uint32_t)rb::kMaxLut) return fail(RB_ERR_INVALID_ARG, "n_lut must be 1..4");
+    if (n_reads > 0x7FFFFFFFull) return fail(RB_ERR_INVALID_ARG, "more than 2^31-1 reads in one batch");
+    const uint64_t max_len = rb::max_read_length(read_off, n_reads);
+    if (max_len >> 63) return fail(RB_ERR_INVALID_ARG, "read offsets must be non-decreasing");
+    const uint32_t max_len32 = (uint32_t)std::min<uint64_t>(max_len, 0xFFFFFFFFu);
+    const uint64_t b0 = read_off[0], nb = read_off[n_reads] - b0, nk = (uint64_t)n_lut * n_reads;
+    const rb_ibf *root = shards[0];
+    int prev = -1;
+    cudaGetDevice(&prev);
+    struct Per { cudaStream_t st = nullptr; cudaEvent_t done = nullptr; uint8_t *d_bases = nullptr; uint64_t *d_off = nullptr;
+                 uint16_t *d_lut = nullptr; };
+    std::vector<Per> per(n_shards);
+    uint64_t *d_keys = nullptr;
+    uint8_t *d_flag = nullptr, *d_res = nullptr;
+    cudaEvent_t zeroed = nullptr;
+    auto body = [&]() -> int {
+        // shard 0's device owns the key array; every other device gets peer access to it
+        RB_CUDA(cudaSetDevice(root->device));
+        RB_CUDA(cudaStreamCreateWithFlags(&per[0].st, cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&zeroed, cudaEventDisableTiming));
+        RB_CUDA(cudaMallocAsync(&d_keys, nk * 8, per[0].st));
+        RB_CUDA(cudaMallocAsync(&d_flag, n_reads, per[0].st));
+        RB_CUDA(cudaMallocAsync(&d_res, nk * 7 + 64, per[0].st));
+        RB_CUDA(cudaMemsetAsync(d_keys, 0, nk * 8, per[0].st));
+        RB_CUDA(cudaEventRecord(zeroed, per[0].st));
+        for (uint32_t i = 0; i < n_shards; ++i) {
+            const rb_ibf *f = shards[i];
+            RB_CUDA(cudaSetDevice(f->device));
+            if (f->device != root->device) {
+                int can = 0;
+                RB_CUDA(cudaDeviceCanAccessPeer(&can, f->device, root->device));
+                if (!can) return fail(RB_ERR_INVALID_ARG, "a shard's device has no peer access to shard 0's device");
+                cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RB_ERR_CUDA, std::string("peer access: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            Per &p = per[i];
+            if (i) RB_CUDA(cudaStreamCreateWithFlags(&p.st, cudaStreamNonBlocking));
+            RB_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+            RB_CUDA(cudaMallocAsync(&p.d_bases, nb + 32, p.st));
+            RB_CUDA(cudaMallocAsync(&p.d_off, (n_reads + 1) * 8, p.st));
+            RB_CUDA(cudaMallocAsync(&p.d_lut, (size_t)n_lut * rb::kLutSize * 2, p.st));
+            RB_CUDA(cudaMemcpyAsync(p.d_bases, bases + b0, nb, cudaMemcpyHostToDevice, p.st));
+            RB_CUDA(cudaMemcpyAsync(p.d_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, p.st));
+            RB_CUDA(cudaMemcpyAsync(p.d_lut, thr_lut, (size_t)n_lut * rb::kLutSize * 2, cudaMemcpyHostToDevice, p.st));
+            g_h2d_bytes += nb + (n_reads + 1) * 8 + (size_t)n_lut * rb::kLutSize * 2;
+            RB_CUDA(cudaStreamWaitEvent(p.st, zeroed, 0));
+            const uint8_t *biased = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(p.d_bases) - (uintptr_t)b0);
+            int s2 = count_dev_impl(f, biased, p.d_off, n_reads, max_len32, p.d_lut, n_lut, d_keys, nullptr, nullptr,
+                                    i == 0 ? d_flag : nullptr, p.st, 1);
+            if (s2 != RB_OK) return s2;
+            RB_CUDA(cudaEventRecord(p.done, p.st));
+        }
+        RB_CUDA(cudaSetDevice(root->device));
+        for (uint32_t i = 1; i < n_shards; ++i) RB_CUDA(cudaStreamWaitEvent(per[0].st, per[i].done, 0));
+        uint32_t *r_amax = reinterpret_cast<uint32_t *>(d_res);
+        uint16_t *r_max = reinterpret_cast<uint16_t *>(d_res + nk * 4);
+        uint8_t *r_hit = d_res + nk * 6;
+        int nl = rb::launch_keys_decode(d_keys, nk, r_max, r_hit, r_amax, per[0].st);
+        if (nl < 0) return fail(RB_ERR_CUDA, "decode launch failed");
+        g_launches += (uint64_t)nl;
+        if (argmax_bin) RB_CUDA(cudaMemcpyAsync(argmax_bin, r_amax, nk * 4, cudaMemcpyDeviceToHost, per[0].st));
+        if (max_count) RB_CUDA(cudaMemcpyAsync(max_count, r_max, nk * 2, cudaMemcpyDeviceToHost, per[0].st));
+        if (hit) RB_CUDA(cudaMemcpyAsync(hit, r_hit, nk, cudaMemcpyDeviceToHost, per[0].st));
+        if (read_flag) RB_CUDA(cudaMemcpyAsync(read_flag, d_flag, n_reads, cudaMemcpyDeviceToHost, per[0].st));
+        g_d2h_bytes += (argmax_bin ? nk * 4 : 0) + (max_count ? nk * 2 : 0) + (hit ? nk : 0) + (read_flag ? n_reads : 0);
+        cudaError_t e = cudaStreamSynchronize(per[0].st);
+        if (e != cudaSuccess) return fail(RB_ERR_COUNT_KMER, std::string("Error counting kmers in IBF bins: ") + cudaGetErrorString(e));
+        return RB_OK;
+    };
+    int st = body();
+    const std::string keep = g_last_error;
+    for (uint32_t i = 0; i < n_shards; ++i) {                      // drain and free, also after an error
+        Per &p = per[i];
+        if (!p.st) continue;
+        cudaSetDevice(shards[i]->device);
+        cudaStreamSynchronize(p.st);
+        if (p.d_bases) cudaFreeAsync(p.d_bases, p.st);
+        if (p.d_off) cudaFreeAsync(p.d_off, p.st);
+        if (p.d_lut) cudaFreeAsync(p.d_lut, p.st);
+        if (i == 0) {
+            if (d_keys) cudaFreeAsync(d_keys, p.st);
+            if (d_flag) cudaFreeAsync(d_flag, p.st);
+            if (d_res) cudaFreeAsync(d_res, p.st);
+        }
+        cudaStreamSynchronize(p.st);
+        if (p.done) cudaEventDestroy(p.done);
+        cudaStreamDestroy(p.st);
+    }
+    if (zeroed) cudaEventDestroy(zeroed);
+    if (prev >= 0) cudaSetDevice(prev);
+    cudaGetLastError();
+    g_last_error = keep;
+    return st;
+}
+
+// ---- bin shards, one process per GPU: the combine as one NCCL call (libnccl is looked up at run time) ----------------------
+int rb_keys_combine_nccl(void *nccl_comm, uint64_t *d_keys, uint64_t n, rb_stream stream)
+{
+    if (!nccl_comm || !d_keys) return fail(RB_ERR_INVALID_ARG, "null communicator or keys");
+    if (n == 0) return RB_OK;
+    // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t)
+    typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    static allreduce_fn fn = [] {
+        // the process usually has NCCL loaded already (its own link, or torch's bundled copy): take that one
+        void *sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+        if (!sym) {
+            void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (h) sym = dlsym(h, "ncclAllReduce");
+        }
+        return reinterpret_cast<allreduce_fn>(sym);
+    }();
+    if (!fn) return fail(RB_ERR_INVALID_ARG, "libnccl.so.2 not found (ncclAllReduce)");
+    // keys < 2^49: MAX over uint64; nccl.h: ncclUint64 = 5, ncclMax = 2
+    const int r = fn(d_keys, d_keys, (size_t)n, 5, 2, nccl_comm, (cudaStream_t)stream);
+    if (r != 0) return fail(RB_ERR_CUDA, "ncclAllReduce failed with ncclResult " + std::to_string(r));
     return RB_OK;
 }
 

@@ -178,6 +178,18 @@ def test_cpp_shim_on_gpu(tmp_path, golden_ibf_paths, known):
     assert out.returncode == 0 and "gpu OK" in out.stdout, out.stdout + out.stderr
 
 
+@pytest.mark.gpu
+def test_cpp_host_bin_sharded_combine(tmp_path):
+    """A C++ host with nothing but the C ABI: whole filter == rb_ibf_count_batch_sharded (keys folded over NVLink peer
+    memory; 2 shards per visible device) == per-rank count + rb_keys_combine_nccl (when there are >= 2 GPUs)."""
+    exe = str(tmp_path / "test_shard_combine")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + INCLUDE, "-I/usr/local/cuda/include",
+                           os.path.join(ROOT, "tests", "cpp", "test_shard_combine.cpp"), "-o", exe, "-L" + LIBDIR, "-lrb_ibf",
+                           "-Wl,-rpath," + LIBDIR, "-L/usr/local/cuda/lib64", "-lcudart", "-lnccl"])
+    out = subprocess.run([exe, "3000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "shard combine OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_reference_arm_prints_the_contract_line():
     """bench.py --impl reference (the CPU oracle port on all host cores) on a small workload: one JSON line with the
     contract's keys, no GPU work, and -- under a multi-rank launch -- nothing from ranks other than 0."""

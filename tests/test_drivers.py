@@ -92,46 +92,7 @@ def test_classify_usage_on_reference_fixture(tmp_path, golden_ibf_paths, chunk, 
     assert len(un) == 3 - found
 
 
-def _expected_classify_reads(reads, dep, tgt, chunk, max_chunks, err):
-    """src/main/classify.hpp:229-303 read by read with the oracle."""
-    assign = []
-    for seq in reads:
-        if len(seq) < chunk:
-            assign.append(-4)
-            continue
-        a = -1
-        for i in range(max_chunks):
-            if i * chunk >= len(seq):
-                break
-            frag = seq[i * chunk:min((i + 1) * chunk, len(seq))]
-            if dep and tgt:
-                t0, d0 = oracle.classify_pair(tgt, dep, frag, err)
-                ok = False
-                if t0 > 0:
-                    if d0 > 0:
-                        t1, d1 = oracle.classify_pair(tgt, dep, frag, err - 0.02)
-                        ok = t1 > 0 and d1 == 0
-                    else:
-                        ok = True
-                if ok:
-                    a = oracle.classify_best(tgt, frag, err)
-            elif dep:
-                if len(frag) < dep[0].k:
-                    a = -3
-                    break
-                if oracle.classify_best(dep, frag, err) > -1:
-                    a = -2
-            else:
-                if len(frag) < tgt[0].k:
-                    a = -3
-                    break
-                b = oracle.classify_best(tgt, frag, err)
-                if b != -1:
-                    a = b
-            if a != -1:
-                break
-        assign.append(a)
-    return assign
+_expected_classify_reads = oracle.classify_reads_serial      # src/main/classify.hpp:229-303 read by read with the oracle
 
 
 @pytest.mark.gpu

@@ -153,7 +153,7 @@ def test_config5_per_rank_shape_vs_oracle():
     # the oracle holds the same column slice as a filter of its own: same rows, local bin ids
     of = oracle.OracleIBF.create(per_bins, 3, k, gf.n_blocks * 64 * gf.col_words)
     assert of.n_blocks == gf.n_blocks and of.bin_width == gf.col_words
-    of.words()[:gf.n_local_words] = gf.download()
+    of.words()[:gf.n_blocks * gf.col_words] = gf.download()[:gf.n_blocks * gf.col_words]
     pick = np.sort(np.random.default_rng(9).choice(n, SAMPLE, replace=False))
     sb = bases.reshape(n, chunk)[pick].reshape(-1)
     so = np.arange(SAMPLE + 1, dtype=np.uint64) * np.uint64(chunk)

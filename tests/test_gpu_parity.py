@@ -424,6 +424,33 @@ def test_create_shard_builds_a_column_slice_in_place():
     assert np.array_equal(mx, exp["max_count"]) and np.array_equal(hit, exp["hit"]) and np.array_equal(am, exp["argmax_bin"])
 
 
+@pytest.mark.parametrize("n_shards,tables", [(2, False), (3, True), (5, True)])
+def test_sharded_call_folds_keys_into_one_array(n_shards, tables):
+    """rb_ibf_count_batch_sharded: every shard's count kernel folds its keys into shard 0's key array (atomicMax; over
+    NVLink when the shards sit on different devices -- here round-robin over the visible ones), == whole filter == oracle.
+    Without tables the streaming kernel runs, with tables the slot kernel; narrow shards take the hashed-probe kernel."""
+    plan, of, gf = make_filter_pair(1, 700 * 2000 + 7, 2000, 13)            # 701 bins, 11 row words
+    bases, off = synth.ragged_reads(plan["bases"], [250] * 300 + [0, 5, 12, 13, 400, 1000], seed=9, frac_from_ref=0.7, n_frac=0.002)
+    luts = np.stack([rb.threshold_lut(0.1, 13), rb.threshold_lut(0.08, 13)])
+    n_dev = rb.device_count()
+    shards = []
+    for s_ in range(n_shards):
+        sh = rb.IBF.create_shard(plan["n_bins"], 3, 13, plan["n_bits"], s_, n_shards, device=s_ % n_dev)
+        sh.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
+        shards.append(sh)
+    if tables:
+        rb.enable_kmer_tables(shards)
+        assert [s.kmer_table_kind() for s in shards] == [3 if s.col_words > 4 else 1 for s in shards]
+    got = rb.count_batch_sharded(shards, bases, off, luts)
+    whole = gf.count_batch(bases, off, luts)
+    for t in range(2):
+        exp = of.count_batch(bases, off, luts[t], dense=False, n_threads=4)
+        for key in ("max_count", "hit", "argmax_bin"):
+            assert np.array_equal(got[key][t], exp[key]), (t, key)
+            assert np.array_equal(whole[key][t], exp[key])
+    assert np.array_equal(got["read_flag"], exp["short_read"])
+
+
 def test_two_threshold_tables_in_one_pass():
     plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
     bases, off, _ = synth.sample_reads(plan["bases"], 3000, 250, seed=5, error_rate=0.12)

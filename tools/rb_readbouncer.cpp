@@ -27,7 +27,8 @@ int main(int argc, char **argv)
         int rc = rbdrv::run_program(c, &r);
         if (rc == 0 && c.usage == "classify")
             std::cout << "RESULT found=" << r.found << " failed=" << r.failed << " too_short=" << r.too_short
-                      << " reads=" << r.readCounter << std::endl;
+                      << " reads=" << r.readCounter << " avg_classify_s=" << r.avgClassifyduration << " read_file_s=" << r.readFileSeconds
+                      << " table_setup_s=" << r.tableSetupSeconds << std::endl;
         return rc;
     } catch (const std::exception &e) {
         std::cerr << "[Error] " << e.what() << std::endl;
