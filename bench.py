@@ -57,7 +57,8 @@ WORKLOADS = {
                                        reads=16_384, bins_per_rank=512),
 }
 DEFAULT_WORKLOAD = "cfg2_100x4Mb_100bins"
-SECONDARY_1GPU = ["cfg3_3.1Gb_31kbins", "cfg2_k15", "cfg2_k17"]
+SECONDARY_1GPU = ["cfg3_3.1Gb_31kbins", "cfg2_k15", "cfg2_k17", "readme_3targets_1deplete"]
+README_READS = 100_000      # the reference's one published workload (README.md:233-262), tools/readme_bench.py
 SECONDARY_NGPU = ["cfg5_3.7Gb_37kbins_per_gpu"]
 ERROR_RATE = 0.1
 SIGNIFICANCE = 0.95
@@ -556,6 +557,12 @@ def run_workload(env, args, name, n_reads, steps, warmup, role):
             # ascii_bound = chunks/s if the ASCII input crossed at that rate with nothing else in the way.
             ceil_gbs = h2d_ceiling(env)
             e2e["h2d_ceiling_gbs"] = ceil_gbs
+            # ... and how fast this rank's packer threads can stream-read the input at all (all ranks at the same time)
+            env.barrier()
+            g, = env.max_over_ranks(-rb.capi.host_read_gbs(hb))
+            e2e["host_read_gbs_per_rank_min"] = -g
+            e2e["host_read_note"] = "packer threads stream-reading the step's input, no work, no stores; the packed path reads the input " \
+                                    "once and writes + DMA-reads 3/8 of it again"
             e2e["h2d_achieved_gbs"] = world * h2d_step / (e2e_s / steps) / 1e9
             e2e["host_input_gbs"] = world * e2e["host_input_bytes_per_step"] / (e2e_s / steps) / 1e9
             e2e["ascii_bound_chunks_per_s"] = ceil_gbs * 1e9 / (e2e["host_input_bytes_per_step"] / n_reads)
@@ -749,12 +756,23 @@ def main():
     out = run_workload(env, args, name, n_reads, args.steps, args.warmup, "primary")
     release(env)
     sec_names = []
+    secondary = []
     if args.secondary is not None:
         sec_names = [s for s in args.secondary.split(",") if s]
     elif not explicit and not args.no_secondary and args.mode == "read_sharded" and args.kernel == 0:
         sec_names = SECONDARY_1GPU if env.world == 1 else SECONDARY_NGPU
-    secondary = []
     for s in sec_names:
+        if s.startswith("readme_"):
+            # the reference's published use case: 3 target + 1 depletion filter, FASTA in -> files out through the C++ driver
+            if env.rank == 0:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import readme_bench
+                n = int(s.split(":")[1]) if ":" in s else README_READS
+                t0 = time.time()
+                r = readme_bench.run(n)
+                r["wall_s"] = time.time() - t0
+                secondary.append(r)
+            continue
         sw = WORKLOADS[s]
         t0 = time.time()
         r = run_workload(env, args, s, sw["reads"], max(3, min(args.steps, 10)), 3, "secondary")

@@ -246,6 +246,13 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
     const clk::time_point t_setup = clk::now();
     enable_kmer_tables(DepletionFilters, TargetFilters);      // one plan for all filters, before the first read
     const double table_setup_s = secs(t_setup, clk::now());
+    for (const std::vector<IBFMeta> *v : {&TargetFilters, &DepletionFilters})
+        for (const IBFMeta &f : *v) {
+            rb_ibf_info_t info{};
+            if (f.filter && rb_ibf_info(f.filter.get(), &info) == RB_OK)
+                std::cerr << "k-mer table: " << f.name << " bins=" << info.n_bins << " kind=" << info.kmer_table_kind << " span="
+                          << info.kmer_table_span << " bytes=" << info.kmer_table_bytes << std::endl;
+        }
     ClassificationResults res;
     std::filesystem::create_directories(config.output_dir);
 
@@ -339,13 +346,27 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
         std::vector<std::ofstream> targetFastas;
         for (IBFMeta &f : TargetFilters) targetFastas.emplace_back(config.output_dir / (f.name + ".fasta"));
         std::ofstream unclassified(config.output_dir / "unclassified.fasta");
+        std::vector<std::string> tbuf(TargetFilters.size());
+        std::string ubuf;
         for (size_t r = 0; r < n; ++r) {
             const int a = res.assignment[r];
-            if (a >= 0) targetFastas[a] << ">" << reads[r].id << std::endl << reads[r].seq << std::endl;
-            else if (a == -1) {                                 // seqan::writeRecord(out, id, (Dna5String) seq): 70 columns
-                unclassified << ">" << reads[r].id << "\n";
-                const std::string d = to_dna5_string(reads[r].seq);
-                for (size_t p = 0; p < d.size(); p += 70) unclassified << d.substr(p, 70) << "\n";
+            if (a >= 0) {                                       // same bytes as `<< ">" << id << endl << seq << endl`, one write
+                std::string &b = tbuf[a];
+                b.append(1, '>').append(reads[r].id).append(1, '\n').append(reads[r].seq).append(1, '\n');
+                if (b.size() > (8u << 20)) { targetFastas[a].write(b.data(), (std::streamsize)b.size()); b.clear(); }
+            } else if (a == -1) {                               // seqan::writeRecord(out, id, (Dna5String) seq): 70 columns
+                ubuf.append(1, '>').append(reads[r].id).append(1, '\n');
+                const std::string &q = reads[r].seq;
+                for (size_t p = 0; p < q.size(); p += 70) {
+                    const size_t e = std::min(q.size(), p + 70), o = ubuf.size();
+                    ubuf.append(q, p, e - p);
+                    for (size_t i = o; i < ubuf.size(); ++i) {  // the Dna5String cast: A C G T (U = T), everything else N
+                        const char c = ubuf[i] & 0xDF;
+                        ubuf[i] = (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? c : (c == 'U' ? 'T' : 'N');
+                    }
+                    ubuf.append(1, '\n');
+                }
+                if (ubuf.size() > (8u << 20)) { unclassified.write(ubuf.data(), (std::streamsize)ubuf.size()); ubuf.clear(); }
             }
         }
         // the reference's per-read timer covers the chunk loop, the decision and the output record of a read; here the same work

@@ -81,8 +81,8 @@ typedef struct rb_ibf_info_t {
     int32_t shard, n_shards;
     int32_t kmer_table_span;   /* consecutive k-mers per table entry (1..4), 0 if not built */
     uint64_t kmer_table_bytes; /* bytes of the k-mer table, 0 if not built */
-    int32_t kmer_table_kind;   /* 0 none, 1 dense k-mer / window table (rows <= 4 words), wider rows: 3 postings in fixed
-                                  slots per k-mer (default), 2 postings as pointer + lists (RB_POSTINGS_LAYOUT=lists) */
+    int32_t kmer_table_kind;   /* 0 none, 1 dense k-mer / window table (rows <= 4 words), wider rows: 2 postings as pointer +
+                                  lists (default), 3 postings in fixed slots per k-mer (RB_POSTINGS_LAYOUT=slots) */
 } rb_ibf_info_t;
 
 /* ---- host-side scalar helpers (FP64, bit-exact with the reference) ------- */
@@ -180,6 +180,9 @@ RB_API int rb_ibf_count_batch(const rb_ibf *f, const char *bases, const uint64_t
  * PCIe transfer (env RB_HOST_THREADS, default min(cores, 16); RB_HOST_PACK=0 ships ASCII instead) and
  * the packer's instruction set (0 scalar, 2 AVX2, 5 AVX-512 BW+VBMI; env RB_HOST_PACK_ISA caps it). */
 RB_API int rb_host_pack_info(int *threads, int *isa);
+/* Measurement aid: the packer's host threads stream-read n_bytes of `buf` `reps` times (its access pattern without its
+ * work or its stores); GB/s of host memory the packer can see.  bench.py reports it next to the end-to-end rate. */
+RB_API int rb_microbench_host_read(const void *buf, uint64_t n_bytes, uint32_t reps, double *gb_per_s);
 /* Bytes rb_ibf_count_batch has moved over PCIe since the library was loaded (all threads): host->device
  * copies (bit planes or ASCII bases, offsets, thresholds) and device->host results (copies or mapped stores). */
 RB_API int rb_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
@@ -247,9 +250,10 @@ RB_API int rb_keys_combine_nccl(void *nccl_comm, uint64_t *d_keys, uint64_t n, r
  * Wide filters (rows > 4 words, <= 65280 local bins, k <= 15) get a POSTINGS table instead: the AND of
  * the probed rows is ~1 % dense by the reference's own sizing, so the list of set bins of every
  * k-mer (2 bytes each, ~50 GB for a human-genome filter at k=13) replaces streaming 2*h rows of
- * thousands of bytes per position; same policy, budget and env switches.  Every k-mer owns a fixed,
- * 128-byte-aligned slot (its size chosen from the sampled list lengths; the few longer lists go to an
- * overflow area), which the lookup kernel fetches with one bulk copy into a shared-memory ring.
+ * thousands of bytes per position; same policy, budget and env switches.  Two layouts: pointer + lists
+ * of 16-byte units read straight into registers (default), or (RB_POSTINGS_LAYOUT=slots) a fixed,
+ * 128-byte-aligned slot per k-mer (size chosen from the sampled list lengths; the few longer lists go to an
+ * overflow area) fetched by one bulk copy into a shared-memory ring.
  *
  * SUPPORTED ENVELOPE of the table paths (outside it results are the same, from the hashed / streaming kernels):
  *   rows <= 2 words (<= 128 bins): window tables for k + span - 1 <= 16, i.e. span 3 up to k = 14, span 2 up to k = 15,

@@ -32,6 +32,7 @@ EXPORTS = [
     "rb_ibf_enable_kmer_table", "rb_ibf_resize_bins", "rb_host_pack_info", "rb_transfer_bytes",
     "rb_ibf_transfer_policy", "rb_ibf_count_traffic_dev", "rb_synth_bases_dev",
     "rb_ibf_enable_kmer_tables", "rb_threshold_lut_raw", "rb_ibf_count_batch_sharded", "rb_keys_combine_nccl",
+    "rb_microbench_host_read",
 ]
 
 
@@ -120,6 +121,7 @@ def lib():
         "rb_threshold_lut_raw": (i32, [dbl, dbl, u32, vp]),
         "rb_ibf_count_batch_sharded": (i32, [vp, u32, vp, vp, u64, vp, u32, vp, vp, vp, vp]),
         "rb_keys_combine_nccl": (i32, [vp, vp, u64, vp]),
+        "rb_microbench_host_read": (i32, [vp, u64, u32, vp]),
     }
     assert sorted(sig) == sorted(EXPORTS)
     for name, (res, args) in sig.items():
@@ -187,6 +189,13 @@ def microbench_gather_coop(d_buf, n_rows, row_bytes, lane_bytes, probes_per_grou
 def synth_bases_dev(d_out, n, seed, start=0, stream=None):
     """n synthetic bases of stream `seed` from position `start` into a device buffer (see synth.hash_bases for the host twin)."""
     _check(lib().rb_synth_bases_dev(_dev_ptr(d_out), int(n), int(seed), int(start), _stream_ptr(stream)))
+
+
+def host_read_gbs(buf, reps=4):
+    """GB/s at which the packer's host threads stream-read a numpy buffer (rb_microbench_host_read)."""
+    g = C.c_double(0)
+    _check(lib().rb_microbench_host_read(_np_ptr(buf), buf.nbytes, reps, C.byref(g)))
+    return float(g.value)
 
 
 def host_pack_info():

@@ -303,4 +303,46 @@ void parallel_tasks(size_t n_tasks, const std::function<void(size_t)> &fn, const
 
 int host_threads() { return pool().size(); }
 
+#if defined(__x86_64__)
+namespace {
+__attribute__((target("avx2"))) uint64_t sum_avx2(const uint8_t *p, size_t n)
+{
+    __m256i a = _mm256_setzero_si256(), b = a, c = a, d = a;
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        _mm_prefetch(reinterpret_cast<const char *>(p + i) + 2048, _MM_HINT_T0);
+        a = _mm256_xor_si256(a, _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p + i)));
+        b = _mm256_xor_si256(b, _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p + i + 32)));
+        c = _mm256_xor_si256(c, _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p + i + 64)));
+        d = _mm256_xor_si256(d, _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p + i + 96)));
+    }
+    a = _mm256_xor_si256(_mm256_xor_si256(a, b), _mm256_xor_si256(c, d));
+    alignas(32) uint64_t v[4];
+    _mm256_store_si256(reinterpret_cast<__m256i *>(v), a);
+    uint64_t r = v[0] ^ v[1] ^ v[2] ^ v[3];
+    for (; i < n; ++i) r ^= p[i];
+    return r;
+}
+}  // namespace
+#endif
+
+uint64_t stream_read(const uint8_t *buf, size_t n)
+{
+    constexpr size_t kTask = 128u << 10;
+    const size_t n_tasks = (n + kTask - 1) / kTask;
+    std::atomic<uint64_t> acc{0};
+    auto task = [&](size_t t) {
+        const size_t o = t * kTask, m = std::min(kTask, n - o);
+        uint64_t r = 0;
+#if defined(__x86_64__)
+        if (g_isa >= 2) r = sum_avx2(buf + o, m);
+        else
+#endif
+            for (size_t i = 0; i < m; ++i) r ^= buf[o + i];
+        acc.fetch_xor(r, std::memory_order_relaxed);
+    };
+    pool().run(n_tasks, task, nullptr);
+    return acc.load();
+}
+
 }  // namespace rb

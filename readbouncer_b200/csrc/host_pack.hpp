@@ -32,4 +32,8 @@ void parallel_tasks(size_t n_tasks, const std::function<void(size_t)> &fn, const
 
 int host_threads();   // pool size + 1 (the caller)
 
+// Measurement aid: the pool's threads stream-read buf[0, n) once (the packer's access pattern without its work or its
+// stores); returns a checksum so the loads stay.  Tells how much of the packer's time is the host memory system.
+uint64_t stream_read(const uint8_t *buf, size_t n);
+
 }  // namespace rb

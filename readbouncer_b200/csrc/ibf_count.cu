@@ -454,7 +454,7 @@ int grid_waves()
     static const int waves = [] {
         const char *e = std::getenv("RB_GRID_WAVES");
         const int v = e ? std::atoi(e) : 0;
-        return v > 0 ? (v > 64 ? 64 : v) : 1;
+        return v > 0 ? (v > 256 ? 256 : v) : 16;
     }();
     return waves;
 }

@@ -864,7 +864,9 @@ int postings_sample_units(const FilterView &fv, uint32_t *d_scratch, uint32_t n_
                           cudaStream_t st)
 {
     const uint64_t n_kmers = 1ull << (2 * fv.hp.k);
-    const uint64_t step = n_kmers / n_sample ? n_kmers / n_sample : 1;
+    // an odd step visits k-mers of every suffix (a power-of-two stride would fix the low bases of all samples)
+    uint64_t step = n_kmers / n_sample ? n_kmers / n_sample : 1;
+    if (step > 2) step |= 1;
     postings_count_kernel<<<sm_count * 8, 256, 0, st>>>(fv, step / 2, step, n_sample, d_scratch);
     std::vector<uint32_t> h(n_sample);
     if (cudaMemcpyAsync(h.data(), d_scratch, (size_t)n_sample * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
@@ -875,13 +877,32 @@ int postings_sample_units(const FilterView &fv, uint32_t *d_scratch, uint32_t n_
     return 1;
 }
 
+// exact 64-bit total of the list sizes (the scan below works in uint32: a table of 2^32 units or more must be refused, not wrapped)
+__global__ void __launch_bounds__(256) sum_units_kernel(const uint32_t *__restrict__ units, uint64_t n, unsigned long long *total)
+{
+    unsigned long long t = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) t += units[i];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(total, t);
+}
+
 // Pass 1 + scan: d_ptr[4^k + 1] (uint32 units).  Returns launches or < 0; *total_units = d_ptr[4^k] (host), stream synchronised.
 int postings_build_ptr(const FilterView &fv, uint32_t *d_ptr, uint64_t *total_units, int sm_count, cudaStream_t st)
 {
     const uint64_t n_kmers = 1ull << (2 * fv.hp.k);
     postings_count_kernel<<<sm_count * 16, 256, 0, st>>>(fv, 0, 1, n_kmers, d_ptr);
     if (cudaMemsetAsync(d_ptr + n_kmers, 0, 4, st) != cudaSuccess) return -1;
-    // the table never exceeds 2^32 units (64 GiB of ids): the caller checked the sampled estimate; a wrap would show below
+    // the table must stay below 2^32 units (64 GiB of ids): the caller's sampled estimate can be off, so count exactly
+    {
+        unsigned long long *d_total = nullptr, h_total = 0;
+        if (cudaMallocAsync(&d_total, sizeof(h_total), st) != cudaSuccess) return -1;
+        cudaMemsetAsync(d_total, 0, sizeof(h_total), st);
+        sum_units_kernel<<<sm_count * 8, 256, 0, st>>>(d_ptr, n_kmers, d_total);
+        cudaMemcpyAsync(&h_total, d_total, sizeof(h_total), cudaMemcpyDeviceToHost, st);
+        cudaFreeAsync(d_total, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+        if (h_total >= 0xFFFFFFF0ull) return -1;
+    }
     void *d_tmp = nullptr;
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_ptr, d_ptr, n_kmers + 1, st);
@@ -892,7 +913,7 @@ int postings_build_ptr(const FilterView &fv, uint32_t *d_ptr, uint64_t *total_un
     if (cudaMemcpyAsync(&last, d_ptr + n_kmers, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
     *total_units = last;
-    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+    return cudaGetLastError() == cudaSuccess ? 3 : -1;
 }
 
 int postings_fill(const FilterView &fv, const uint32_t *d_ptr, uint16_t *d_ids, int sm_count, cudaStream_t st)

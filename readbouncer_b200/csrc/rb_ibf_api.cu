@@ -296,7 +296,7 @@ uint64_t postings_estimate_bytes(const rb_ibf *f, cudaStream_t st)
     const uint32_t n_sample = (uint32_t)std::min<uint64_t>(65536, n_kmers);
     uint32_t *d_tmp = nullptr;
     const char *lay = std::getenv("RB_POSTINGS_LAYOUT");
-    if (!(lay && lay[0] == 'l') && rb::slots_applicable(fv)) {
+    if (lay && lay[0] == 's' && rb::slots_applicable(fv)) {
         if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); return 0; }
         std::vector<uint32_t> lengths;
         const int r0 = rb::slots_sample_lengths(fv, d_tmp, n_sample, &lengths, f->sm_count, st);
@@ -342,10 +342,13 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>((uint64_t)(free_b * 0.6), cap);
     if (f->col_words > 4) {
         const rb::FilterView fv = view_of(f);
-        // wide rows: postings.  Default layout: one fixed slot per k-mer (bulk copies into shared-memory rings);
-        // RB_POSTINGS_LAYOUT=lists keeps the pointer + variable-length lists of round 1 (A/B measurements).
+        // wide rows: postings.  Default layout: pointer + variable-length lists, loaded straight into registers.
+        // RB_POSTINGS_LAYOUT=slots: one fixed slot per k-mer fetched by bulk copies into shared-memory rings -- fewer DRAM bytes
+        // and no pointer chase, but the counting is bound by the shared-memory pipe (ATOMS wavefronts), and staging the lists
+        // through shared memory adds a third to its load: measured 6.8 ms against 6.3 ms per 65 536 chunks on BASELINE
+        // config #3 (profiles/r2_c_slots_cfg3_ncu.json), so it stays opt-in.
         const char *lay = std::getenv("RB_POSTINGS_LAYOUT");
-        const bool want_slots = !(lay && lay[0] == 'l');
+        const bool want_slots = lay && lay[0] == 's';
         if (want_slots && rb::slots_applicable(fv)) {
             const uint64_t n_kmers = 1ull << (2 * f->k);
             const uint32_t n_sample = (uint32_t)std::min<uint64_t>(65536, n_kmers);
@@ -1732,6 +1735,17 @@ int rb_transfer_bytes(uint64_t *h2d, uint64_t *d2h)
 {
     if (h2d) *h2d = g_h2d_bytes.load();
     if (d2h) *d2h = g_d2h_bytes.load();
+    return RB_OK;
+}
+
+int rb_microbench_host_read(const void *buf, uint64_t n_bytes, uint32_t reps, double *gb_per_s)
+{
+    if (!buf || !gb_per_s || n_bytes == 0 || reps == 0) return fail(RB_ERR_INVALID_ARG, "null buffer");
+    volatile uint64_t sink = rb::stream_read(static_cast<const uint8_t *>(buf), (size_t)n_bytes);      // warm the pool
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t r = 0; r < reps; ++r) sink = sink ^ rb::stream_read(static_cast<const uint8_t *>(buf), (size_t)n_bytes);
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *gb_per_s = (double)n_bytes * reps / s / 1e9;
     return RB_OK;
 }
 

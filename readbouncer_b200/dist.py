@@ -28,12 +28,12 @@ def bin_shard_columns(bin_width, rank, world):
 
 def per_rank_bin_ranges(bins_per_rank, world):
     """Bin ranges [lo, hi) of the column slices when every rank contributes `bins_per_rank` bins (a multiple of 64) to ONE
-    filter that is built slice by slice (rb_ibf_create_shard): the filter has world * bins_per_rank bins and
-    world * bins_per_rank / 64 + 1 row words (IBFBuild.cpp:404-413 reserves one more 64-bin word); slice r starts exactly at
-    bin r * bins_per_rank, and the last slice also holds the spare word."""
+    filter that is built slice by slice (rb_ibf_create_shard): the filter has world * bins_per_rank bins in
+    ceil(bins / 64) = world * bins_per_rank / 64 row words (derive_geometry in the C ABI), split evenly, so slice r is
+    exactly the bins [r * bins_per_rank, (r + 1) * bins_per_rank)."""
     assert bins_per_rank % 64 == 0 and bins_per_rank > 0
     n_bins = bins_per_rank * world
-    bin_width = n_bins // 64 + 1
+    bin_width = (n_bins + 63) // 64
     out = []
     for r in range(world):
         b, w = bin_shard_columns(bin_width, r, world)
@@ -42,7 +42,9 @@ def per_rank_bin_ranges(bins_per_rank, world):
 
 
 def combine_keys(keys, group=None):
-    """In-place elementwise MAX of packed summary keys across ranks (int64 tensor; keys are < 2^49)."""
+    """In-place elementwise MAX of packed summary keys across ranks (int64 tensor; keys are < 2^49).  The C-ABI twins for
+    a C++ host: rb_keys_combine_nccl (one process per GPU) and rb_ibf_count_batch_sharded (one process, keys folded over
+    NVLink peer memory by the count kernels themselves)."""
     assert keys.dtype == torch.int64
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)

@@ -108,7 +108,7 @@ def test_config3_and_config4_full_size_vs_oracle():
     bases, off, from_ref = synth.sample_reads(ref, n, chunk, seed=1234)
     luts = np.stack([rb.threshold_lut(0.1, k), rb.threshold_lut(0.08, k)])
     keys = _classify_dev(gf, bases, off, luts, chunk, torch)
-    assert gf.kmer_table_kind() == 3                                   # postings in slots
+    assert gf.kmer_table_kind() == 2                                   # postings
     mx, hit, am = rb.keys_decode(keys)
     of = oracle.OracleIBF.create(plan["n_bins"], 3, k, plan["n_bits"])
     of.words()[:plan["n_bits"] // 64] = words
@@ -148,7 +148,7 @@ def test_config5_per_rank_shape_vs_oracle():
     bases, off, from_ref = synth.sample_reads(src, n, chunk, seed=1234)
     luts = np.stack([rb.threshold_lut(0.1, k), rb.threshold_lut(0.08, k)])
     keys = _classify_dev(gf, bases, off, luts, chunk, torch)
-    assert gf.kmer_table_kind() == 3                                   # postings in slots
+    assert gf.kmer_table_kind() == 2                                   # postings
     mx, hit, am = rb.keys_decode(keys)
     # the oracle holds the same column slice as a filter of its own: same rows, local bin ids
     of = oracle.OracleIBF.create(per_bins, 3, k, gf.n_blocks * 64 * gf.col_words)
@@ -267,5 +267,5 @@ def test_bench_default_line_shape_with_secondary():
         assert r["traffic"] > 0 and abs(r["frac"] - r["traffic"] / (r["kernel_ms"] * 1e-3) / 1e9 / r["peak"]) < 1e-9
         assert "oracle" in e["parity"] and "host_call" in e["parity"]
         assert e["config"]["cold_first_call_ms"] > 0 and e["e2e"]["value"] > 0
-    assert d["secondary"][0]["roofline"]["kernel"] == "count_slots_kernel" and "build" in d["secondary"][0]["parity"]
+    assert d["secondary"][0]["roofline"]["kernel"] == "count_postings_kernel" and "build" in d["secondary"][0]["parity"]
     assert d["e2e"]["h2d_ceiling_gbs"] > 1

@@ -161,7 +161,7 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
             sb[int(so[5]):int(so[6])] = ord("N")
             sb[int(so[7]) + 100] = ord("U")
             sexp = of.count_batch(sb, so, lut, n_threads=4)
-            # slots: one fixed slot per k-mer fetched by bulk copies (default); lists: pointer + variable-length lists
+            # lists: pointer + variable-length lists (default); slots: one fixed slot per k-mer fetched by bulk copies
             for layout, kind in (("slots", 3), ("lists", 2)):
                 os.environ["RB_POSTINGS_LAYOUT"] = layout
                 try:
@@ -305,6 +305,7 @@ def test_postings_slots(n_blocks, order, slot_bytes, ring, monkeypatch):
     """The same over-full filters through the SLOT layout: the sampled slot size (0) and forced ones -- 128 / 256 bytes push most
     / many lists into the overflow area, 1 024 holds nearly all -- with ring depths 1 and 2 next to the default."""
     monkeypatch.setenv("RB_POSTINGS_ORDER", order)
+    monkeypatch.setenv("RB_POSTINGS_LAYOUT", "slots")
     if slot_bytes:
         monkeypatch.setenv("RB_SLOT_BYTES", str(slot_bytes))
     if ring:
@@ -424,11 +425,12 @@ def test_create_shard_builds_a_column_slice_in_place():
     assert np.array_equal(mx, exp["max_count"]) and np.array_equal(hit, exp["hit"]) and np.array_equal(am, exp["argmax_bin"])
 
 
-@pytest.mark.parametrize("n_shards,tables", [(2, False), (3, True), (5, True)])
-def test_sharded_call_folds_keys_into_one_array(n_shards, tables):
+@pytest.mark.parametrize("n_shards,tables", [(2, ""), (3, "lists"), (5, "lists"), (3, "slots")])
+def test_sharded_call_folds_keys_into_one_array(n_shards, tables, monkeypatch):
     """rb_ibf_count_batch_sharded: every shard's count kernel folds its keys into shard 0's key array (atomicMax; over
     NVLink when the shards sit on different devices -- here round-robin over the visible ones), == whole filter == oracle.
-    Without tables the streaming kernel runs, with tables the slot kernel; narrow shards take the hashed-probe kernel."""
+    Without tables the streaming kernel runs, with tables the postings kernel of either layout; narrow shards take the
+    hashed-probe kernel."""
     plan, of, gf = make_filter_pair(1, 700 * 2000 + 7, 2000, 13)            # 701 bins, 11 row words
     bases, off = synth.ragged_reads(plan["bases"], [250] * 300 + [0, 5, 12, 13, 400, 1000], seed=9, frac_from_ref=0.7, n_frac=0.002)
     luts = np.stack([rb.threshold_lut(0.1, 13), rb.threshold_lut(0.08, 13)])
@@ -439,8 +441,9 @@ def test_sharded_call_folds_keys_into_one_array(n_shards, tables):
         sh.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
         shards.append(sh)
     if tables:
+        monkeypatch.setenv("RB_POSTINGS_LAYOUT", tables)
         rb.enable_kmer_tables(shards)
-        assert [s.kmer_table_kind() for s in shards] == [3 if s.col_words > 4 else 1 for s in shards]
+        assert [s.kmer_table_kind() for s in shards] == [(2 if tables == "lists" else 3) if s.col_words > 4 else 1 for s in shards]
     got = rb.count_batch_sharded(shards, bases, off, luts)
     whole = gf.count_batch(bases, off, luts)
     for t in range(2):
