@@ -769,13 +769,21 @@ def main():
                 import readme_bench
                 n = int(s.split(":")[1]) if ":" in s else README_READS
                 t0 = time.time()
-                r = readme_bench.run(n)
+                try:
+                    r = readme_bench.run(n)
+                except Exception as e:                      # a failed secondary must not cost the primary line
+                    r = {"workload": s, "error": "%s: %s" % (type(e).__name__, e)}
                 r["wall_s"] = time.time() - t0
                 secondary.append(r)
             continue
         sw = WORKLOADS[s]
         t0 = time.time()
-        r = run_workload(env, args, s, sw["reads"], max(3, min(args.steps, 10)), 3, "secondary")
+        try:
+            r = run_workload(env, args, s, sw["reads"], max(3, min(args.steps, 10)), 3, "secondary")
+        except Exception as e:
+            if env.world > 1:
+                raise                                       # the other ranks would wait in a collective
+            r = {"config": {"workload": s}, "error": "%s: %s" % (type(e).__name__, e)}
         release(env)
         if r is not None:
             r["wall_s"] = time.time() - t0

@@ -369,6 +369,9 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
                 if (ubuf.size() > (8u << 20)) { unclassified.write(ubuf.data(), (std::streamsize)ubuf.size()); ubuf.clear(); }
             }
         }
+        for (size_t t = 0; t < tbuf.size(); ++t) { targetFastas[t].write(tbuf[t].data(), (std::streamsize)tbuf[t].size()); targetFastas[t].flush(); }
+        unclassified.write(ubuf.data(), (std::streamsize)ubuf.size());
+        unclassified.flush();
         // the reference's per-read timer covers the chunk loop, the decision and the output record of a read; here the same work
         // is done for all reads of the file at once
         res.avgClassifyduration = res.readCounter ? secs(t_classify, clk::now()) / (double)res.readCounter : 0.0;
