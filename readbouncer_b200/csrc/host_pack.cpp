@@ -74,6 +74,9 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *bases, size_t n, u
     if (n % 32) pack_word_scalar(bases + 32 * full, n % 32, lo[full], hi[full], bad[full]);
 }
 
+// measurement switch (tools/pack_bench.cpp): RB_PACK_STORE = 0 write-combining stores (product), 1 ordinary stores, 2 none
+const int g_store_mode = [] { const char *e = std::getenv("RB_PACK_STORE"); return e ? std::atoi(e) : 0; }();
+
 // AVX-512 (BW + VBMI): one 128-entry byte look-up (vpermi2b) classifies 64 bases, vptestmb turns code bits into
 // 64-bit masks directly -- no movemask, no shifts.
 __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const uint8_t *bases, size_t n, uint32_t *lo,
@@ -89,6 +92,7 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const ui
     const __m512i c02 = _mm512_set1_epi8(0x02), c04 = _mm512_set1_epi8(0x04);
     const size_t full = n / 64;
     size_t w = 0;
+    __m512i acc = _mm512_setzero_si512();
     if (nt && ((reinterpret_cast<uintptr_t>(lo) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(bad)) & 63) == 0) {
         // 512 bases per step: eight mask words per plane leave as ONE full-line write-combining store, and the input is
         // prefetched 2 KB ahead (a core's demand stream alone does not keep enough lines in flight)
@@ -105,11 +109,20 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const ui
                 H[j] = _mm512_test_epi8_mask(x, c04) & good;
                 B[j] = ~good;
             }
-            _mm512_stream_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
-            _mm512_stream_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
-            _mm512_stream_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
+            if (g_store_mode == 0) {
+                _mm512_stream_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
+                _mm512_stream_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
+                _mm512_stream_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
+            } else if (g_store_mode == 1) {              // measurement: ordinary (cache-allocating) stores
+                _mm512_store_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
+                _mm512_store_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
+                _mm512_store_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
+            } else {                                     // measurement: no plane stores at all (read + classify only)
+                acc = _mm512_xor_si512(acc, _mm512_xor_si512(_mm512_load_si512(L), _mm512_xor_si512(_mm512_load_si512(H), _mm512_load_si512(B))));
+            }
         }
     }
+    if (g_store_mode == 2 && w) lo[0] ^= (uint32_t)_mm512_reduce_add_epi64(acc) & 0u;     // keeps the measurement variant's work alive
     for (; w < full; ++w) {
         const __m512i x = _mm512_loadu_si512(bases + 64 * w);
         const __m512i cls = _mm512_permutex2var_epi8(t0, x, t1);              // index = low 7 bits of the byte

@@ -1,7 +1,17 @@
 #!/bin/bash
-# host packer speed on the GPU box's cores (no GPU work), then the default bench line
+# host packer on the GPU box's cores (no GPU work): thread scaling, store variants, and the pool's pure stream-read rate
 mkdir -p gpurun_out
+O=gpurun_out/f_pack_box.txt
+lscpu | grep -E "Model name|Thread|Core|Socket|L3|NUMA node\(s\)" > $O
 g++ -std=c++17 -O2 -Ireadbouncer_b200/csrc tools/pack_bench.cpp readbouncer_b200/csrc/host_pack.o -lpthread -o /tmp/pack_bench
-/tmp/pack_bench > gpurun_out/pack_bench.txt 2>&1
-RB_HOST_THREADS=8 /tmp/pack_bench >> gpurun_out/pack_bench.txt 2>&1
-cat gpurun_out/pack_bench.txt
+for t in 4 8 12 16; do for m in 0 1 2; do
+  echo "threads=$t store_mode=$m" >> $O
+  RB_HOST_THREADS=$t RB_PACK_STORE=$m /tmp/pack_bench | sed -n 2,5p >> $O
+done; done
+for t in 1 4 8 12 16; do RB_HOST_THREADS=$t python - >> $O <<'P'
+import sys; sys.path.insert(0,'.')
+import numpy as np, readbouncer_b200 as rb
+a=np.ones(512<<20,np.uint8); print(rb.host_pack_info()['threads'], "threads read-only GB/s %.1f"%rb.capi.host_read_gbs(a))
+P
+done
+cat $O
