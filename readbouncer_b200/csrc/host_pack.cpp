@@ -74,25 +74,27 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *bases, size_t n, u
     if (n % 32) pack_word_scalar(bases + 32 * full, n % 32, lo[full], hi[full], bad[full]);
 }
 
-// measurement switch (tools/pack_bench.cpp): RB_PACK_STORE = 0 write-combining stores (product), 1 ordinary stores, 2 none
-const int g_store_mode = [] { const char *e = std::getenv("RB_PACK_STORE"); return e ? std::atoi(e) : 0; }();
-
-// AVX-512 (BW + VBMI): one 128-entry byte look-up (vpermi2b) classifies 64 bases, vptestmb turns code bits into
-// 64-bit masks directly -- no movemask, no shifts.
+// AVX-512 (BW + VBMI): one 64-entry byte look-up (vpermb on the low 6 bits) classifies 64 bases, the mask-register tests
+// turn code bits into 64-bit masks directly -- no movemask, no shifts.
+//   good(c) = table[c & 63] and bit 6 of c set and bit 7 clear: A C G T U are 0x41 0x43 0x47 0x54 0x55 (+ 0x20 lower case),
+//   so the table marks 0x01 0x03 0x07 0x14 0x15 0x21 0x23 0x27 0x34 0x35 and the two high bits rule out the bytes that alias.
+// vpermb is one port-5 operation (the two-table vpermt2b took three and a register copy); `good` serves as the write mask of
+// the two plane tests, so a 64-base block costs a load, vpermb, vpaddb, vpternlogd, vpmovb2m, 2 vptestmb, knot, 3 mask stores.
 __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const uint8_t *bases, size_t n, uint32_t *lo,
                                                                         uint32_t *hi, uint32_t *bad, bool nt)
 {
     nt = nt && ((reinterpret_cast<uintptr_t>(lo) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(bad)) & 7) == 0;
-    alignas(64) uint8_t tab[128];
-    for (int c = 0; c < 128; ++c) {
-        const int u = c & 0xDF;
+    alignas(64) uint8_t tab[64];
+    for (int c = 0; c < 64; ++c) {
+        const int u = 0x40 | (c & 0x1F);                    // the upper-case letter both aliases (0x40 | c, 0x60 | c - 0x20) stand for
         tab[c] = (u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'U') ? 0xFF : 0x00;
     }
-    const __m512i t0 = _mm512_load_si512(tab), t1 = _mm512_load_si512(tab + 64);
+    const __m512i tb = _mm512_load_si512(tab);
     const __m512i c02 = _mm512_set1_epi8(0x02), c04 = _mm512_set1_epi8(0x04);
+    // sign bit of (cls & (x << 1) & ~x) = table hit, bit 6 set, bit 7 clear; the table index is the low 6 bits of the byte
+#define RB_CLASSIFY(x) _mm512_movepi8_mask(_mm512_ternarylogic_epi32(_mm512_permutexvar_epi8((x), tb), _mm512_add_epi8((x), (x)), (x), 0x40))
     const size_t full = n / 64;
     size_t w = 0;
-    __m512i acc = _mm512_setzero_si512();
     if (nt && ((reinterpret_cast<uintptr_t>(lo) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(bad)) & 63) == 0) {
         // 512 bases per step: eight mask words per plane leave as ONE full-line write-combining store, and the input is
         // prefetched 2 KB ahead (a core's demand stream alone does not keep enough lines in flight)
@@ -103,31 +105,20 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const ui
                 const uint8_t *p = bases + 64 * (w + j);
                 _mm_prefetch(reinterpret_cast<const char *>(p) + 2048, _MM_HINT_T0);
                 const __m512i x = _mm512_loadu_si512(p);
-                const __m512i cls = _mm512_permutex2var_epi8(t0, x, t1);
-                const __mmask64 good = _mm512_movepi8_mask(cls) & ~_mm512_movepi8_mask(x);
-                L[j] = _mm512_test_epi8_mask(x, c02) & good;
-                H[j] = _mm512_test_epi8_mask(x, c04) & good;
+                const __mmask64 good = RB_CLASSIFY(x);
+                L[j] = _mm512_mask_test_epi8_mask(good, x, c02);
+                H[j] = _mm512_mask_test_epi8_mask(good, x, c04);
                 B[j] = ~good;
             }
-            if (g_store_mode == 0) {
-                _mm512_stream_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
-                _mm512_stream_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
-                _mm512_stream_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
-            } else if (g_store_mode == 1) {              // measurement: ordinary (cache-allocating) stores
-                _mm512_store_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
-                _mm512_store_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
-                _mm512_store_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
-            } else {                                     // measurement: no plane stores at all (read + classify only)
-                acc = _mm512_xor_si512(acc, _mm512_xor_si512(_mm512_load_si512(L), _mm512_xor_si512(_mm512_load_si512(H), _mm512_load_si512(B))));
-            }
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
         }
     }
-    if (g_store_mode == 2 && w) lo[0] ^= (uint32_t)_mm512_reduce_add_epi64(acc) & 0u;     // keeps the measurement variant's work alive
     for (; w < full; ++w) {
         const __m512i x = _mm512_loadu_si512(bases + 64 * w);
-        const __m512i cls = _mm512_permutex2var_epi8(t0, x, t1);              // index = low 7 bits of the byte
-        const __mmask64 good = _mm512_movepi8_mask(cls) & ~_mm512_movepi8_mask(x);   // and the byte is < 0x80
-        const uint64_t l = _mm512_test_epi8_mask(x, c02) & good, h = _mm512_test_epi8_mask(x, c04) & good, b = ~good;
+        const __mmask64 good = RB_CLASSIFY(x);
+        const uint64_t l = _mm512_mask_test_epi8_mask(good, x, c02), h = _mm512_mask_test_epi8_mask(good, x, c04), b = ~good;
         if (nt) {        // write-combining stores: the planes go to DRAM for the DMA engine, not into this core's cache
             _mm_stream_si64(reinterpret_cast<long long *>(lo + 2 * w), (long long)l);
             _mm_stream_si64(reinterpret_cast<long long *>(hi + 2 * w), (long long)h);
@@ -143,6 +134,7 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const ui
     for (size_t o = 0; o < rest; o += 32)
         pack_word_scalar(bases + done + o, std::min<size_t>(32, rest - o), lo[2 * full + o / 32], hi[2 * full + o / 32],
                          bad[2 * full + o / 32]);
+#undef RB_CLASSIFY
 }
 #endif
 
