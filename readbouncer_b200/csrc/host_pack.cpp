@@ -80,9 +80,12 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *bases, size_t n, u
 //   so the table marks 0x01 0x03 0x07 0x14 0x15 0x21 0x23 0x27 0x34 0x35 and the two high bits rule out the bytes that alias.
 // vpermb is one port-5 operation (the two-table vpermt2b took three and a register copy); `good` serves as the write mask of
 // the two plane tests, so a 64-base block costs a load, vpermb, vpaddb, vpternlogd, vpmovb2m, 2 vptestmb, knot, 3 mask stores.
+// lazy_dirty != null: the "not ACGT" plane is written only from the first block that has such a base on (the words before it
+// are zero-filled then); *lazy_dirty tells whether that happened.  A clean call leaves `bad` untouched.
 __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const uint8_t *bases, size_t n, uint32_t *lo,
-                                                                        uint32_t *hi, uint32_t *bad, bool nt)
+                                                                        uint32_t *hi, uint32_t *bad, bool nt, bool *lazy_dirty)
 {
+    bool dirty = lazy_dirty == nullptr;                  // not lazy: always write
     nt = nt && ((reinterpret_cast<uintptr_t>(lo) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(bad)) & 7) == 0;
     alignas(64) uint8_t tab[64];
     for (int c = 0; c < 64; ++c) {
@@ -112,28 +115,37 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const ui
             }
             _mm512_stream_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
             _mm512_stream_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
-            _mm512_stream_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
+            if (!dirty && (B[0] | B[1] | B[2] | B[3] | B[4] | B[5] | B[6] | B[7])) {
+                dirty = true;
+                std::memset(bad, 0, 8 * w);              // the clean blocks before this one
+            }
+            if (dirty) _mm512_stream_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
         }
     }
     for (; w < full; ++w) {
         const __m512i x = _mm512_loadu_si512(bases + 64 * w);
         const __mmask64 good = RB_CLASSIFY(x);
         const uint64_t l = _mm512_mask_test_epi8_mask(good, x, c02), h = _mm512_mask_test_epi8_mask(good, x, c04), b = ~good;
+        if (!dirty && b) { dirty = true; std::memset(bad, 0, 8 * w); }
         if (nt) {        // write-combining stores: the planes go to DRAM for the DMA engine, not into this core's cache
             _mm_stream_si64(reinterpret_cast<long long *>(lo + 2 * w), (long long)l);
             _mm_stream_si64(reinterpret_cast<long long *>(hi + 2 * w), (long long)h);
-            _mm_stream_si64(reinterpret_cast<long long *>(bad + 2 * w), (long long)b);
+            if (dirty) _mm_stream_si64(reinterpret_cast<long long *>(bad + 2 * w), (long long)b);
         } else {
             std::memcpy(lo + 2 * w, &l, 8);
             std::memcpy(hi + 2 * w, &h, 8);
-            std::memcpy(bad + 2 * w, &b, 8);
+            if (dirty) std::memcpy(bad + 2 * w, &b, 8);
         }
     }
     if (nt) _mm_sfence();
     const size_t done = 64 * full, rest = n - done;
-    for (size_t o = 0; o < rest; o += 32)
-        pack_word_scalar(bases + done + o, std::min<size_t>(32, rest - o), lo[2 * full + o / 32], hi[2 * full + o / 32],
-                         bad[2 * full + o / 32]);
+    for (size_t o = 0; o < rest; o += 32) {
+        uint32_t b = 0;
+        pack_word_scalar(bases + done + o, std::min<size_t>(32, rest - o), lo[2 * full + o / 32], hi[2 * full + o / 32], b);
+        if (!dirty && b) { dirty = true; std::memset(bad, 0, 4 * (2 * full + o / 32)); }
+        if (dirty) bad[2 * full + o / 32] = b;
+    }
+    if (lazy_dirty) *lazy_dirty = dirty;
 #undef RB_CLASSIFY
 }
 #endif
@@ -290,10 +302,23 @@ uint64_t max_read_length(const uint64_t *off, size_t n)
     return r;
 }
 
+bool pack_bases_lazy(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad, bool streaming_stores)
+{
+#if defined(__x86_64__)
+    if (g_isa == 5) { bool dirty = false; pack_avx512(bases, n, lo, hi, bad, streaming_stores, &dirty); return dirty; }
+#endif
+    // the other code paths write the whole plane (so the region is consistent either way) and report what it holds
+    pack_bases(bases, n, lo, hi, bad, streaming_stores);
+    const size_t nw = (n + 31) / 32;
+    for (size_t w = 0; w < nw; ++w)
+        if (bad[w]) return true;
+    return false;
+}
+
 void pack_bases(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad, bool streaming_stores)
 {
 #if defined(__x86_64__)
-    if (g_isa == 5) { pack_avx512(bases, n, lo, hi, bad, streaming_stores); return; }
+    if (g_isa == 5) { pack_avx512(bases, n, lo, hi, bad, streaming_stores, nullptr); return; }
     if (g_isa == 2) { pack_avx2(bases, n, lo, hi, bad); return; }
 #endif
     pack_scalar(bases, n, lo, hi, bad);

@@ -18,6 +18,11 @@ namespace rb {
 // streaming_stores: write the planes with non-temporal stores (staging memory that a DMA engine reads next).
 void pack_bases(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad, bool streaming_stores = false);
 
+// The same, but the "not ACGT" plane is only written if the range has such a base (returns true then: all ceil(n / 32) words
+// of `bad` are valid).  When it returns false `bad` may be untouched: most reads have no such base, and a plane that is
+// neither written by the host threads nor read by the DMA engine is an eighth less host-memory traffic per base.
+bool pack_bases_lazy(const uint8_t *bases, size_t n, uint32_t *lo, uint32_t *hi, uint32_t *bad, bool streaming_stores = false);
+
 // max over i < n of off[i+1] - off[i] as unsigned 64-bit (a decreasing pair shows up as a value >= 2^63)
 uint64_t max_read_length(const uint64_t *off, size_t n);
 

@@ -557,6 +557,7 @@ struct CallCtx {
     cudaEvent_t ev_start = nullptr;
     DevBuf d_off[kSlots], d_keys[kSlots], d_flag[kSlots], d_in[kSlots], d_cf[kSlots], d_cr[kSlots];
     DevBuf d_lut, d_res;
+    DevBuf d_zero;                           // all-zero "not ACGT" plane for the pieces that have no such base
     HostBuf h_planes;
     std::vector<uint16_t> lut_host;          // what d_lut holds
     int init()
@@ -577,7 +578,7 @@ struct CallCtx {
             d_off[s].release(); d_keys[s].release(); d_flag[s].release(); d_in[s].release(); d_cf[s].release(); d_cr[s].release();
         }
         if (ev_start) cudaEventDestroy(ev_start);
-        d_lut.release(); d_res.release(); h_planes.release();
+        d_lut.release(); d_res.release(); d_zero.release(); h_planes.release();
         cudaGetLastError();
     }
 };
@@ -831,13 +832,24 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
                 const size_t n_tasks = task_piece.size();
                 size_t next_reg = 0;
                 int err = RB_OK;
+                // The "not ACGT" plane of a task is written only if the task has such a base (task_bad); a piece none of whose
+                // tasks has one ships two planes and classifies against a zero plane that lives on the device.
+                std::vector<uint8_t> task_bad(n_tasks, 0);
+                uint64_t max_nw = 0;
+                for (const Region &r : reg) max_nw = std::max(max_nw, r.nw);
+                if (ctx->d_zero.cap < max_nw * 4) {
+                    if ((s2 = ctx->d_zero.reserve(max_nw * 4)) != RB_OK) return s2;
+                    RB_CUDA(cudaMemsetAsync(ctx->d_zero.p, 0, ctx->d_zero.cap, user));     // the slot streams start after `user`
+                    RB_CUDA(cudaEventRecord(ctx->ev_start, user));
+                    for (int s = 0; s < kSlots; ++s) RB_CUDA(cudaStreamWaitEvent(ctx->st[s], ctx->ev_start, 0));
+                }
                 auto pack_task = [&](size_t t) {
                     const Region &r = reg[task_piece[t]];
                     const uint64_t o = (uint64_t)(t - r.task0) * kPackTask;
                     if (o >= r.nb) return;
                     const uint64_t m = std::min<uint64_t>(kPackTask, r.nb - o);
                     uint32_t *h = h_base + r.h_word + o / 32;
-                    rb::pack_bases(bases + r.base0 + o, m, h, h + r.nw, h + 2 * r.nw, true);
+                    task_bad[t] = rb::pack_bases_lazy(bases + r.base0 + o, m, h, h + r.nw, h + 2 * r.nw, true) ? 1 : 0;
                 };
                 auto poll = [&](size_t tasks_done) {
                     while (err == RB_OK && next_reg < reg.size()) {
@@ -846,10 +858,21 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
                         const int s = (int)(r.piece % kSlots);
                         if ((err = ctx->d_in[s].reserve(r.nw * 12)) != RB_OK) break;
                         uint32_t *d = static_cast<uint32_t *>(ctx->d_in[s].p);
-                        cudaError_t ce = cudaMemcpyAsync(d, h_base + r.h_word, r.nw * 12, cudaMemcpyHostToDevice, ctx->st[s]);
+                        bool any_bad = false;
+                        for (size_t t = r.task0; t < r.task0 + r.n_tasks; ++t) any_bad = any_bad || task_bad[t];
+                        if (any_bad) {                     // rare: the clean tasks of this piece left their share of the plane unwritten
+                            for (size_t t = r.task0; t < r.task0 + r.n_tasks; ++t) {
+                                const uint64_t o = (uint64_t)(t - r.task0) * kPackTask;
+                                if (task_bad[t] || o >= r.nb) continue;
+                                const uint64_t m = std::min<uint64_t>(kPackTask, r.nb - o);
+                                std::memset(h_base + r.h_word + 2 * r.nw + o / 32, 0, (m + 31) / 32 * 4);
+                            }
+                        }
+                        const size_t copy_bytes = r.nw * (any_bad ? 12 : 8);
+                        cudaError_t ce = cudaMemcpyAsync(d, h_base + r.h_word, copy_bytes, cudaMemcpyHostToDevice, ctx->st[s]);
                         if (ce != cudaSuccess) { err = fail(RB_ERR_CUDA, std::string("plane copy: ") + cudaGetErrorString(ce)); break; }
-                        g_h2d_bytes += r.nw * 12;
-                        err = submit(r.piece, d, d + r.nw, d + 2 * r.nw, r.base0);
+                        g_h2d_bytes += copy_bytes;
+                        err = submit(r.piece, d, d + r.nw, any_bad ? d + 2 * r.nw : static_cast<const uint32_t *>(ctx->d_zero.p), r.base0);
                         ++next_reg;
                     }
                 };

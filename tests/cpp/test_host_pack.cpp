@@ -42,6 +42,26 @@ int main()
             std::printf("MISMATCH n=%zu\n", n);
             ++fails;
         }
+        // lazy "not ACGT" plane: written completely when the range has such a base (first one early, in the middle, at the very
+        // end, in the scalar tail), untouched-or-complete and reported clean when it has none; aligned planes with streaming
+        // stores (the library's staging layout) and unaligned ones
+        for (int variant = 0; variant < 5 && n; ++variant) {
+            std::vector<uint8_t> c(b.begin(), b.begin() + n);
+            for (size_t i = 0; i < n; ++i) if (bad[i >> 5] >> (i & 31) & 1u) c[i] = 'A';          // all ACGTU now
+            size_t at = variant == 1 ? 0 : variant == 2 ? n / 2 : variant == 3 ? n - 1 : variant == 4 ? (n > 40 ? n - 40 : 0) : n;
+            if (at < n) c[at] = 'N';
+            std::vector<uint32_t> lo4, hi4, bad4;
+            restate(c.data(), n, lo4, hi4, bad4);
+            for (int aligned = 0; aligned < 2; ++aligned) {
+                std::vector<uint32_t> buf(3 * (nw + 32) + 16, 0xDEADBEEF);
+                uint32_t *l = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(buf.data()) + 63) & ~(uintptr_t)63) + (aligned ? 0 : 1);
+                uint32_t *h = l + (nw + 15) / 16 * 16, *bd = h + (nw + 15) / 16 * 16;
+                const bool dirty = rb::pack_bases_lazy(c.data(), n, l, h, bd, aligned != 0);
+                bool ok = dirty == (at < n) && !std::memcmp(lo4.data(), l, nw * 4) && !std::memcmp(hi4.data(), h, nw * 4);
+                if (dirty) ok = ok && !std::memcmp(bad4.data(), bd, nw * 4);
+                if (!ok) { std::printf("LAZY MISMATCH n=%zu variant=%d aligned=%d\n", n, variant, aligned); ++fails; }
+            }
+        }
         // through the pool, in 128 K-base tasks, with a poll that checks the prefix is monotone
         const size_t task = 131072, nt = (n + task - 1) / task;
         std::vector<uint32_t> l3(nw + 1, 0), h3(nw + 1, 0), b3(nw + 1, 0);

@@ -298,6 +298,45 @@ def test_host_buffer_pipeline_packed_pieces_and_rounds(monkeypatch):
     assert xfer[("1", None)] < xfer[("1", "0.25")] < xfer[("1", "0.5")] < xfer[("0", None)]
 
 
+def test_packed_pieces_ship_the_bad_plane_only_when_needed(monkeypatch):
+    """The packed transfer writes and ships the "not ACGT" plane of a piece only if the piece has such a base: a batch whose
+    N / IUPAC bases sit in a few reads (one dirty 128 K-base task inside an otherwise clean piece, one dirty piece between
+    clean ones, a dirty last word) gives the oracle's answers, twice over the same staging memory (a clean piece after a dirty
+    one must not see its stale plane), and crosses PCIe with ~2 instead of 3 bits per base."""
+    plan, of, gf = make_filter_pair(100, 20000, 21000, 13)
+    n = 40000
+    bases, off, _ = synth.sample_reads(plan["bases"], n, 250, seed=77)
+    luts = np.stack([rb.threshold_lut(0.1, 13), rb.threshold_lut(0.08, 13)])
+    gf.enable_kmer_table(0)
+    assert gf.kmer_table_span() == 3
+    monkeypatch.setenv("RB_PIECE_MB", "1")                  # 4 194 reads per piece, 8 tasks per piece
+    monkeypatch.setenv("RB_HOST_PACK", "1")
+
+    def run(b):
+        x0 = rb.transfer_bytes()[0]
+        got = gf.count_batch(b, off, luts)
+        moved = rb.transfer_bytes()[0] - x0
+        for t in range(2):
+            exp = of.count_batch(b, off, luts[t], dense=False, n_threads=8)
+            for key in ("max_count", "hit", "argmax_bin"):
+                assert np.array_equal(got[key][t], exp[key]), (t, key)
+        return moved
+
+    run(bases)                                              # (the first call also uploads the threshold tables)
+    clean = run(bases)                                      # no such base anywhere: two planes per piece
+    dirty = bases.copy()
+    for r, at in ((9000, 17), (9001, 249), (21000, 100), (n - 1, 249)):     # pieces 2, 5 and the last one
+        dirty[r * 250 + at] = ord("N")
+    dirty[30000 * 250:30010 * 250] = ord("R")               # ten reads of IUPAC codes in piece 7
+    some = run(dirty)
+    again = run(bases)                                      # the same staging memory, clean again
+    every = run(np.where(np.arange(bases.size) % 1000 == 0, ord("N"), bases).astype(np.uint8))
+    nb = bases.size
+    assert again == clean and clean < some < every
+    assert abs(clean - (nb / 4 + 8 * (n + 1))) < 0.02 * nb and abs(every - (3 * nb / 8 + 8 * (n + 1))) < 0.02 * nb
+    assert some - clean < 5 * (1 << 20) / 8 + 4096          # four dirty pieces of 1 MB of bases: one more bit per base each
+
+
 @pytest.mark.parametrize("order", ["1", "0"])
 @pytest.mark.parametrize("n_blocks", [2600, 3700, 6000, 9000])
 @pytest.mark.parametrize("slot_bytes,ring", [(0, 0), (128, 0), (256, 1), (1024, 2)])
