@@ -1571,7 +1571,9 @@ int rb_ibf_count_batch_sharded(const rb_ibf *const *shards, uint32_t n_shards, c
         RB_CUDA(cudaSetDevice(root->device));
         RB_CUDA(cudaStreamCreateWithFlags(&per[0].st, cudaStreamNonBlocking));
         RB_CUDA(cudaEventCreateWithFlags(&zeroed, cudaEventDisableTiming));
-        RB_CUDA(cudaMallocAsync(&d_keys, nk * 8, per[0].st));
+        // plain cudaMalloc: peers reach it through cudaDeviceEnablePeerAccess (stream-ordered pool memory would need its own
+        // cudaMemPoolSetAccess grant per peer)
+        RB_CUDA(cudaMalloc(&d_keys, nk * 8));
         RB_CUDA(cudaMallocAsync(&d_flag, n_reads, per[0].st));
         RB_CUDA(cudaMallocAsync(&d_res, nk * 7 + 64, per[0].st));
         RB_CUDA(cudaMemsetAsync(d_keys, 0, nk * 8, per[0].st));
@@ -1632,7 +1634,6 @@ int rb_ibf_count_batch_sharded(const rb_ibf *const *shards, uint32_t n_shards, c
         if (p.d_off) cudaFreeAsync(p.d_off, p.st);
         if (p.d_lut) cudaFreeAsync(p.d_lut, p.st);
         if (i == 0) {
-            if (d_keys) cudaFreeAsync(d_keys, p.st);
             if (d_flag) cudaFreeAsync(d_flag, p.st);
             if (d_res) cudaFreeAsync(d_res, p.st);
         }
@@ -1641,6 +1642,7 @@ int rb_ibf_count_batch_sharded(const rb_ibf *const *shards, uint32_t n_shards, c
         cudaStreamDestroy(p.st);
     }
     if (zeroed) cudaEventDestroy(zeroed);
+    if (d_keys) { cudaSetDevice(root->device); cudaFree(d_keys); }
     if (prev >= 0) cudaSetDevice(prev);
     cudaGetLastError();
     g_last_error = keep;
