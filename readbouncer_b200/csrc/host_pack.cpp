@@ -74,8 +74,6 @@ __attribute__((target("avx2"))) void pack_avx2(const uint8_t *bases, size_t n, u
     if (n % 32) pack_word_scalar(bases + 32 * full, n % 32, lo[full], hi[full], bad[full]);
 }
 
-const bool g_cached_stores = [] { const char *e = std::getenv("RB_PACK_STORE"); return e && e[0] == '1'; }();
-
 // AVX-512 (BW + VBMI): one 64-entry byte look-up (vpermb on the low 6 bits) classifies 64 bases, the mask-register tests
 // turn code bits into 64-bit masks directly -- no movemask, no shifts.
 //   good(c) = table[c & 63] and bit 6 of c set and bit 7 clear: A C G T U are 0x41 0x43 0x47 0x54 0x55 (+ 0x20 lower case),
@@ -115,19 +113,13 @@ __attribute__((target("avx512f,avx512bw,avx512vbmi"))) void pack_avx512(const ui
                 H[j] = _mm512_mask_test_epi8_mask(good, x, c04);
                 B[j] = ~good;
             }
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
             if (!dirty && (B[0] | B[1] | B[2] | B[3] | B[4] | B[5] | B[6] | B[7])) {
                 dirty = true;
                 std::memset(bad, 0, 8 * w);              // the clean blocks before this one
             }
-            if (g_cached_stores) {                       // RB_PACK_STORE=1 (measurement): ordinary stores, planes stay in the cache
-                _mm512_store_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
-                _mm512_store_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
-                if (dirty) _mm512_store_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
-            } else {
-                _mm512_stream_si512(reinterpret_cast<__m512i *>(lo + 2 * w), _mm512_load_si512(L));
-                _mm512_stream_si512(reinterpret_cast<__m512i *>(hi + 2 * w), _mm512_load_si512(H));
-                if (dirty) _mm512_stream_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
-            }
+            if (dirty) _mm512_stream_si512(reinterpret_cast<__m512i *>(bad + 2 * w), _mm512_load_si512(B));
         }
     }
     for (; w < full; ++w) {

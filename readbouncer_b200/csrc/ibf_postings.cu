@@ -33,7 +33,7 @@ namespace {
 // Threads per CTA (template parameter of the lookup kernel) follow from how many CTAs of counters fit the shared memory
 // of an SM: 3 x 256, 2 x 384 or 1 x 768 -- always 24 warps per SM under the 85-register ceiling of 768 threads.
 constexpr int kPostPiece = 512;               // k-mer positions staged per pass over a read
-constexpr int kPostingsPipeDefault = 0;       // see launch_count_postings (RB_POSTINGS_PIPE)
+constexpr int kPostInFlight = 4;              // lists a warp loads before it counts them (even: strands alternate)
 
 // base-5 hashes of the forward and reverse-complement strand of the ACGT k-mer x (ranks, first base most significant)
 __device__ __forceinline__ void kmer_hashes(uint64_t x, uint32_t k, uint64_t &Hf, uint64_t &Hr)
@@ -275,13 +275,10 @@ __device__ __noinline__ void add_hashed(const FilterView &fv, const uint8_t *dig
 template <int CB>
 __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return CB == 8 ? __vmaxu4(a, b) : __vmaxu2(a, b); }
 
-// F lists per group; PIPE: group g + 1 is fetched before group g is counted (two groups of registers), so a warp always has
-// loads in flight while it feeds the shared-memory atomics; MINB = CTAs per SM the register budget is cut for.
-template <int CB, int kPostThreads, int MINB, int F, bool PIPE>
-__global__ void __launch_bounds__(kPostThreads, MINB)
+template <int CB, int kPostThreads>
+__global__ void __launch_bounds__(kPostThreads, 768 / kPostThreads)
 count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const uint4 *__restrict__ ids, const uint32_t cnt_words)
 {
-    constexpr int kPostInFlight = F;
     constexpr int PER = 32 / CB;
     constexpr uint32_t CMASK = (CB == 8) ? 0xFFu : 0xFFFFu;
     constexpr int kPostWarps = kPostThreads / 32;
@@ -350,82 +347,29 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                 };
                 uint32_t p0, p1, np0 = 0, np1 = 0;
                 bool hashed, nhashed = false;
-                if constexpr (PIPE) {
-                    const uint32_t q_begin = min(q_end, warp * share);
-                    list_bounds(q_begin + lane, p0, p1, hashed);
-                    if (q_begin + 32 < q_end) list_bounds(q_begin + 32 + lane, np0, np1, nhashed);
-                    // The bounds of a group come from the current round's registers (p0, p1) or, for the group that opens the
-                    // next round of 32 pairs, from (np0, np1), requested one round ahead.
-                    uint32_t q0 = q_begin;                                      // first pair of the current round
-                    auto fetch_group = [&](ListRegs (&lr)[F], const uint32_t q) {
+                list_bounds(warp * share + lane, p0, p1, hashed);
+                for (uint32_t q0 = warp * share; q0 < q_end; q0 += 32) {
+                    if (q0 + 32 < q_end) list_bounds(q0 + 32 + lane, np0, np1, nhashed);
+                    const uint32_t any_hashed = __ballot_sync(0xffffffffu, hashed);
+                    const uint32_t n_here = min(32u, q_end - q0);
+                    for (uint32_t t = 0; t < n_here; t += kPostInFlight) {  // kPostInFlight lists in flight
+                        ListRegs lr[kPostInFlight];
 #pragma unroll
-                        for (int j = 0; j < F; ++j) {
-                            const uint32_t qq = q + j;
-                            const bool nxt = qq >= q0 + 32;
-                            const uint32_t src = (qq - q0) & 31u;
-                            const uint32_t a0 = __shfl_sync(0xffffffffu, p0, src), a1 = __shfl_sync(0xffffffffu, p1, src);
-                            const uint32_t b0 = __shfl_sync(0xffffffffu, np0, src), b1 = __shfl_sync(0xffffffffu, np1, src);
-                            const uint32_t u0 = nxt ? b0 : a0, u1 = nxt ? b1 : a1;
-                            fetch_list(lr[j], ids, u0, qq < q_end ? u1 - u0 : 0u, lane);
+                        for (int j = 0; j < kPostInFlight; ++j) {
+                            const uint32_t tj = min(t + j, 31u);
+                            const uint32_t u0 = __shfl_sync(0xffffffffu, p0, tj), u1 = __shfl_sync(0xffffffffu, p1, tj);
+                            fetch_list(lr[j], ids, u0, t + j < n_here ? u1 - u0 : 0u, lane);
                         }
-                    };
-                    auto count_group = [&](const ListRegs (&lr)[F]) {
 #pragma unroll
-                        for (int j = 0; j < F; ++j)                         // q is even: list j is strand j & 1
+                        for (int j = 0; j < kPostInFlight; ++j)         // q0 and t are even: list j is strand j & 1
                             count_list<CB>(lr[j], (j & 1) ? cntR : cntF, ids, lane, sentinel);
-                    };
-                    auto end_of_round = [&]() {
-                        const uint32_t any_hashed = __ballot_sync(0xffffffffu, hashed);
-                        if (any_hashed) {
-                            const uint32_t n_here = min(32u, q_end - q0);
-                            for (uint32_t t = 0; t < n_here; ++t)
-                                if ((any_hashed >> t) & 1u)
-                                    add_hashed<CB>(a.fv, s_dig + ((q0 + t) >> 1), (q0 + t) & 1u, ((q0 + t) & 1u) ? cntR : cntF, lane);
-                        }
-                        q0 += 32;
-                        p0 = np0; p1 = np1; hashed = nhashed;
-                        np0 = 0; np1 = 0; nhashed = false;
-                        if (q0 + 32 < q_end) list_bounds(q0 + 32 + lane, np0, np1, nhashed);
-                    };
-                    ListRegs A[F], B[F];
-                    uint32_t q = q_begin;
-                    if (q < q_end) fetch_group(A, q);
-                    while (q < q_end) {
-                        if (q + F < q_end) fetch_group(B, q + F);               // A holds group q
-                        count_group(A);
-                        q += F;
-                        if (q >= q0 + 32 || q >= q_end) end_of_round();
-                        if (q >= q_end) break;
-                        if (q + F < q_end) fetch_group(A, q + F);               // B holds group q
-                        count_group(B);
-                        q += F;
-                        if (q >= q0 + 32 || q >= q_end) end_of_round();
                     }
-                } else {
-                    list_bounds(warp * share + lane, p0, p1, hashed);
-                    for (uint32_t q0 = warp * share; q0 < q_end; q0 += 32) {
-                        if (q0 + 32 < q_end) list_bounds(q0 + 32 + lane, np0, np1, nhashed);
-                        const uint32_t any_hashed = __ballot_sync(0xffffffffu, hashed);
-                        const uint32_t n_here = min(32u, q_end - q0);
-                        for (uint32_t t = 0; t < n_here; t += kPostInFlight) {  // kPostInFlight lists in flight
-                            ListRegs lr[kPostInFlight];
-#pragma unroll
-                            for (int j = 0; j < kPostInFlight; ++j) {
-                                const uint32_t tj = min(t + j, 31u);
-                                const uint32_t u0 = __shfl_sync(0xffffffffu, p0, tj), u1 = __shfl_sync(0xffffffffu, p1, tj);
-                                fetch_list(lr[j], ids, u0, t + j < n_here ? u1 - u0 : 0u, lane);
-                            }
-#pragma unroll
-                            for (int j = 0; j < kPostInFlight; ++j)         // q0 and t are even: list j is strand j & 1
-                                count_list<CB>(lr[j], (j & 1) ? cntR : cntF, ids, lane, sentinel);
-                        }
-                        if (any_hashed) {
-                            for (uint32_t t = 0; t < n_here; ++t)
-                                if ((any_hashed >> t) & 1u)
-                                    add_hashed<CB>(a.fv, s_dig + ((q0 + t) >> 1), (q0 + t) & 1u, ((q0 + t) & 1u) ? cntR : cntF, lane);
-                        }
-                        p0 = np0; p1 = np1; hashed = nhashed;
+                    if (any_hashed) {
+                        for (uint32_t t = 0; t < n_here; ++t)
+                            if ((any_hashed >> t) & 1u)
+                                add_hashed<CB>(a.fv, s_dig + ((q0 + t) >> 1), (q0 + t) & 1u, ((q0 + t) & 1u) ? cntR : cntF, lane);
                     }
+                    p0 = np0; p1 = np1; hashed = nhashed;
                 }
             }
         }
@@ -1121,35 +1065,14 @@ int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint1
         const uint32_t gx = (uint32_t)(a.n_reads < cap ? a.n_reads : cap);
         kernel<<<gx, threads, smem, st>>>(a, d_ptr, ids, cnt_words);
     };
-    // RB_POSTINGS_PIPE (measurements): 0 = fetch a group of 4 lists, then count it; 1 = groups of 2, software-pipelined, same
-    // register budget; 2 = groups of 4 pipelined with 128 registers (2 CTAs of 256 threads per SM); 3 = groups of 4 pipelined,
-    // 3 CTAs of 192 threads (113 registers)
-    static const int pipe_env = [] { const char *e = std::getenv("RB_POSTINGS_PIPE"); return e ? std::atoi(e) : -1; }();
-    const int pipe = pipe_env >= 0 ? pipe_env : kPostingsPipeDefault;
     if (narrow) {
-        if (fit >= 3) {
-            if (pipe == 1) launch(count_postings_kernel<8, 256, 3, 2, true>, 256);
-            else if (pipe == 2) launch(count_postings_kernel<8, 256, 2, 4, true>, 256);
-            else if (pipe == 3) launch(count_postings_kernel<8, 192, 3, 4, true>, 192);
-            else launch(count_postings_kernel<8, 256, 3, 4, false>, 256);
-        } else if (fit == 2) {
-            if (pipe >= 1) launch(count_postings_kernel<8, 384, 2, 2, true>, 384);
-            else launch(count_postings_kernel<8, 384, 2, 4, false>, 384);
-        } else {
-            if (pipe >= 1) launch(count_postings_kernel<8, 768, 1, 2, true>, 768);
-            else launch(count_postings_kernel<8, 768, 1, 4, false>, 768);
-        }
+        if (fit >= 3) launch(count_postings_kernel<8, 256>, 256);
+        else if (fit == 2) launch(count_postings_kernel<8, 384>, 384);
+        else launch(count_postings_kernel<8, 768>, 768);
     } else {
-        if (fit >= 3) {
-            if (pipe >= 1) launch(count_postings_kernel<16, 256, 3, 2, true>, 256);
-            else launch(count_postings_kernel<16, 256, 3, 4, false>, 256);
-        } else if (fit == 2) {
-            if (pipe >= 1) launch(count_postings_kernel<16, 384, 2, 2, true>, 384);
-            else launch(count_postings_kernel<16, 384, 2, 4, false>, 384);
-        } else {
-            if (pipe >= 1) launch(count_postings_kernel<16, 768, 1, 2, true>, 768);
-            else launch(count_postings_kernel<16, 768, 1, 4, false>, 768);
-        }
+        if (fit >= 3) launch(count_postings_kernel<16, 256>, 256);
+        else if (fit == 2) launch(count_postings_kernel<16, 384>, 384);
+        else launch(count_postings_kernel<16, 768>, 768);
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -379,25 +379,14 @@ def test_postings_slots(n_blocks, order, slot_bytes, ring, monkeypatch):
     assert tb >= 0.95 * pairs * min(sbytes, 128) and reqs >= 0.95 * pairs and io > sb.size
 
 
-@pytest.mark.parametrize("pipe", ["0", "1", "2", "3"])
 @pytest.mark.parametrize("order", ["1", "0"])
 @pytest.mark.parametrize("n_blocks", [2600, 3700, 6000, 9000])
-def test_postings_long_lists(n_blocks, order, pipe, monkeypatch):
+def test_postings_long_lists(n_blocks, order, monkeypatch):
     """Postings lists of ~610 / ~380 / ~160 / ~70 bins per k-mer (an over-full 1 100-bin filter: 56 % .. 6 % false positives
     per bin), so that the lookup kernel walks full rounds, further rounds and every tail width (ibf_postings_layout.cuh),
     with the ids dealt over the groups (default) and ascending (RB_POSTINGS_ORDER=0)."""
     monkeypatch.setenv("RB_POSTINGS_ORDER", order)
     monkeypatch.setenv("RB_POSTINGS_LAYOUT", "lists")
-    # how a warp overlaps loading and counting its lists: 0 fetch 4 / count 4, 1-3 software-pipelined groups (launch_count_postings).
-    # The library reads the switch once per process, so the variants other than the default run in a child interpreter.
-    if pipe != "0":
-        import subprocess, sys
-        env = dict(os.environ, RB_POSTINGS_PIPE=pipe, RB_POSTINGS_ORDER=order, RB_POSTINGS_LAYOUT="lists")
-        out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu",
-                              "%s::test_postings_long_lists[%d-%s-0]" % (__file__, n_blocks, order)],
-                             capture_output=True, text=True, env=env, timeout=600)
-        assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-1500:] + out.stderr[-500:]
-        return
     k, n_hash = 11, 3
     ref = [synth.random_bases(1500, 300 + i) for i in range(1100)]
     plan = synth.build_plan(ref, 2000, k, n_hash=n_hash)
