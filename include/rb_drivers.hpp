@@ -291,11 +291,16 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
             const uint64_t m = owner.size();
             if (m == 0) break;
             // per-filter summaries of the whole batch: max_count at error_rate (and at error_rate-0.02 when both sets are given)
-            auto run = [&](std::vector<IBFMeta> &filters, std::vector<std::vector<uint16_t>> &cnt, std::vector<std::vector<uint16_t>> &cnt_s,
+            // all filters of both sets at once: one host thread per filter (count_matches_batch_all)
+            std::vector<const TIbf *> all;
+            for (IBFMeta &f : TargetFilters) all.push_back(&f.filter);
+            for (IBFMeta &f : DepletionFilters) all.push_back(&f.filter);
+            const std::vector<BatchCounts> counts = count_matches_batch_all(all, bases.data(), off.data(), m, Conf, deplete && target);
+            auto run = [&](size_t first, size_t count, std::vector<std::vector<uint16_t>> &cnt, std::vector<std::vector<uint16_t>> &cnt_s,
                            std::vector<uint8_t> &flag) {
                 flag.assign(m, 0);
-                for (IBFMeta &f : filters) {
-                    BatchCounts c = count_matches_batch(f.filter, bases.data(), off.data(), m, Conf, deplete && target);
+                for (size_t fi = first; fi < first + count; ++fi) {
+                    const BatchCounts &c = counts[fi];
                     cnt.emplace_back(c.max_count.begin(), c.max_count.begin() + m);
                     if (deplete && target) cnt_s.emplace_back(c.max_count.begin() + m, c.max_count.begin() + 2 * m);
                     for (uint64_t j = 0; j < m; ++j) flag[j] = std::max(flag[j], c.read_flag[j]);
@@ -303,8 +308,8 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
             };
             std::vector<std::vector<uint16_t>> tc, tcs, dc, dcs;
             std::vector<uint8_t> tflag, dflag;
-            if (target) run(TargetFilters, tc, tcs, tflag);
-            if (deplete) run(DepletionFilters, dc, dcs, dflag);
+            if (target) run(0, TargetFilters.size(), tc, tcs, tflag);
+            if (deplete) run(TargetFilters.size(), DepletionFilters.size(), dc, dcs, dflag);
             auto best_of = [&](const std::vector<std::vector<uint16_t>> &c, uint64_t j, int &idx) {
                 uint64_t best = 0; idx = -1;
                 for (size_t f = 0; f < c.size(); ++f) if (c[f][j] > best) { best = c[f][j]; idx = (int)f; }   // strictly greater, lowest index

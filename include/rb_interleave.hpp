@@ -17,8 +17,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <exception>
 #include <fstream>
+#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -407,6 +409,34 @@ inline BatchCounts count_matches_batch(const TIbf &filter, const char *bases, co
     return out;
 }
 
+// The same for several filters at once: one host thread per filter, each with its own streams and staging buffers inside
+// the library, so the passes overlap instead of queueing behind one another's synchronisation (the reference spawns one
+// std::async per filter per READ, src/IBF/IBFClassify.cpp:259; here it is one per filter per BATCH).
+inline std::vector<BatchCounts> count_matches_batch_all(const std::vector<const TIbf *> &filters, const char *bases,
+                                                        const uint64_t *read_off, uint64_t n_reads, const ClassifyConfig &config,
+                                                        bool with_retry_threshold = false)
+{
+    std::vector<BatchCounts> out(filters.size());
+    static const bool serial = [] { const char *e = std::getenv("RB_FILTERS_SERIAL"); return e && e[0] == '1'; }();   // measurements
+    if (filters.size() == 1 || serial) {
+        for (size_t i = 0; i < filters.size(); ++i)
+            out[i] = count_matches_batch(*filters[i], bases, read_off, n_reads, config, with_retry_threshold);
+        return out;
+    }
+    std::vector<std::future<BatchCounts>> fut;
+    fut.reserve(filters.size());
+    for (const TIbf *f : filters)
+        fut.push_back(std::async(std::launch::async, [=, &config] {
+            return count_matches_batch(*f, bases, read_off, n_reads, config, with_retry_threshold);
+        }));
+    std::exception_ptr first;
+    for (size_t i = 0; i < fut.size(); ++i) {
+        try { out[i] = fut[i].get(); } catch (...) { if (!first) first = std::current_exception(); }
+    }
+    if (first) std::rethrow_exception(first);
+    return out;
+}
+
 // ---- interleave::Read (src/IBF/IBF.hpp:169-226, src/IBF/IBFClassify.cpp) --------------------------------------------
 class Read {
 public:
@@ -508,11 +538,16 @@ inline std::vector<uint8_t> check_unblock_batch(const char *bases, const uint64_
     const bool withTarget = !TargetFilters.empty(), withDepletion = !DepletionFilters.empty();
     if (!withTarget && !withDepletion) throw NullFilterException("No IBF provided to classify the read!");
     const bool both = withTarget && withDepletion;
-    auto best_of = [&](std::vector<IBFMeta> &filters, std::vector<uint16_t> &best, std::vector<uint16_t> &best_strict,
+    // all filters of both sets in one go (one host thread per filter), then the best count per set
+    std::vector<const TIbf *> all;
+    for (IBFMeta &f : DepletionFilters) all.push_back(&f.filter);
+    for (IBFMeta &f : TargetFilters) all.push_back(&f.filter);
+    const std::vector<BatchCounts> counts = count_matches_batch_all(all, bases, read_off, n_reads, conf, both);
+    auto best_of = [&](size_t first, size_t count, std::vector<uint16_t> &best, std::vector<uint16_t> &best_strict,
                        std::vector<uint8_t> &flag) {
         best.assign(n_reads, 0); best_strict.assign(n_reads, 0); flag.assign(n_reads, 0);
-        for (IBFMeta &f : filters) {
-            BatchCounts c = count_matches_batch(f.filter, bases, read_off, n_reads, conf, both);
+        for (size_t fi = first; fi < first + count; ++fi) {
+            const BatchCounts &c = counts[fi];
             for (uint64_t i = 0; i < n_reads; ++i) {
                 best[i] = std::max(best[i], c.max_count[i]);
                 if (both) best_strict[i] = std::max(best_strict[i], c.max_count[n_reads + i]);
@@ -523,8 +558,8 @@ inline std::vector<uint8_t> check_unblock_batch(const char *bases, const uint64_
     std::vector<uint16_t> dep, dep_s, tgt, tgt_s;
     std::vector<uint8_t> fd, ft;
     std::vector<uint8_t> out(n_reads, 0);
-    if (withDepletion) best_of(DepletionFilters, dep, dep_s, fd);
-    if (withTarget) best_of(TargetFilters, tgt, tgt_s, ft);
+    if (withDepletion) best_of(0, DepletionFilters.size(), dep, dep_s, fd);
+    if (withTarget) best_of(DepletionFilters.size(), TargetFilters.size(), tgt, tgt_s, ft);
     for (uint64_t i = 0; i < n_reads; ++i) {
         if (both) {
             // reads shorter than k are skipped per filter by the pair overload (count 0); a read the engine cannot
