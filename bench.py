@@ -58,7 +58,7 @@ WORKLOADS = {
                                        reads=16_384, bins_per_rank=512),
 }
 DEFAULT_WORKLOAD = "cfg2_100x4Mb_100bins"
-SECONDARY_1GPU = ["cfg3_3.1Gb_31kbins", "cfg2_k15", "cfg2_k17", "cfg1_5Mb_51bins", "readme_3targets_1deplete"]
+SECONDARY_1GPU = ["cfg3_3.1Gb_31kbins", "cfg2_k15", "cfg2_k17", "cfg1_5Mb_51bins", "readme_3targets_1deplete", "live_3targets_1deplete"]
 README_READS = 100_000      # the reference's one published workload (README.md:233-262), tools/readme_bench.py
 SECONDARY_NGPU = ["cfg5_3.7Gb_37kbins_per_gpu"]
 ERROR_RATE = 0.1
@@ -763,6 +763,25 @@ def main():
     elif not explicit and not args.no_secondary and args.mode == "read_sharded" and args.kernel == 0:
         sec_names = SECONDARY_1GPU if env.world == 1 else SECONDARY_NGPU
     for s in sec_names:
+        if s.startswith("live_"):
+            # usage="target" without a sequencer: micro-batches of 250-base chunks through rblive::LiveClassifier (check_unblock
+            # against 3 target + 1 depletion filter, both thresholds of the retry in one pass per filter); latency per batch
+            if env.rank == 0:
+                t0 = time.time()
+                exe = os.path.join(ROOT, "readbouncer_b200", "bin", "rb_live_bench")
+                try:
+                    p = subprocess.run([exe, "3", "1", "4000000", "100", "64", "512", "4096"], capture_output=True, text=True, timeout=300)
+                    rows = [json.loads(ln) for ln in p.stdout.splitlines() if ln.startswith("{")]
+                    r = {"workload": s, "what": "time from handing a micro-batch to rblive::LiveClassifier::classify_batch to having its "
+                                              "decisions (adaptive_sampling.hpp:214-356 batched; 4 filters, k = 13, fragment_size 100 000)",
+                         "micro_batches": rows}
+                    if p.returncode != 0 or not rows:
+                        r["error"] = p.stderr[-500:]
+                except Exception as e:
+                    r = {"workload": s, "error": "%s: %s" % (type(e).__name__, e)}
+                r["wall_s"] = time.time() - t0
+                secondary.append(r)
+            continue
         if s.startswith("readme_"):
             # the reference's published use case: 3 target + 1 depletion filter, FASTA in -> files out through the C++ driver
             if env.rank == 0:

@@ -291,7 +291,7 @@ inline ClassificationResults classify_reads(const ConfigReader &config, std::vec
             const uint64_t m = owner.size();
             if (m == 0) break;
             // per-filter summaries of the whole batch: max_count at error_rate (and at error_rate-0.02 when both sets are given)
-            // all filters of both sets at once: one host thread per filter (count_matches_batch_all)
+            // all filters of both sets (count_matches_batch_all)
             std::vector<const TIbf *> all;
             for (IBFMeta &f : TargetFilters) all.push_back(&f.filter);
             for (IBFMeta &f : DepletionFilters) all.push_back(&f.filter);

@@ -20,7 +20,6 @@
 #include <cstdlib>
 #include <exception>
 #include <fstream>
-#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -409,31 +408,17 @@ inline BatchCounts count_matches_batch(const TIbf &filter, const char *bases, co
     return out;
 }
 
-// The same for several filters at once: one host thread per filter, each with its own streams and staging buffers inside
-// the library, so the passes overlap instead of queueing behind one another's synchronisation (the reference spawns one
-// std::async per filter per READ, src/IBF/IBFClassify.cpp:259; here it is one per filter per BATCH).
+// The same for several filters, one after the other.  (One host thread per filter -- the reference spawns one std::async per
+// filter per read, src/IBF/IBFClassify.cpp:259 -- was measured and is slower here: 623 vs 445 us for a micro-batch of 64 chunks
+// against 4 filters, 4.09 vs 2.76 ms for 4 096; thread start-up and the contention of four packers cost more than the calls'
+// synchronisation they would hide, profiles/r2_k_live_microbatch_latency.jsonl.)
 inline std::vector<BatchCounts> count_matches_batch_all(const std::vector<const TIbf *> &filters, const char *bases,
                                                         const uint64_t *read_off, uint64_t n_reads, const ClassifyConfig &config,
                                                         bool with_retry_threshold = false)
 {
     std::vector<BatchCounts> out(filters.size());
-    static const bool serial = [] { const char *e = std::getenv("RB_FILTERS_SERIAL"); return e && e[0] == '1'; }();   // measurements
-    if (filters.size() == 1 || serial) {
-        for (size_t i = 0; i < filters.size(); ++i)
-            out[i] = count_matches_batch(*filters[i], bases, read_off, n_reads, config, with_retry_threshold);
-        return out;
-    }
-    std::vector<std::future<BatchCounts>> fut;
-    fut.reserve(filters.size());
-    for (const TIbf *f : filters)
-        fut.push_back(std::async(std::launch::async, [=, &config] {
-            return count_matches_batch(*f, bases, read_off, n_reads, config, with_retry_threshold);
-        }));
-    std::exception_ptr first;
-    for (size_t i = 0; i < fut.size(); ++i) {
-        try { out[i] = fut[i].get(); } catch (...) { if (!first) first = std::current_exception(); }
-    }
-    if (first) std::rethrow_exception(first);
+    for (size_t i = 0; i < filters.size(); ++i)
+        out[i] = count_matches_batch(*filters[i], bases, read_off, n_reads, config, with_retry_threshold);
     return out;
 }
 
@@ -538,7 +523,7 @@ inline std::vector<uint8_t> check_unblock_batch(const char *bases, const uint64_
     const bool withTarget = !TargetFilters.empty(), withDepletion = !DepletionFilters.empty();
     if (!withTarget && !withDepletion) throw NullFilterException("No IBF provided to classify the read!");
     const bool both = withTarget && withDepletion;
-    // all filters of both sets in one go (one host thread per filter), then the best count per set
+    // all filters of both sets, then the best count per set
     std::vector<const TIbf *> all;
     for (IBFMeta &f : DepletionFilters) all.push_back(&f.filter);
     for (IBFMeta &f : TargetFilters) all.push_back(&f.filter);

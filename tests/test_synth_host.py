@@ -77,5 +77,5 @@ def test_bench_workloads_consume_exactly_their_bins():
         else:
             p = bench.make_reference(w).plan(w["fragment"], w["k"])
             assert p["bin_ids_consumed"] == p["n_bins"], name      # no quirk-Q3 overrun in the bench references
-    assert set(bench.SECONDARY_1GPU) - {"readme_3targets_1deplete"} <= set(bench.WORKLOADS)
+    assert set(bench.SECONDARY_1GPU) - {"readme_3targets_1deplete", "live_3targets_1deplete"} <= set(bench.WORKLOADS)
     assert set(bench.SECONDARY_NGPU) <= set(bench.WORKLOADS)
