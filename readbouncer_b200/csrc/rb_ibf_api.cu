@@ -661,17 +661,6 @@ int run_count_batch(const rb_ibf *f, CallCtx *ctx, const uint8_t *bases, const u
         cut.push_back(std::min<uint64_t>(rmax, (uint64_t)(it - read_off)));
         if (cut.back() <= r0) cut.back() = r0 + 1;
     }
-    // Taper the end of a long batch: what follows the packing of the last piece -- its copy, its kernels, the final
-    // synchronisation -- is not overlapped by anything, so the last piece is cut in half twice (.., 8, 4, 2, 2 MB).
-    static const bool taper = [] { const char *e = std::getenv("RB_TAPER"); return !(e && e[0] == '0'); }();   // RB_TAPER=0: measurements
-    if (taper && cut.size() - 1 >= 8) {
-        for (int rep = 0; rep < 2; ++rep) {
-            const uint64_t a = cut[cut.size() - 2], b = cut.back();
-            if (b - a < 1024) break;
-            cut.back() = a + (b - a) / 2;
-            cut.push_back(b);
-        }
-    }
     const size_t n_pieces = cut.size() - 1;
 
     // ---- which way in ----------------------------------------------------------------------------------------------------
