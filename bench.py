@@ -42,6 +42,9 @@ WORKLOADS = {
     "cfg2_100x4Mb_100bins": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=13, chunk=250, reads=1_000_000),
     "cfg2_k15": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=15, chunk=250, reads=1_000_000),
     "cfg2_k17": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=17, chunk=250, reads=262_144),
+    "cfg2_k14": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=14, chunk=250, reads=1_000_000),
+    "cfg2_k16": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=16, chunk=250, reads=262_144),
+    "w4_200x2Mb_200bins": dict(lengths=[1_999_999] * 200, seed0=2, fragment=2_100_000, k=13, chunk=250, reads=1_000_000),
     "cfg3_3.1Gb_31kbins": dict(lengths=[129_166_666] * 24, seed0=300, fragment=100_000, k=13, chunk=250, reads=65_536,
                                cpu_build_frags=1024),
     "w1_50x4Mb_50bins": dict(lengths=[3_999_999] * 50, seed0=2, fragment=4_200_000, k=13, chunk=250, reads=1_000_000),
