@@ -421,6 +421,13 @@ static void launch_table_bs_np(const CountArgs &a, const uint64_t *table, bool s
     else launch_table_bs<WT, 16, S>(a, table, sm_count, st);
 }
 
+// entries a lane keeps in flight in the atomic-counter kernel for rows of 3-4 words (RB_TABLE_U: measurements)
+static int table_u()
+{
+    static const int u = [] { const char *e = std::getenv("RB_TABLE_U"); const int v = e ? std::atoi(e) : 0; return (v == 2 || v == 4) ? v : 1; }();
+    return u;
+}
+
 // variant 0: bit-sliced register counters (rows <= 2 words); 1: shared-memory atomic counters.
 int launch_count_table(const CountArgs &a, const uint64_t *table, int span, uint32_t max_read_len, int variant,
                        int sm_count, cudaStream_t st)
@@ -436,8 +443,8 @@ int launch_count_table(const CountArgs &a, const uint64_t *table, int span, uint
     switch (a.fv.stride) {
     case 1: launch_table_wt<1, 2>(a, table, sm_count, st); break;
     case 2: launch_table_wt<2, 2>(a, table, sm_count, st); break;
-    case 3: launch_table_wt<3, 1>(a, table, sm_count, st); break;
-    case 4: launch_table_wt<4, 1>(a, table, sm_count, st); break;
+    case 3: if (table_u() == 4) launch_table_wt<3, 4>(a, table, sm_count, st); else if (table_u() == 2) launch_table_wt<3, 2>(a, table, sm_count, st); else launch_table_wt<3, 1>(a, table, sm_count, st); break;
+    case 4: if (table_u() == 4) launch_table_wt<4, 4>(a, table, sm_count, st); else if (table_u() == 2) launch_table_wt<4, 2>(a, table, sm_count, st); else launch_table_wt<4, 1>(a, table, sm_count, st); break;
     default: return -1;
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
