@@ -45,6 +45,12 @@ WORKLOADS = {
     "cfg2_k14": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=14, chunk=250, reads=1_000_000),
     "cfg2_k16": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=16, chunk=250, reads=262_144),
     "w4_200x2Mb_200bins": dict(lengths=[1_999_999] * 200, seed0=2, fragment=2_100_000, k=13, chunk=250, reads=1_000_000),
+    # mid-size filters (a few target chromosomes): rows of 5, 16 and 64 words, all on the postings path
+    "w5_30Mb_303bins": dict(lengths=[10_050_000] * 3, seed0=400, fragment=100_000, k=13, chunk=250, reads=262_144, cpu_build_frags=64),
+    "w16_100Mb_1010bins": dict(lengths=[10_050_000] * 10, seed0=400, fragment=100_000, k=13, chunk=250, reads=262_144,
+                               cpu_build_frags=128),
+    "w64_400Mb_4040bins": dict(lengths=[10_050_000] * 40, seed0=400, fragment=100_000, k=13, chunk=250, reads=131_072,
+                               cpu_build_frags=256),
     "cfg3_3.1Gb_31kbins": dict(lengths=[129_166_666] * 24, seed0=300, fragment=100_000, k=13, chunk=250, reads=65_536,
                                cpu_build_frags=1024),
     "w1_50x4Mb_50bins": dict(lengths=[3_999_999] * 50, seed0=2, fragment=4_200_000, k=13, chunk=250, reads=1_000_000),
@@ -583,7 +589,8 @@ def run_workload(env, args, name, n_reads, steps, warmup, role):
     span = gf.kmer_table_span()
     kind = gf.kmer_table_kind()
     group_ok = span >= 2 and chunk - k + 1 <= 127 * span and chunk <= 545   # ibf_wtable.cu: wgroup_applicable
-    kernel_name = ("count_slots_kernel" if kind == 3 else "count_postings_kernel" if kind == 2 else "count_wgroup_kernel" if group_ok else "count_wtable_kernel" if span >= 2
+    kernel_name = ("count_slots_kernel" if kind == 3 else "count_postings_kernel" if kind == 2 else "count_ctable_kernel" if kind == 4
+                   else "count_wgroup_kernel" if group_ok else "count_wtable_kernel" if span >= 2
                    else "count_table_kernel" if span == 1 else
                    "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel")
     streamed = kernel_name == "count_stream_kernel"
@@ -628,6 +635,16 @@ def run_workload(env, args, name, n_reads, steps, warmup, role):
     npos = chunk - k + 1
     if kind in (2, 3):
         pass                # postings lists are streamed: the HBM-bandwidth roofline above applies
+    elif kind == 4:     # one k-mer per entry of 64 / 128 / 256 bytes, 16 bytes per lane, adjacent lanes
+        entry_bytes = gf.kmer_table_bytes() // 4 ** k
+        lanes = entry_bytes // 16
+        ppg = 64 * lanes
+        g_ms = time_gather(lambda: rb.microbench_gather_coop(gf.device_kmer_table_ptr(), 4 ** k, entry_bytes, 16, ppg, blocks, sink,
+                                                              stream=stream))
+        roofline["requests"] = {"what": "one %d-byte table entry (1 k-mer position, both strands, %d lanes) per request" % (entry_bytes, lanes),
+                                "per_chunk": npos, "peak_per_s": blocks * 256 // lanes * ppg / (g_ms * 1e-3),
+                                "achieved_per_s": n_reads * npos / (kernel_ms * 1e-3),
+                                "how": "rb_microbench_gather_coop over the k-mer table itself (%d entries)" % 4 ** k}
     elif span >= 2:     # window table: one request per entry of `lanes` slots, adjacent lanes
         lanes = 2 if span == 2 else 4
         entry_bytes = lanes * 16 * int(gf.col_words)

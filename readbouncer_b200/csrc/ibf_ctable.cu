@@ -1,0 +1,241 @@
+// ibf_ctable.cu -- one-k-mer table for MEDIUM filters (rows of 3..16 words, 129..1024 bins), entries loaded by lane groups.
+//
+// Same tabulated function as ibf_table.cu -- what seqan::count does per k-mer and strand (src/IBF/IBFClassify.cpp:149-150,
+// SURVEY.md App. A.6):
+//
+//     table[x] = [ AND_i row(h_i(x)) : G words ][ AND_i row(h_i(revcomp(x))) : G words ]        x in [0, 4^k)
+//
+// with the row padded to G = 4, 8 or 16 words, so an entry is G pieces of 16 bytes = 64, 128 or 256 bytes, aligned to its
+// size.  What differs is who loads it.  A lane that fetches a whole 64..256-byte entry issues 4..16 separate 16-byte loads,
+// i.e. 4..16 requests per k-mer position; here G ADJACENT LANES load one entry with ONE instruction (lane p takes piece p),
+// which the memory system serves as one request per 128-byte line (profiles/r1_d_gather_sweep3_coop.jsonl) -- one or two
+// requests per position and both strands, against two dependent ones per position AND strand for the postings lists these
+// filters used before (ibf_postings.cu).  A lane then owns two words of one strand's mask for every position of its group
+// and bumps the counters of their set bits in shared memory (a mask of a 1000-bin filter has ~10 false-positive bits, so
+// this is a handful of atomics per entry, spread over the group).
+//
+// Windows with a non-ACGT base are not in the table: their lanes evaluate their two words from the original bit matrix
+// (three row probes), so every output bit is the reference's.
+#include "ibf_device.cuh"
+
+#include <cstdlib>
+
+namespace rb {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// build: one thread per (k-mer, piece)
+// ------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(256) ctable_build_kernel(const FilterView fv, uint4 *__restrict__ table, const uint64_t n_kmers)
+{
+    const HashParams &hp = fv.hp;
+    const uint32_t k = hp.k;
+    const uint64_t n = n_kmers * G;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t x = t / G;
+        const uint32_t p = (uint32_t)(t % G);
+        const bool rev = p >= G / 2;
+        const uint32_t w0 = 2u * (p % (G / 2));
+        uint64_t H = 0, pw = 1;
+        for (uint32_t j = 0; j < k; ++j) {
+            const uint32_t d = (uint32_t)(x >> (2 * (k - 1 - j))) & 3u;          // base j of the k-mer
+            if (!rev) H = H * 5 + d;
+            else { H += (uint64_t)(3u - d) * pw; pw *= 5; }
+        }
+        uint64_t m0 = w0 < fv.stride ? ~0ULL : 0ULL, m1 = w0 + 1 < fv.stride ? ~0ULL : 0ULL;
+        for (uint32_t i = 0; i < hp.n_hash; ++i) {
+            const uint64_t *row = fv.words + hash_row(H, hp.pre[i], hp.n_blocks, hp.magic) * fv.stride;
+            if (w0 < fv.stride) m0 &= __ldg(row + w0);
+            if (w0 + 1 < fv.stride) m1 &= __ldg(row + w0 + 1);
+        }
+        table[t] = make_uint4((uint32_t)m0, (uint32_t)(m0 >> 32), (uint32_t)m1, (uint32_t)(m1 >> 32));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// count: warp per read, G lanes per entry, 32/G runs of consecutive positions per warp
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bump_word(uint32_t *cnt, uint32_t w)
+{
+    while (w) {
+        const int b = __ffs((int)w) - 1;
+        atomicAdd(cnt + b, 1u);
+        w &= w - 1;
+    }
+}
+
+// the lane's two mask words of a window that is not in the table, from the original rows
+__device__ __noinline__ uint4 piece_hashed(const FilterView &fv, const uint8_t *dig, const bool rev, const uint32_t w0)
+{
+    const HashParams &hp = fv.hp;
+    uint64_t H = 0, pw = 1;
+    for (uint32_t u = 0; u < hp.k; ++u) {
+        const uint32_t d = dig[u];
+        if (!rev) H = H * 5 + d;
+        else { H += comp5(d) * pw; pw *= 5; }
+    }
+    uint64_t m0 = w0 < fv.stride ? ~0ULL : 0ULL, m1 = w0 + 1 < fv.stride ? ~0ULL : 0ULL;
+    for (uint32_t i = 0; i < hp.n_hash; ++i) {
+        const uint64_t *row = fv.words + hash_row(H, hp.pre[i], hp.n_blocks, hp.magic) * fv.stride;
+        if (w0 < fv.stride) m0 &= __ldg(row + w0);
+        if (w0 + 1 < fv.stride) m1 &= __ldg(row + w0 + 1);
+    }
+    return make_uint4((uint32_t)m0, (uint32_t)(m0 >> 32), (uint32_t)m1, (uint32_t)(m1 >> 32));
+}
+
+constexpr int kCtWarps = 8;
+
+template <int G, int U>
+__global__ void __launch_bounds__(kCtWarps * 32) count_ctable_kernel(const CountArgs a, const uint4 *__restrict__ table)
+{
+    constexpr int NG = 32 / G;                                          // entries per warp-wide load
+    extern __shared__ __align__(16) uint32_t s_ct[];
+    uint32_t *const s_cnt = s_ct;                                       // [kCtWarps][2][64 * G]
+    uint8_t *const s_dig = reinterpret_cast<uint8_t *>(s_ct + kCtWarps * 2 * 64 * G);   // [kCtWarps][kDigBytes]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t total_warps = (uint64_t)gridDim.x * kCtWarps;
+    const uint32_t k = a.fv.hp.k;
+    const uint64_t kmask = (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    uint8_t *const dig = s_dig + warp * kDigBytes;
+    uint32_t *const cntF = s_cnt + warp * (2 * 64 * G), *const cntR = cntF + 64 * G;
+    const uint32_t p = (uint32_t)lane % G, gi = (uint32_t)lane / G;
+    const bool rev = p >= G / 2;
+    const uint32_t w0 = 2u * (p % (G / 2));
+    uint32_t *const cnt = (rev ? cntR : cntF) + 64 * w0;               // the 128 counters of my two words
+
+    for (int b = lane; b < 2 * 64 * G; b += 32) cntF[b] = 0;
+    __syncwarp();
+
+    for (uint64_t read = (uint64_t)blockIdx.x * kCtWarps + warp; read < a.n_reads; read += total_warps) {
+        const uint64_t off = a.read_off[read];
+        const uint64_t len = a.read_off[read + 1] - off;
+        const uint32_t flag = read_flag_of(len, k);
+        if (lane == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
+
+        if (flag == 0) {
+            const uint32_t npos = (uint32_t)len - k + 1;
+            for (uint32_t cs = 0; cs < npos; cs += kChunkPos) {
+                const uint32_t cn = min((uint32_t)kChunkPos, npos - cs);
+                __syncwarp();
+                for (uint32_t i = lane; i < cn + k - 1; i += 32) dig[i] = (uint8_t)dna5(a.bases[off + cs + i]);
+                __syncwarp();
+                const uint32_t seg = (cn + NG - 1) / NG;
+                const uint32_t j0 = gi * seg;
+                const uint32_t j1 = min(j0 + seg, cn);
+                if (j0 < j1) {
+                    uint64_t x = 0;          // 2-bit packed k-mer
+                    uint32_t nbad = 0;       // non-ACGT bases inside it
+#pragma unroll 1                 // (nvcc 12.9's cicc crashes when it unrolls this loop here)
+                    for (uint32_t u = 0; u < k; ++u) {
+                        const uint32_t d = dig[j0 + u];
+                        x = (x << 2) | (d & 3u);
+                        nbad += d >> 2;
+                    }
+                    x &= kmask;
+                    for (uint32_t j = j0; j < j1; j += U) {
+                        uint4 v[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            v[u] = make_uint4(0, 0, 0, 0);
+                            if (j + u < j1) {
+                                if (nbad == 0) v[u] = __ldg(table + x * G + p);
+                                else v[u] = piece_hashed(a.fv, dig + j + u, rev, w0);
+                                if (j + u + 1 < j1) {
+                                    const uint32_t dout = dig[j + u], din = dig[j + u + k];
+                                    x = ((x << 2) | (din & 3u)) & kmask;
+                                    nbad += (din >> 2) - (dout >> 2);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            bump_word(cnt, v[u].x);
+                            bump_word(cnt + 32, v[u].y);
+                            bump_word(cnt + 64, v[u].z);
+                            bump_word(cnt + 96, v[u].w);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        tile_epilogue<G>(a, read, len, flag, 0, cntF, cntR, lane, 0);
+        __syncwarp();
+    }
+}
+
+template <int G, int U>
+void launch_count_g(const CountArgs &a, const uint64_t *table, int sm_count, cudaStream_t st)
+{
+    const size_t smem = (size_t)kCtWarps * (2 * 64 * G * 4 + kDigBytes);
+    static int occ = 0;
+    if (occ == 0) {
+        cudaFuncSetAttribute(count_ctable_kernel<G, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, count_ctable_kernel<G, U>, kCtWarps * 32, smem);
+        occ = o > 0 ? o : 1;
+    }
+    const uint64_t blocks_needed = (a.n_reads + kCtWarps - 1) / kCtWarps;
+    const uint64_t max_x = (uint64_t)sm_count * occ * grid_waves();
+    const uint32_t gx = (uint32_t)(blocks_needed < max_x ? blocks_needed : max_x);
+    count_ctable_kernel<G, U><<<gx ? gx : 1, kCtWarps * 32, smem, st>>>(a, reinterpret_cast<const uint4 *>(table));
+}
+
+int ct_inflight()
+{
+    const char *e = std::getenv("RB_CTABLE_U");                           // measurements, tests
+    const int v = e ? std::atoi(e) : 0;
+    return (v == 1 || v == 2 || v == 8) ? v : 4;
+}
+
+template <int G>
+void launch_count_gu(const CountArgs &a, const uint64_t *table, int sm_count, cudaStream_t st)
+{
+    switch (ct_inflight()) {
+    case 1: launch_count_g<G, 1>(a, table, sm_count, st); break;
+    case 2: launch_count_g<G, 2>(a, table, sm_count, st); break;
+    case 8: launch_count_g<G, 8>(a, table, sm_count, st); break;
+    default: launch_count_g<G, 4>(a, table, sm_count, st); break;
+    }
+}
+
+}  // namespace
+
+// lanes per entry (= padded row words) for a row of `stride` words; 0: this layout does not apply
+int ctable_lanes(uint64_t stride)
+{
+    return stride < 3 ? 0 : stride <= 4 ? 4 : stride <= 8 ? 8 : stride <= 16 ? 16 : 0;
+}
+
+int launch_ctable_build(const FilterView &fv, uint64_t *table, uint64_t n_kmers, int sm_count, cudaStream_t st)
+{
+    const int G = ctable_lanes(fv.stride);
+    const uint64_t blocks = (n_kmers * (uint64_t)G + 255) / 256, cap = (uint64_t)sm_count * 32;
+    const uint32_t gx = (uint32_t)(blocks < cap ? blocks : cap);
+    uint4 *t = reinterpret_cast<uint4 *>(table);
+    switch (G) {
+    case 4: ctable_build_kernel<4><<<gx, 256, 0, st>>>(fv, t, n_kmers); break;
+    case 8: ctable_build_kernel<8><<<gx, 256, 0, st>>>(fv, t, n_kmers); break;
+    case 16: ctable_build_kernel<16><<<gx, 256, 0, st>>>(fv, t, n_kmers); break;
+    default: return -1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_count_ctable(const CountArgs &a, const uint64_t *table, int sm_count, cudaStream_t st)
+{
+    if (a.n_reads == 0) return 0;
+    if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut) return -1;
+    switch (ctable_lanes(a.fv.stride)) {
+    case 4: launch_count_gu<4>(a, table, sm_count, st); break;
+    case 8: launch_count_gu<8>(a, table, sm_count, st); break;
+    case 16: launch_count_gu<16>(a, table, sm_count, st); break;
+    default: return -1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace rb

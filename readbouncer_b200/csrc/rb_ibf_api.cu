@@ -73,7 +73,7 @@ struct rb_ibf {
                                             // entries loaded by adjacent lanes (ibf_wtable.cu)
     mutable uint64_t table_bytes = 0;
     // wide filters: k-mer postings table (ibf_postings.cu) instead of the dense window table
-    mutable int table_kind = 0;             // 0 none, 1 dense k-mer / window table, 2 postings
+    mutable int table_kind = 0;             // 0 none, 1 dense k-mer / window table, 2 postings, 4 k-mer table loaded by lane groups
     mutable uint32_t *d_post_ptr = nullptr;
     mutable uint16_t *d_post_ids = nullptr;
     // ... or, by default, the same lists as one fixed slot per k-mer + an overflow area (table_kind 3)
@@ -278,6 +278,17 @@ constexpr uint64_t kTableMinReads = 1024;   // batches smaller than this never t
 // span = consecutive k-mers per entry.  span 1: 4^k entries of 2*col_words words, one lane per entry
 // (ibf_table.cu, rows <= 4 words).  span 2..4: (k+span-1)-base windows, canonical when that length is odd,
 // `lanes` slots of 2*col_words words per entry, loaded by adjacent lanes (ibf_wtable.cu, rows <= 2 words).
+// rows of 3..16 words: one k-mer per entry, the row padded to 4, 8 or 16 words, loaded by that many lanes (ibf_ctable.cu).
+// RB_CTABLE=0 turns the layout off (measurements: rows of 3-4 words fall back to ibf_table.cu, wider ones to postings).
+uint64_t ctable_bytes(const rb_ibf *f)
+{
+    const char *e = std::getenv("RB_CTABLE");
+    const bool on = !(e && e[0] == '0');
+    const int lanes = rb::ctable_lanes(f->col_words);
+    if (!on || !lanes || f->k > 16) return 0;
+    return (1ull << (2 * f->k)) * (uint64_t)lanes * 16;
+}
+
 uint64_t table_bytes_needed(const rb_ibf *f, int span)
 {
     if (f->col_words == 0 || f->k + span - 1 > 16) return 0;
@@ -340,6 +351,22 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     uint64_t cap = 80ull << 30;
     if (const char *gb = std::getenv("RB_KMER_TABLE_MAX_GB")) cap = (uint64_t)std::max(0, std::atoi(gb)) << 30;
     const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>((uint64_t)(free_b * 0.6), cap);
+    if (const uint64_t need = ctable_bytes(f); need && need <= budget && need <= free_b) {
+        uint64_t *t = nullptr;
+        if (cudaMalloc(&t, need) == cudaSuccess) {
+            const uint64_t n_kmers = 1ull << (2 * f->k);
+            const int n = rb::launch_ctable_build(view_of(f), t, n_kmers, f->sm_count, st);
+            if (n < 0 || cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(t); cudaGetLastError(); return nullptr; }
+            g_launches += (uint64_t)n;
+            f->d_table = t;
+            f->table_kind = 4;
+            f->table_entries = n_kmers;
+            f->table_span = 1;
+            f->table_bytes = need;
+            return t;
+        }
+        cudaGetLastError();               // no memory after all: the smaller layouts below
+    }
     if (f->col_words > 4) {
         const rb::FilterView fv = view_of(f);
         // wide rows: postings.  Default layout: pointer + variable-length lists, loaded straight into registers.
@@ -427,6 +454,13 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     for (int sp = max_span; sp >= 1 && !span; --sp) {   // the widest window that fits the budget
         const uint64_t b = table_bytes_needed(f, sp);
         if (b && b <= budget && b <= free_b) { span = sp; need = b; }
+    }
+    // An explicit request with the automatic budget: when only the one-k-mer table is possible and it misses the 60 % / 80 GiB
+    // rule (k = 16: 137 GB for 65-128 bins) it still gets up to 85 % of the free memory -- the alternative is six hashed probes
+    // per k-mer and strand, 4-5 times slower.  A lazy build inside a count call never takes that much.
+    if (!span && force && f->table_budget == 0) {
+        const uint64_t b = table_bytes_needed(f, 1);
+        if (b && b <= (uint64_t)(free_b * 0.85)) { span = 1; need = b; }
     }
     if (!span) return nullptr;
     uint64_t *t = nullptr;
@@ -1342,10 +1376,13 @@ int rb_ibf_enable_kmer_tables(rb_ibf *const *filters, uint32_t n_filters, uint64
             rb_ibf *f = fs[i];
             if (f->col_words > 4) {
                 const uint64_t est = postings_estimate_bytes(f, (cudaStream_t)stream);
-                if (est) opts[i].push_back({est + est / 16, 1});  // the estimate comes from a sample: leave a margin
+                if (est) opts[i].push_back({est + est / 16, 0});  // the estimate comes from a sample: leave a margin
+                // rows of 5..16 words: the group-loaded k-mer table is the widening step after the postings lists
+                if (const uint64_t ct = ctable_bytes(f); ct && (opts[i].empty() || ct > opts[i][0].bytes)) opts[i].push_back({ct, 1});
             } else {
                 for (int sp = 1; sp <= (f->col_words <= 2 ? 4 : 1); ++sp) {
-                    const uint64_t b = table_bytes_needed(f, sp);
+                    const uint64_t ct = sp == 1 ? ctable_bytes(f) : 0;           // rows of 3-4 words: padded, group-loaded entries
+                    const uint64_t b = ct ? ct : table_bytes_needed(f, sp);
                     if (b) opts[i].push_back({b, sp});
                 }
             }
@@ -1500,6 +1537,12 @@ static int count_dev_impl(const rb_ibf *f, const uint8_t *d_bases, const uint64_
     if (which == 0 || which >= 3) table = ensure_table(f, (cudaStream_t)stream, which >= 3, n_reads);   // 3..5: table kernels
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
     if (keys_shared && table && f->table_kind == 1) table = nullptr;      // the dense-table kernels store their keys: hashed probes fold them
+    if (table && f->table_kind == 4) {
+        int n = rb::launch_count_ctable(a, table, f->sm_count, (cudaStream_t)stream);
+        if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        g_launches += (uint64_t)n;
+        return RB_OK;
+    }
     if (table && f->table_kind == 3) {
         int n = rb::launch_count_slots(a, f->d_slots, f->slot_bytes, f->d_slot_ovf, max_read_len, f->sm_count, f->d_err + 1, (cudaStream_t)stream);
         if (n == -1) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -1726,7 +1769,8 @@ int rb_ibf_count_traffic_dev(const rb_ibf *f, const uint8_t *d_bases, const uint
     {
         std::lock_guard<std::mutex> lock(f->table_mu);
         kind = f->table_kind; span = f->table_span;
-        if (kind == 1) entry_bytes = (uint32_t)(span == 1 ? 16 * f->col_words : (span == 2 ? 2 : 4) * 16 * f->col_words);
+        if (kind == 4) { entry_bytes = 16u * (uint32_t)rb::ctable_lanes(f->col_words); kind = 1; }
+        else if (kind == 1) entry_bytes = (uint32_t)(span == 1 ? 16 * f->col_words : (span == 2 ? 2 : 4) * 16 * f->col_words);
         else if (kind == 2) { entry_bytes = 16; ptr = f->d_post_ptr; }
         else if (kind == 3) { entry_bytes = f->slot_bytes; ptr = reinterpret_cast<const uint32_t *>(f->d_slots); }
         else entry_bytes = (uint32_t)(8 * f->col_words);

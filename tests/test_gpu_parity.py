@@ -161,13 +161,22 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
             sb[int(so[5]):int(so[6])] = ord("N")
             sb[int(so[7]) + 100] = ord("U")
             sexp = of.count_batch(sb, so, lut, n_threads=4)
+            if gf.bin_width <= 16:                       # rows of 5..16 words: the group-loaded k-mer table comes first
+                gf.enable_kmer_table(0)
+                lanes = 8 if gf.bin_width <= 8 else 16
+                assert (gf.kmer_table_kind(), gf.kmer_table_bytes(), gf.kmer_table_span()) == (4, 4 ** k * lanes * 16, 1)
+                assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+                assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)
+                assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+                gf.disable_kmer_table()
             # lists: pointer + variable-length lists (default); slots: one fixed slot per k-mer fetched by bulk copies
             for layout, kind in (("slots", 3), ("lists", 2)):
                 os.environ["RB_POSTINGS_LAYOUT"] = layout
+                os.environ["RB_CTABLE"] = "0"
                 try:
                     gf.enable_kmer_table(0)
                 finally:
-                    del os.environ["RB_POSTINGS_LAYOUT"]
+                    del os.environ["RB_POSTINGS_LAYOUT"], os.environ["RB_CTABLE"]
                 assert gf.kmer_table_kind() == kind and gf.kmer_table_bytes() > 4 ** k * 4
                 assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)          # long reads: 16-bit counters
                 assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)             # <= 255 positions: 8-bit counters
@@ -179,7 +188,21 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
         span1 = 4 ** k * 16 * gf.bin_width
         gf.enable_kmer_table(span1)                      # budget admits only one k-mer per entry
         assert (gf.kmer_table_bytes(), gf.kmer_table_span()) == (span1, 1)
+        # rows of 3-4 words: entries padded to 4 words and loaded by 4 lanes (ibf_ctable.cu) when that fits the budget
+        assert gf.kmer_table_kind() == (4 if gf.bin_width == 4 else 1)
         assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+        if gf.bin_width in (3, 4):                       # ... and the lane-per-entry kernel of ibf_table.cu on the unpadded layout
+            os.environ["RB_CTABLE"] = "0"
+            try:
+                gf.enable_kmer_table(span1)
+            finally:
+                del os.environ["RB_CTABLE"]
+            assert (gf.kmer_table_kind(), gf.kmer_table_bytes()) == (1, span1)
+            assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
+            if gf.bin_width == 3 and 4 ** k * 64 < (70 << 30):
+                gf.enable_kmer_table(4 ** k * 64)        # the padded layout for 3-word rows
+                assert (gf.kmer_table_kind(), gf.kmer_table_bytes()) == (4, 4 ** k * 64)
+                assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
         if gf.bin_width <= 2 and kernel == "table":      # window tables: 2..4 consecutive k-mers per entry
             for span in (2, 3, 4):
                 need = wtable_bytes(k, gf.bin_width, span)
@@ -337,6 +360,42 @@ def test_packed_pieces_ship_the_bad_plane_only_when_needed(monkeypatch):
     assert some - clean < 5 * (1 << 20) / 8 + 4096          # four dirty pieces of 1 MB of bases: one more bit per base each
 
 
+@pytest.mark.parametrize("inflight", ["", "1", "8"])
+@pytest.mark.parametrize("n_bins,k", [(129, 11), (192, 10), (256, 11), (257, 11), (320, 10), (512, 11), (513, 10), (1000, 11), (1024, 10)])
+def test_medium_rows_group_loaded_table(n_bins, k, inflight, monkeypatch):
+    """Rows of 3..16 words (129..1024 bins): k-mer table entries padded to 4 / 8 / 16 words, one entry per group of as many lanes
+    (ibf_ctable.cu).  Every width class at both ends, ragged and multi-chunk reads, N / IUPAC windows (hashed on the fly), two
+    threshold tables in one pass, dense counts; default and extreme numbers of entries in flight per lane."""
+    if inflight:
+        if (n_bins, k) not in ((192, 10), (512, 11), (1000, 11)):
+            pytest.skip("in-flight variants on one shape per width class")
+        monkeypatch.setenv("RB_CTABLE_U", inflight)
+    plan, of, gf = make_filter_pair(n_bins, 1500, 2000, k)
+    assert plan["n_bins"] == n_bins
+    gf.enable_kmer_table(0)
+    lanes = 4 if n_bins <= 256 else 8 if n_bins <= 512 else 16
+    assert (gf.kmer_table_kind(), gf.kmer_table_span(), gf.kmer_table_bytes()) == (4, 1, 4 ** k * lanes * 16)
+    bases, off = synth.ragged_reads(plan["bases"], RAGGED + [k - 1, k, k + 1, 1023 + k, 1024 + k, 3000], seed=31, frac_from_ref=0.7,
+                                    n_frac=0.004, lower_frac=0.1)
+    bases[int(off[3]):int(off[4])] = ord("N")
+    bases[int(off[6]) + 100] = ord("R")
+    luts = np.stack([rb.threshold_lut(0.1, k), rb.threshold_lut(0.08, k)])
+    for t in range(2):
+        exp = of.count_batch(bases, off, luts[t], n_threads=8)
+        assert_same_results(gf.count_batch(bases, off, luts[t], dense=True), exp)
+    both = gf.count_batch(bases, off, luts)
+    for t in range(2):
+        exp = of.count_batch(bases, off, luts[t], dense=False, n_threads=8)
+        for key in ("max_count", "hit", "argmax_bin"):
+            assert np.array_equal(both[key][t], exp[key]), (t, key)
+    # the roofline's traffic figure: one entry per k-mer position, whole 128-byte lines
+    import torch
+    d_b, d_o = torch.from_numpy(bases).cuda(), torch.from_numpy(off.astype(np.int64)).cuda()
+    tb, reqs, io = gf.count_traffic_dev(d_b, d_o, len(off) - 1, 1)
+    npos = sum(max(0, int(n) - k + 1) for n in np.diff(off.astype(np.int64)) if n <= 65535)
+    assert reqs == npos and tb == npos * max(128, lanes * 16)
+
+
 @pytest.mark.parametrize("order", ["1", "0"])
 @pytest.mark.parametrize("n_blocks", [2600, 3700, 6000, 9000])
 @pytest.mark.parametrize("slot_bytes,ring", [(0, 0), (128, 0), (256, 1), (1024, 2)])
@@ -464,7 +523,7 @@ def test_create_shard_builds_a_column_slice_in_place():
     assert np.array_equal(mx, exp["max_count"]) and np.array_equal(hit, exp["hit"]) and np.array_equal(am, exp["argmax_bin"])
 
 
-@pytest.mark.parametrize("n_shards,tables", [(2, ""), (3, "lists"), (5, "lists"), (3, "slots")])
+@pytest.mark.parametrize("n_shards,tables", [(2, ""), (3, "lists"), (5, "lists"), (3, "slots"), (2, "ctable"), (5, "ctable")])
 def test_sharded_call_folds_keys_into_one_array(n_shards, tables, monkeypatch):
     """rb_ibf_count_batch_sharded: every shard's count kernel folds its keys into shard 0's key array (atomicMax; over
     NVLink when the shards sit on different devices -- here round-robin over the visible ones), == whole filter == oracle.
@@ -479,8 +538,12 @@ def test_sharded_call_folds_keys_into_one_array(n_shards, tables, monkeypatch):
         sh = rb.IBF.create_shard(plan["n_bins"], 3, 13, plan["n_bits"], s_, n_shards, device=s_ % n_dev)
         sh.insert_batch(plan["bases"], plan["frag_begin"], plan["frag_end"], plan["frag_bin"])
         shards.append(sh)
-    if tables:
+    if tables == "ctable":                              # shards of 3..16 row words: the group-loaded k-mer table folds its keys too
+        rb.enable_kmer_tables(shards)
+        assert [s.kmer_table_kind() for s in shards] == [4 if s.col_words >= 3 else 1 for s in shards]
+    elif tables:
         monkeypatch.setenv("RB_POSTINGS_LAYOUT", tables)
+        monkeypatch.setenv("RB_CTABLE", "0")
         rb.enable_kmer_tables(shards)
         assert [s.kmer_table_kind() for s in shards] == [(2 if tables == "lists" else 3) if s.col_words > 4 else 1 for s in shards]
     got = rb.count_batch_sharded(shards, bases, off, luts)
