@@ -66,7 +66,7 @@ int launch_count_table(const CountArgs &a, const uint64_t *table, int span, uint
 // one-k-mer table for rows of 3..16 words, entries padded to 4 / 8 / 16 words and loaded by that many lanes (ibf_ctable.cu)
 int ctable_lanes(uint64_t stride);
 int launch_ctable_build(const FilterView &fv, uint64_t *table, uint64_t n_kmers, int sm_count, cudaStream_t st);
-int launch_count_ctable(const CountArgs &a, const uint64_t *table, int sm_count, cudaStream_t st);
+int launch_count_ctable(const CountArgs &a, const uint64_t *table, uint32_t max_read_len, int variant, int sm_count, cudaStream_t st);
 // window k-mer table with cooperative entry loads (ibf_wtable.cu): span = 2..4 k-mers per entry, rows <= 2 words
 bool wtable_geometry(uint64_t stride, uint32_t k, int span, int *lanes, int *canon, uint64_t *n_entries);
 int launch_wtable_build(const FilterView &fv, uint64_t *table, int span, int sm_count, cudaStream_t st);

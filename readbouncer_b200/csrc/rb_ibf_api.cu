@@ -1538,7 +1538,7 @@ static int count_dev_impl(const rb_ibf *f, const uint8_t *d_bases, const uint64_
     if (which >= 3 && !table) return fail(RB_ERR_INVALID_ARG, "k-mer table not applicable to this filter (row > 4 words, k > 16 or no memory)");
     if (keys_shared && table && f->table_kind == 1) table = nullptr;      // the dense-table kernels store their keys: hashed probes fold them
     if (table && f->table_kind == 4) {
-        int n = rb::launch_count_ctable(a, table, f->sm_count, (cudaStream_t)stream);
+        int n = rb::launch_count_ctable(a, table, max_read_len, which == 4 ? 1 : 0, f->sm_count, (cudaStream_t)stream);
         if (n < 0) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         g_launches += (uint64_t)n;
         return RB_OK;

@@ -360,16 +360,20 @@ def test_packed_pieces_ship_the_bad_plane_only_when_needed(monkeypatch):
     assert some - clean < 5 * (1 << 20) / 8 + 4096          # four dirty pieces of 1 MB of bases: one more bit per base each
 
 
-@pytest.mark.parametrize("inflight", ["", "1", "8"])
+@pytest.mark.parametrize("inflight", ["", "atomic", "1", "8"])
 @pytest.mark.parametrize("n_bins,k", [(129, 11), (192, 10), (256, 11), (257, 11), (320, 10), (512, 11), (513, 10), (1000, 11), (1024, 10)])
 def test_medium_rows_group_loaded_table(n_bins, k, inflight, monkeypatch):
     """Rows of 3..16 words (129..1024 bins): k-mer table entries padded to 4 / 8 / 16 words, one entry per group of as many lanes
     (ibf_ctable.cu).  Every width class at both ends, ragged and multi-chunk reads, N / IUPAC windows (hashed on the fly), two
-    threshold tables in one pass, dense counts; default and extreme numbers of entries in flight per lane."""
-    if inflight:
-        if (n_bins, k) not in ((192, 10), (512, 11), (1000, 11)):
-            pytest.skip("in-flight variants on one shape per width class")
-        monkeypatch.setenv("RB_CTABLE_U", inflight)
+    threshold tables in one pass, dense counts; bit-sliced register counters (default) and the shared-memory-atomic variant with
+    the default and extreme numbers of entries in flight per lane.  Reads up to 250 bases take the single-chunk accumulator
+    (max_read_len known), the ragged batch the 16-plane one."""
+    if inflight:                                        # the shared-memory-atomic variant of the kernel (default: bit-sliced)
+        monkeypatch.setenv("RB_CTABLE_ATOMIC", "1")
+        if inflight != "atomic":
+            if (n_bins, k) not in ((192, 10), (512, 11), (1000, 11)):
+                pytest.skip("in-flight variants on one shape per width class")
+            monkeypatch.setenv("RB_CTABLE_U", inflight)
     plan, of, gf = make_filter_pair(n_bins, 1500, 2000, k)
     assert plan["n_bins"] == n_bins
     gf.enable_kmer_table(0)
@@ -388,6 +392,12 @@ def test_medium_rows_group_loaded_table(n_bins, k, inflight, monkeypatch):
         exp = of.count_batch(bases, off, luts[t], dense=False, n_threads=8)
         for key in ("max_count", "hit", "argmax_bin"):
             assert np.array_equal(both[key][t], exp[key]), (t, key)
+    short = [250] * 70 + [0, 1, k - 1, k, k + 1, 31, 32, 33, 64, 100, 249, 251, 253 + k, 254 + k - 1]
+    sb, so = synth.ragged_reads(plan["bases"], short, seed=12, frac_from_ref=0.7, n_frac=0.004, lower_frac=0.1)
+    sb[int(so[5]):int(so[6])] = ord("N")
+    sexp = of.count_batch(sb, so, luts[0], n_threads=8)
+    assert_same_results(gf.count_batch(sb, so, luts[0], dense=True), sexp)
+    assert_same_results(gf.count_batch(sb, so, luts[0], dense=False), sexp, dense=False)
     # the roofline's traffic figure: one entry per k-mer position, whole 128-byte lines
     import torch
     d_b, d_o = torch.from_numpy(bases).cuda(), torch.from_numpy(off.astype(np.int64)).cuda()
