@@ -45,9 +45,11 @@ WORKLOADS = {
     "cfg2_k14": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=14, chunk=250, reads=1_000_000),
     "cfg2_k16": dict(lengths=[3_999_999] * 100, seed0=2, fragment=4_200_000, k=16, chunk=250, reads=262_144),
     "w4_200x2Mb_200bins": dict(lengths=[1_999_999] * 200, seed0=2, fragment=2_100_000, k=13, chunk=250, reads=1_000_000),
-    # mid-size filters (a few target chromosomes): rows of 5, 16 and 64 words, all on the postings path
+    # mid-size filters (a few target chromosomes): rows of 5, 16, 32 words (group-loaded k-mer table) and 64 words (postings)
     "w5_30Mb_303bins": dict(lengths=[10_050_000] * 3, seed0=400, fragment=100_000, k=13, chunk=250, reads=262_144, cpu_build_frags=64),
     "w16_100Mb_1010bins": dict(lengths=[10_050_000] * 10, seed0=400, fragment=100_000, k=13, chunk=250, reads=262_144,
+                               cpu_build_frags=128),
+    "w32_200Mb_2020bins": dict(lengths=[10_050_000] * 20, seed0=400, fragment=100_000, k=13, chunk=250, reads=262_144,
                                cpu_build_frags=128),
     "w64_400Mb_4040bins": dict(lengths=[10_050_000] * 40, seed0=400, fragment=100_000, k=13, chunk=250, reads=131_072,
                                cpu_build_frags=256),

@@ -1,11 +1,11 @@
-// ibf_ctable.cu -- one-k-mer table for MEDIUM filters (rows of 3..16 words, 129..1024 bins), entries loaded by lane groups.
+// ibf_ctable.cu -- one-k-mer table for MEDIUM filters (rows of 3..32 words, 129..2048 bins), entries loaded by lane groups.
 //
 // Same tabulated function as ibf_table.cu -- what seqan::count does per k-mer and strand (src/IBF/IBFClassify.cpp:149-150,
 // SURVEY.md App. A.6):
 //
 //     table[x] = [ AND_i row(h_i(x)) : G words ][ AND_i row(h_i(revcomp(x))) : G words ]        x in [0, 4^k)
 //
-// with the row padded to G = 4, 8 or 16 words, so an entry is G pieces of 16 bytes = 64, 128 or 256 bytes, aligned to its
+// with the row padded to G = 4, 8, 16 or 32 words, so an entry is G pieces of 16 bytes = 64 .. 512 bytes, aligned to its
 // size.  What differs is who loads it.  A lane that fetches a whole 64..256-byte entry issues 4..16 separate 16-byte loads,
 // i.e. 4..16 requests per k-mer position; here G ADJACENT LANES load one entry with ONE instruction (lane p takes piece p),
 // which the memory system serves as one request per 128-byte line (profiles/r1_d_gather_sweep3_coop.jsonl) -- one or two
@@ -182,16 +182,19 @@ constexpr int kCbPlanes = 7;                       // per-lane planes: up to 127
 constexpr int kCbCap = (1 << kCbPlanes) - 1;
 
 template <int G> struct CbGeom {
-    static constexpr int LV = G == 4 ? 3 : G == 8 ? 2 : 1;       // butterfly levels
+    static constexpr int LV = G == 4 ? 3 : G == 8 ? 2 : G == 16 ? 1 : 0;   // butterfly levels
     static constexpr int NPF = kCbPlanes + LV;                   // planes after the fold
-    static constexpr int RW = G == 16 ? 2 : 1;                   // 32-bit words of bins a lane ends up with
+    static constexpr int RW = G == 32 ? 4 : G == 16 ? 2 : 1;     // 32-bit words of bins a lane ends up with
     static constexpr int B = G == 4 ? 16 : 32;                   // bins per such word
     static constexpr int NG = 32 / G;
-    static constexpr int CHUNK = NG * kCbCap;                    // positions per warp chunk: 1016 / 508 / 254
+    static constexpr int CHUNK = NG * kCbCap;                    // positions per warp chunk: 1016 / 508 / 254 / 127
+    // accumulator planes when the caller promises short reads: one chunk, or (G = 32) two chunks
+    static constexpr int NPS = G == 32 ? 8 : NPF;
+    static constexpr int SHORT_POS = G == 32 ? 254 : CHUNK;      // positions such a read may have
 };
 
 template <int G, int NPA>
-__global__ void __launch_bounds__(kCtWarps * 32) count_ctable_bs_kernel(const CountArgs a, const uint4 *__restrict__ table)
+__global__ void __launch_bounds__(kCtWarps * 32, 2) count_ctable_bs_kernel(const CountArgs a, const uint4 *__restrict__ table)
 {
     using Ge = CbGeom<G>;
     constexpr int NG = Ge::NG, RW = Ge::RW, B = Ge::B, NPF = Ge::NPF;
@@ -208,7 +211,10 @@ __global__ void __launch_bounds__(kCtWarps * 32) count_ctable_bs_kernel(const Co
     const uint32_t w0 = 2u * (p % (G / 2));
     // the bins this lane reports after the fold: 32-bit word i of its piece (upper half of the words for lane bit 4, ...)
     uint32_t bin0[RW];
-    if constexpr (G == 16) {
+    if constexpr (G == 32) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) bin0[r] = 64u * w0 + 32u * r;
+    } else if constexpr (G == 16) {
         bin0[0] = 64u * w0 + 64u * ((lane >> 4) & 1u);
         bin0[1] = bin0[0] + 32u;
     } else {
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(kCtWarps * 32) count_ctable_bs_kernel(const Co
         const uint64_t len = a.read_off[read + 1] - off;
         uint32_t flag = read_flag_of(len, k);
         // a read longer than the caller's max_read_len promised does not fit the NPA-bit accumulator: flag 3, not classified
-        if (flag == 0 && NPA < 16 && len - k + 1 > (uint64_t)Ge::CHUNK) flag = 3;
+        if (flag == 0 && NPA < 16 && len - k + 1 > (uint64_t)Ge::SHORT_POS) flag = 3;
         if (lane == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
 
         uint32_t acc[RW][NPA];
@@ -291,7 +297,12 @@ __global__ void __launch_bounds__(kCtWarps * 32) count_ctable_bs_kernel(const Co
                 }
                 // sum over the lanes that own the same piece
                 uint32_t res[RW][NPF];
-                {
+                if constexpr (G == 32) {                                   // the whole warp shares one piece layout: nothing to fold
+#pragma unroll
+                    for (int q = 0; q < NPF; ++q)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) res[r][q] = pl[q][r];
+                } else {
                     uint32_t f1[kCbPlanes + 1][2];
                     fold_words<4, kCbPlanes, 16>(pl, f1, lane);
                     if constexpr (G == 16) {
@@ -391,8 +402,8 @@ void launch_count_bs(const CountArgs &a, const uint64_t *table, int sm_count, cu
 template <int G>
 void launch_count_bs_np(const CountArgs &a, const uint64_t *table, uint32_t max_read_len, int sm_count, cudaStream_t st)
 {
-    const bool single_chunk = max_read_len != 0 && (max_read_len < a.fv.hp.k || max_read_len - a.fv.hp.k + 1 <= (uint32_t)CbGeom<G>::CHUNK);
-    if (single_chunk) launch_count_bs<G, CbGeom<G>::NPF>(a, table, sm_count, st);
+    const bool short_reads = max_read_len != 0 && (max_read_len < a.fv.hp.k || max_read_len - a.fv.hp.k + 1 <= (uint32_t)CbGeom<G>::SHORT_POS);
+    if (short_reads) launch_count_bs<G, CbGeom<G>::NPS>(a, table, sm_count, st);
     else launch_count_bs<G, 16>(a, table, sm_count, st);
 }
 
@@ -436,7 +447,7 @@ void launch_count_gu(const CountArgs &a, const uint64_t *table, int sm_count, cu
 // lanes per entry (= padded row words) for a row of `stride` words; 0: this layout does not apply
 int ctable_lanes(uint64_t stride)
 {
-    return stride < 3 ? 0 : stride <= 4 ? 4 : stride <= 8 ? 8 : stride <= 16 ? 16 : 0;
+    return stride < 3 ? 0 : stride <= 4 ? 4 : stride <= 8 ? 8 : stride <= 16 ? 16 : stride <= 32 ? 32 : 0;
 }
 
 int launch_ctable_build(const FilterView &fv, uint64_t *table, uint64_t n_kmers, int sm_count, cudaStream_t st)
@@ -449,6 +460,7 @@ int launch_ctable_build(const FilterView &fv, uint64_t *table, uint64_t n_kmers,
     case 4: ctable_build_kernel<4><<<gx, 256, 0, st>>>(fv, t, n_kmers); break;
     case 8: ctable_build_kernel<8><<<gx, 256, 0, st>>>(fv, t, n_kmers); break;
     case 16: ctable_build_kernel<16><<<gx, 256, 0, st>>>(fv, t, n_kmers); break;
+    case 32: ctable_build_kernel<32><<<gx, 256, 0, st>>>(fv, t, n_kmers); break;
     default: return -1;
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -466,6 +478,7 @@ int launch_count_ctable(const CountArgs &a, const uint64_t *table, uint32_t max_
         case 4: launch_count_bs_np<4>(a, table, max_read_len, sm_count, st); break;
         case 8: launch_count_bs_np<8>(a, table, max_read_len, sm_count, st); break;
         case 16: launch_count_bs_np<16>(a, table, max_read_len, sm_count, st); break;
+        case 32: launch_count_bs_np<32>(a, table, max_read_len, sm_count, st); break;
         default: return -1;
         }
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
@@ -474,6 +487,7 @@ int launch_count_ctable(const CountArgs &a, const uint64_t *table, uint32_t max_
     case 4: launch_count_gu<4>(a, table, sm_count, st); break;
     case 8: launch_count_gu<8>(a, table, sm_count, st); break;
     case 16: launch_count_gu<16>(a, table, sm_count, st); break;
+    case 32: launch_count_gu<32>(a, table, sm_count, st); break;
     default: return -1;
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

@@ -163,7 +163,7 @@ extern "C" RB_API int rb_microbench_gather_coop(const void *d_buf, uint64_t n_ro
         return cudaGetLastError() == cudaSuccess ? RB_OK : RB_ERR_CUDA;                                            \
     }
     RB_COOP(16, 16) RB_COOP(32, 16) RB_COOP(32, 32) RB_COOP(64, 16) RB_COOP(64, 32) RB_COOP(128, 16) RB_COOP(128, 32)
-    RB_COOP(256, 16) RB_COOP(256, 32)
+    RB_COOP(256, 16) RB_COOP(256, 32) RB_COOP(512, 16)
 #undef RB_COOP
     return RB_ERR_INVALID_ARG;
 }

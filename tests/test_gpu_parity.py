@@ -161,9 +161,9 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
             sb[int(so[5]):int(so[6])] = ord("N")
             sb[int(so[7]) + 100] = ord("U")
             sexp = of.count_batch(sb, so, lut, n_threads=4)
-            if gf.bin_width <= 16:                       # rows of 5..16 words: the group-loaded k-mer table comes first
+            if gf.bin_width <= 32:                       # rows of 5..32 words: the group-loaded k-mer table comes first
                 gf.enable_kmer_table(0)
-                lanes = 8 if gf.bin_width <= 8 else 16
+                lanes = 8 if gf.bin_width <= 8 else 16 if gf.bin_width <= 16 else 32
                 assert (gf.kmer_table_kind(), gf.kmer_table_bytes(), gf.kmer_table_span()) == (4, 4 ** k * lanes * 16, 1)
                 assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
                 assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)
@@ -361,9 +361,10 @@ def test_packed_pieces_ship_the_bad_plane_only_when_needed(monkeypatch):
 
 
 @pytest.mark.parametrize("inflight", ["", "atomic", "1", "8"])
-@pytest.mark.parametrize("n_bins,k", [(129, 11), (192, 10), (256, 11), (257, 11), (320, 10), (512, 11), (513, 10), (1000, 11), (1024, 10)])
+@pytest.mark.parametrize("n_bins,k", [(129, 11), (192, 10), (256, 11), (257, 11), (320, 10), (512, 11), (513, 10), (1000, 11), (1024, 10),
+                                        (1025, 10), (1500, 11), (2048, 10)])
 def test_medium_rows_group_loaded_table(n_bins, k, inflight, monkeypatch):
-    """Rows of 3..16 words (129..1024 bins): k-mer table entries padded to 4 / 8 / 16 words, one entry per group of as many lanes
+    """Rows of 3..32 words (129..2048 bins): k-mer table entries padded to 4 / 8 / 16 / 32 words, one entry per group of as many lanes
     (ibf_ctable.cu).  Every width class at both ends, ragged and multi-chunk reads, N / IUPAC windows (hashed on the fly), two
     threshold tables in one pass, dense counts; bit-sliced register counters (default) and the shared-memory-atomic variant with
     the default and extreme numbers of entries in flight per lane.  Reads up to 250 bases take the single-chunk accumulator
@@ -371,13 +372,13 @@ def test_medium_rows_group_loaded_table(n_bins, k, inflight, monkeypatch):
     if inflight:                                        # the shared-memory-atomic variant of the kernel (default: bit-sliced)
         monkeypatch.setenv("RB_CTABLE_ATOMIC", "1")
         if inflight != "atomic":
-            if (n_bins, k) not in ((192, 10), (512, 11), (1000, 11)):
+            if (n_bins, k) not in ((192, 10), (512, 11), (1000, 11), (1500, 11)):
                 pytest.skip("in-flight variants on one shape per width class")
             monkeypatch.setenv("RB_CTABLE_U", inflight)
     plan, of, gf = make_filter_pair(n_bins, 1500, 2000, k)
     assert plan["n_bins"] == n_bins
     gf.enable_kmer_table(0)
-    lanes = 4 if n_bins <= 256 else 8 if n_bins <= 512 else 16
+    lanes = 4 if n_bins <= 256 else 8 if n_bins <= 512 else 16 if n_bins <= 1024 else 32
     assert (gf.kmer_table_kind(), gf.kmer_table_span(), gf.kmer_table_bytes()) == (4, 1, 4 ** k * lanes * 16)
     bases, off = synth.ragged_reads(plan["bases"], RAGGED + [k - 1, k, k + 1, 1023 + k, 1024 + k, 3000], seed=31, frac_from_ref=0.7,
                                     n_frac=0.004, lower_frac=0.1)
@@ -414,6 +415,7 @@ def test_postings_slots(n_blocks, order, slot_bytes, ring, monkeypatch):
     / many lists into the overflow area, 1 024 holds nearly all -- with ring depths 1 and 2 next to the default."""
     monkeypatch.setenv("RB_POSTINGS_ORDER", order)
     monkeypatch.setenv("RB_POSTINGS_LAYOUT", "slots")
+    monkeypatch.setenv("RB_CTABLE", "0")                    # 18 row words: the group-loaded k-mer table would come first
     if slot_bytes:
         monkeypatch.setenv("RB_SLOT_BYTES", str(slot_bytes))
     if ring:
@@ -456,6 +458,7 @@ def test_postings_long_lists(n_blocks, order, monkeypatch):
     with the ids dealt over the groups (default) and ascending (RB_POSTINGS_ORDER=0)."""
     monkeypatch.setenv("RB_POSTINGS_ORDER", order)
     monkeypatch.setenv("RB_POSTINGS_LAYOUT", "lists")
+    monkeypatch.setenv("RB_CTABLE", "0")                    # 18 row words: the group-loaded k-mer table would come first
     k, n_hash = 11, 3
     ref = [synth.random_bases(1500, 300 + i) for i in range(1100)]
     plan = synth.build_plan(ref, 2000, k, n_hash=n_hash)

@@ -17,6 +17,8 @@ import bench                                       # noqa: E402
 
 
 def main():
+    os.environ["RB_CTABLE"] = "0"          # rows of <= 32 words would take the group-loaded k-mer table
+
     w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg3_3.1Gb_31kbins"]
     n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else w["reads"]
     dev = torch.device("cuda", 0)

@@ -18,6 +18,8 @@ from readbouncer_b200 import synth                 # noqa: E402
 
 
 def main():
+    os.environ["RB_CTABLE"] = "0"          # rows of <= 32 words would take the group-loaded k-mer table
+
     k, n_hash = 9, 3
     ref = [synth.random_bases(1500, 300 + i) for i in range(1100)]
     plan = synth.build_plan(ref, 2000, k, n_hash=n_hash)
