@@ -261,22 +261,30 @@ __global__ void __launch_bounds__(kCtWarps * 32, 2) count_ctable_bs_kernel(const
                         nbad += d >> 2;
                     }
                     x &= kmask;
-                    for (uint32_t j = j0; j < j1; j += 4) {
-                        uint32_t m[4][4];
+                    // four entries in flight per lane.  (Issuing the next four before the current four are added was measured
+                    // 4-6 % slower on all four widths, profiles/r2_z_ctable_prefetch.jsonl: 16 warps per SM x 4 entries already
+                    // cover the latency; what is left is the address chain of the sliding k-mer and the ~3 800 instructions.)
+                    auto fetch4 = [&](const uint32_t jb, uint4 (&v)[4]) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            uint4 v = make_uint4(0, 0, 0, 0);
-                            if (j + u < j1) {
-                                if (nbad == 0) v = __ldg(table + x * G + p);
-                                else v = piece_hashed(a.fv, dig + j + u, rev, w0);
-                                if (j + u + 1 < j1) {
-                                    const uint32_t dout = dig[j + u], din = dig[j + u + k];
+                            v[u] = make_uint4(0, 0, 0, 0);
+                            if (jb + u < j1) {
+                                if (nbad == 0) v[u] = __ldg(table + x * G + p);
+                                else v[u] = piece_hashed(a.fv, dig + jb + u, rev, w0);
+                                if (jb + u + 1 < j1) {
+                                    const uint32_t dout = dig[jb + u], din = dig[jb + u + k];
                                     x = ((x << 2) | (din & 3u)) & kmask;
                                     nbad += (din >> 2) - (dout >> 2);
                                 }
                             }
-                            m[u][0] = v.x; m[u][1] = v.y; m[u][2] = v.z; m[u][3] = v.w;
                         }
+                    };
+                    uint4 nxt[4];
+                    fetch4(j0, nxt);
+                    for (uint32_t j = j0; j < j1; j += 4) {
+                        uint32_t m[4][4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { m[u][0] = nxt[u].x; m[u][1] = nxt[u].y; m[u][2] = nxt[u].z; m[u][3] = nxt[u].w; }
                         // carry-save add of the four masks into planes ones / twos, the carry ripples through the rest
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
@@ -293,6 +301,7 @@ __global__ void __launch_bounds__(kCtWarps * 32, 2) count_ctable_bs_kernel(const
                                 carry = c;
                             }
                         }
+                        if (j + 4 < j1) fetch4(j + 4, nxt);
                     }
                 }
                 // sum over the lanes that own the same piece
