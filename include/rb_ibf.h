@@ -81,8 +81,10 @@ typedef struct rb_ibf_info_t {
     int32_t shard, n_shards;
     int32_t kmer_table_span;   /* consecutive k-mers per table entry (1..4), 0 if not built */
     uint64_t kmer_table_bytes; /* bytes of the k-mer table, 0 if not built */
-    int32_t kmer_table_kind;   /* 0 none, 1 dense k-mer / window table (rows <= 4 words), wider rows: 2 postings as pointer +
-                                  lists (default), 3 postings in fixed slots per k-mer (RB_POSTINGS_LAYOUT=slots) */
+    int32_t kmer_table_kind;   /* 0 none, 1 dense k-mer / window table (rows <= 2 words; 3-4 words when kind 4 does not fit),
+                                  4 one k-mer per entry, rows of 3..32 words padded to 4/8/16/32 and loaded by as many lanes,
+                                  wider rows: 2 postings as pointer + lists (default), 3 postings in fixed slots per k-mer
+                                  (RB_POSTINGS_LAYOUT=slots) */
 } rb_ibf_info_t;
 
 /* ---- host-side scalar helpers (FP64, bit-exact with the reference) ------- */
@@ -233,7 +235,7 @@ RB_API int rb_ibf_count_batch_sharded(const rb_ibf *const *shards, uint32_t n_sh
  * time (the copy already loaded in the process, if any), so the library itself does not link NCCL. */
 RB_API int rb_keys_combine_nccl(void *nccl_comm, uint64_t *d_keys, uint64_t n, rb_stream stream);
 
-/* Direct k-mer table for narrow filters (row <= 4 words, k <= 16): the AND of the h probed rows is a
+/* Direct k-mer table for narrow filters (row <= 2 words, k <= 16): the AND of the h probed rows is a
  * pure function of the k-mer, so it is tabulated once for all ACGT k-mers and both strands.  An entry
  * covers a window of `span` consecutive k-mers (k+span-1 bases).  span 1: 4^k entries of 16*col_words
  * bytes (2.1 GB for k=13, 100 bins), read by one lane each.  span 2..4 (rows <= 2 words): entries of
@@ -246,8 +248,13 @@ RB_API int rb_keys_combine_nccl(void *nccl_comm, uint64_t *d_keys, uint64_t n, r
  * min(60 % of the free HBM, 80 GiB) (env RB_KMER_TABLE=0 disables, RB_KMER_TABLE_MAX_GB changes the
  * cap, RB_KMER_TABLE_SPAN the widest span tried); dropped by rb_ibf_insert_batch*.  This call
  * (re)builds it now under the given byte budget (0 = automatic); UINT64_MAX disables the table for
- * this handle.
- * Wide filters (rows > 4 words, <= 65280 local bins, k <= 15) get a POSTINGS table instead: the AND of
+ * this handle.  With the automatic budget an explicit call may take up to 85 % of the free HBM when only the one-k-mer
+ * table is possible (k = 16).
+ * MEDIUM filters (rows of 3..32 words = 129..2048 bins, k <= 16) get the same one-k-mer table with the row padded to
+ * 4 / 8 / 16 / 32 words: entries of 64..512 bytes, each loaded by 4..32 adjacent lanes in one instruction and counted in
+ * bit-sliced registers (ibf_ctable.cu; 8.6 GB for 303 bins, 34 GB for 2020 bins at k = 13).  RB_CTABLE=0 turns this layout
+ * off (rows of 3-4 words then use the unpadded lane-per-entry table, wider ones the postings below).
+ * Wide filters (rows > 32 words, or > 4 words when that table does not fit; <= 65280 local bins, k <= 15) get a POSTINGS table instead: the AND of
  * the probed rows is ~1 % dense by the reference's own sizing, so the list of set bins of every
  * k-mer (2 bytes each, ~50 GB for a human-genome filter at k=13) replaces streaming 2*h rows of
  * thousands of bytes per position; same policy, budget and env switches.  Two layouts: pointer + lists
@@ -258,8 +265,10 @@ RB_API int rb_keys_combine_nccl(void *nccl_comm, uint64_t *d_keys, uint64_t n, r
  * SUPPORTED ENVELOPE of the table paths (outside it results are the same, from the hashed / streaming kernels):
  *   rows <= 2 words (<= 128 bins): window tables for k + span - 1 <= 16, i.e. span 3 up to k = 14, span 2 up to k = 15,
  *                                   span 1 up to k = 16; k >= 17: hashed probes (count_tile_kernel)
- *   rows of 3-4 words:             span 1 up to k = 16
- *   rows > 4 words:                postings up to k = 15 while 4^k slots fit the HBM budget (k = 13 for a human-sized
+ *                                   (k = 16, 65-128 bins: 137 GB, built on an explicit request / by the joint planner only)
+ *   rows of 3-32 words:            padded one-k-mer table while 4^k * 16 * {4,8,16,32} bytes fit (k = 13: 4.3 .. 34 GB;
+ *                                   k = 15 up to 8 words); else the unpadded table (3-4 words) / postings (5+ words)
+ *   rows > 32 words:               postings up to k = 15 while 4^k slots fit the HBM budget (k = 13 for a human-sized
  *                                   filter); else count_stream_kernel
  * bench.py's `secondary` reports k = 13, 15 and 17 on the BASELINE config #2 shape so the steps are visible. */
 RB_API int rb_ibf_enable_kmer_table(rb_ibf *f, uint64_t max_table_bytes, rb_stream stream);
