@@ -9,7 +9,8 @@ insert kernels) from 100 synthetic 4 Mb genomes.  Multi-GPU = read-sharded with 
 
 The default line also carries `secondary`: at 1 GPU BASELINE config #3 (human depletion: 3.1 Gb, 31 008
 bins, postings kernel) with its GPU build (= config #4) beside a CPU build sample, config #2 at k = 15 and
-k = 17 (where the window table stops applying), config #1's 51-bin filter, and the reference's published
+k = 17 (where the window table stops applying), config #1's 51-bin filter, two target-panel filters of 303 and 2 020 bins
+(rows of 5 and 32 words: the group-loaded k-mer table of ibf_ctable.cu), and the reference's published
 3-target + 1-depletion workload through the C++ driver; at N > 1 GPUs BASELINE config #5's per-GPU workload
 (bin-sharded 30 Gb filter, one eighth per GPU) with the NCCL all-reduce(MAX) of the per-read keys inside the
 timed region.  `--no-secondary` or any explicit `--workload` prints the primary line alone.
@@ -69,7 +70,8 @@ WORKLOADS = {
                                        reads=16_384, bins_per_rank=512),
 }
 DEFAULT_WORKLOAD = "cfg2_100x4Mb_100bins"
-SECONDARY_1GPU = ["cfg3_3.1Gb_31kbins", "cfg2_k15", "cfg2_k17", "cfg1_5Mb_51bins", "readme_3targets_1deplete", "live_3targets_1deplete"]
+SECONDARY_1GPU = ["cfg3_3.1Gb_31kbins", "cfg2_k15", "cfg2_k17", "cfg1_5Mb_51bins", "w5_30Mb_303bins", "w32_200Mb_2020bins",
+                  "readme_3targets_1deplete", "live_3targets_1deplete"]
 README_READS = 100_000      # the reference's one published workload (README.md:233-262), tools/readme_bench.py
 SECONDARY_NGPU = ["cfg5_3.7Gb_37kbins_per_gpu"]
 ERROR_RATE = 0.1
