@@ -78,8 +78,8 @@ int postings_sample_units(const FilterView &fv, uint32_t *d_scratch, uint32_t n_
                           cudaStream_t st);
 int postings_build_ptr(const FilterView &fv, uint32_t *d_ptr, uint64_t *total_units, int sm_count, cudaStream_t st);
 int postings_fill(const FilterView &fv, const uint32_t *d_ptr, uint16_t *d_ids, int sm_count, cudaStream_t st);
-int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint16_t *d_ids, uint32_t max_read_len, int sm_count,
-                          cudaStream_t st);
+int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint16_t *d_ids, uint32_t max_read_len, double mean_units,
+                          int sm_count, cudaStream_t st);
 // the same lists as fixed, 128-byte-aligned slots per k-mer, fetched by bulk copies into shared-memory rings (ibf_postings.cu)
 bool slots_applicable(const FilterView &fv);
 int slots_sample_lengths(const FilterView &fv, uint32_t *d_scratch, uint32_t n_sample, std::vector<uint32_t> *lengths, int sm_count,

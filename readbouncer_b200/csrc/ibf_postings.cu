@@ -33,6 +33,7 @@ namespace {
 // Threads per CTA (template parameter of the lookup kernel) follow from how many CTAs of counters fit the shared memory
 // of an SM: 3 x 256, 2 x 384 or 1 x 768 -- always 24 warps per SM under the 85-register ceiling of 768 threads.
 constexpr int kPostPiece = 512;               // k-mer positions staged per pass over a read
+constexpr double kSub8Units = 8.0, kSub16Units = 16.0;   // mean list length (16-byte units) up to which 8 / 16 lanes own a list
 constexpr int kPostInFlight = 4;              // lists a warp loads before it counts them (even: strands alternate)
 
 // base-5 hashes of the forward and reverse-complement strand of the ACGT k-mer x (ranks, first base most significant)
@@ -275,6 +276,86 @@ __device__ __noinline__ void add_hashed(const FilterView &fv, const uint8_t *dig
 template <int CB>
 __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return CB == 8 ? __vmaxu4(a, b) : __vmaxu2(a, b); }
 
+// Per-read epilogue of the CTA-per-read kernels: M = max over bins of max(fwd, rev) and its lowest bin, one key per threshold
+// table; the counters go back to zero.  Called by all threads after a __syncthreads().
+template <int CB, int kPostThreads>
+__device__ __forceinline__ void postings_epilogue(const CountArgs &a, const uint64_t read, const uint64_t len, const uint32_t flag,
+                                                  uint32_t *const cntF, uint32_t *const cntR, uint32_t *const s_red)
+{
+    constexpr int PER = 32 / CB;
+    constexpr uint32_t CMASK = (CB == 8) ? 0xFFu : 0xFFFFu;
+    constexpr int kPostWarps = kPostThreads / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t nbl = a.fv.n_bins_local;
+    // ---- epilogue: M = max over bins of max(fwd, rev), its lowest bin; counters back to zero ----------------
+    // The sentinel's counter lies in the quad of words after the bins: it is not scanned, only cleared.
+    const uint32_t sent_word = postings_sentinel(nbl) / PER;
+    const uint32_t scan_quads = ((uint32_t)nbl + 4u * PER - 1u) / (4u * PER);
+    if (tid == 0) { cntF[sent_word] = 0; cntR[sent_word] = 0; }
+    if (a.counts_fwd || a.counts_rev) {                                 // dense counts on request (tests, tools)
+        for (uint32_t w = tid; w * PER < nbl; w += kPostThreads) {
+            const uint32_t f = cntF[w], r = cntR[w];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const uint32_t bin = w * PER + i;
+                if (bin < nbl) {
+                    if (a.counts_fwd) a.counts_fwd[read * nbl + bin] = (uint16_t)((f >> (i * CB)) & CMASK);
+                    if (a.counts_rev) a.counts_rev[read * nbl + bin] = (uint16_t)((r >> (i * CB)) & CMASK);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // One pass over quads of counter words (LDS.128 / STS.128): every thread keeps the largest count it has seen and
+    // the first bin that had it (its bins ascend); a quad is unpacked only when the SWAR test says that one of its
+    // counters may beat that.  A maximum below every threshold of the read yields key 0 whatever it is, so the search
+    // starts at min(thr) - 1 and the unpacking is rare (random reads: never).
+    constexpr uint32_t LOW = CB == 8 ? 0x7F7F7F7Fu : 0x7FFF7FFFu, ONES = CB == 8 ? 0x01010101u : 0x00010001u;
+    constexpr uint32_t HALF = (CMASK + 1u) / 2u;                        // 128 or 32 768
+    uint32_t thr_min = CMASK + 1u;                                      // not classified: nothing to find
+    if (flag == 0)
+        for (uint32_t t = 0; t < a.n_lut; ++t) thr_min = min(thr_min, (uint32_t)__ldg(a.lut + (size_t)t * kLutSize + len));
+    uint32_t cur = min(thr_min, CMASK + 1u) - (thr_min ? 1u : 0u), cur_bin = 0;
+    // counter c > cur  =>  c >= HALF, or (c & LOW) + (HALF - 1 - cur) carries into the top bit (cur < HALF);
+    // for cur >= HALF only the first test is left: necessary, not sufficient -- the unpacking decides
+    uint32_t add = (HALF - 1u - min(cur, HALF - 1u)) * ONES;
+    uint4 *const qF = reinterpret_cast<uint4 *>(cntF), *const qR = reinterpret_cast<uint4 *>(cntR);
+    for (uint32_t qd = tid; qd < scan_quads; qd += kPostThreads) {
+        const uint4 f = qF[qd], r = qR[qd];
+        qF[qd] = make_uint4(0, 0, 0, 0); qR[qd] = make_uint4(0, 0, 0, 0);
+        const uint32_t gx = f.x | r.x, gy = f.y | r.y, gz = f.z | r.z, gw = f.w | r.w;
+        const uint32_t h = (((gx & LOW) + add) | gx) | (((gy & LOW) + add) | gy) | (((gz & LOW) + add) | gz) | (((gw & LOW) + add) | gw);
+        if (h & ~LOW) {
+            const uint32_t m[4] = {vmax<CB>(f.x, r.x), vmax<CB>(f.y, r.y), vmax<CB>(f.z, r.z), vmax<CB>(f.w, r.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const uint32_t v = (m[j] >> (i * CB)) & CMASK;
+                    if (v > cur) { cur = v; cur_bin = (4u * qd + j) * PER + i; }
+                }
+            add = (HALF - 1u - min(cur, HALF - 1u)) * ONES;
+        }
+    }
+    // (count, lowest bin) as one key: larger count wins, then the smaller bin (bins < 65 535)
+    uint32_t best_key = __reduce_max_sync(0xffffffffu, (cur << 16) | (0xFFFFu - cur_bin));
+    if (lane == 0) s_red[warp] = best_key;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kPostWarps; ++i) best_key = max(best_key, s_red[i]);
+    const uint32_t M = best_key >> 16, best_bin = 0xFFFFu - (best_key & 0xFFFFu);
+    if (tid < (int)a.n_lut) {
+        uint64_t key = 0;
+        if (flag == 0) {
+            const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)tid * kLutSize + len);
+            if (M >= thr) key = pack_key(M, (uint32_t)(a.fv.bin_begin + best_bin));
+        }
+        uint64_t *const dst = a.keys + (size_t)tid * a.n_reads + read;
+        if (a.keys_shared) { if (key) key_max(dst, key, 1); }          // all bin shards fold into one array (NVLink peer atomics)
+        else *dst = key;
+    }
+}
+
 template <int CB, int kPostThreads>
 __global__ void __launch_bounds__(kPostThreads, 768 / kPostThreads)
 count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const uint4 *__restrict__ ids, const uint32_t cnt_words)
@@ -375,73 +456,132 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
         }
         __syncthreads();
 
-        // ---- epilogue: M = max over bins of max(fwd, rev), its lowest bin; counters back to zero ----------------
-        // The sentinel's counter lies in the quad of words after the bins: it is not scanned, only cleared.
-        const uint32_t sent_word = postings_sentinel(nbl) / PER;
-        const uint32_t scan_quads = ((uint32_t)nbl + 4u * PER - 1u) / (4u * PER);
-        if (tid == 0) { cntF[sent_word] = 0; cntR[sent_word] = 0; }
-        if (a.counts_fwd || a.counts_rev) {                                 // dense counts on request (tests, tools)
-            for (uint32_t w = tid; w * PER < nbl; w += kPostThreads) {
-                const uint32_t f = cntF[w], r = cntR[w];
+        postings_epilogue<CB, kPostThreads>(a, read, len, flag, cntF, cntR, s_red);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// lookup for SHORT lists: LG lanes per list, 32 / LG lists per warp step
+// ------------------------------------------------------------------------------------------
+// The kernel above spends a warp-wide step on every list: right for the ~360 ids per list of a human-sized filter, wasteful
+// for a 4 000-bin one (46 ids = 6 units: most lanes idle, ~40 warp instructions and a dependent pair of requests per list,
+// four lists in flight per warp -- 13.6 M chunks/s with the DRAM a third busy, profiles/r2_x_*).  Here a group of LG = 8 or 16
+// lanes owns a list: lane s loads unit s (and s + LG, ... of a longer list), 4 or 2 lists per warp step, four steps' bounds
+// and then four steps' units requested before the first counter is touched (16 or 8 lists in flight per warp in 16
+// registers).  The order of the ids inside a list does not matter (counting is commutative), so the same table serves both
+// kernels; the launcher picks by the mean list length of the table.
+template <int CB>
+__device__ __forceinline__ void add_ids_skip(uint32_t *cnt, const uint4 v, const uint32_t sentinel)
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int i = 0; i < PER; ++i) {
-                    const uint32_t bin = w * PER + i;
-                    if (bin < nbl) {
-                        if (a.counts_fwd) a.counts_fwd[read * nbl + bin] = (uint16_t)((f >> (i * CB)) & CMASK);
-                        if (a.counts_rev) a.counts_rev[read * nbl + bin] = (uint16_t)((r >> (i * CB)) & CMASK);
+    for (int i = 0; i < 4; ++i) {
+        if ((w[i] & 0xFFFFu) != sentinel) bump<CB>(cnt, w[i]);
+        if ((w[i] >> 16) != sentinel) bump<CB>(cnt, w[i] >> 16);
+    }
+}
+
+template <int CB, int kPostThreads, int LG>
+__global__ void __launch_bounds__(kPostThreads, 768 / kPostThreads)
+count_postings_sub_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const uint4 *__restrict__ ids, const uint32_t cnt_words)
+{
+    constexpr int kPostWarps = kPostThreads / 32;
+    constexpr int NL = 32 / LG;                                          // lists per warp step
+    constexpr int U = 4;                                                 // steps in flight
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint32_t *const cntF = s_mem, *const cntR = s_mem + cnt_words;
+    uint32_t *const s_x = s_mem + 2 * cnt_words;                         // [kPostPiece] packed k-mer or ~0u (not ACGT)
+    uint8_t *const s_dig = reinterpret_cast<uint8_t *>(s_x + kPostPiece); // [kPostPiece + 32] Dna5 ranks
+    __shared__ uint32_t s_red[kPostWarps];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t grp = (uint32_t)lane / LG, sub = (uint32_t)lane % LG;
+    const uint32_t k = a.fv.hp.k;
+    const uint32_t kbits = 2 * k;
+    const uint32_t kmask = kbits >= 32 ? ~0u : ((1u << kbits) - 1u);
+    const uint32_t sentinel = postings_sentinel(a.fv.n_bins_local);
+    uint32_t *const cnt = (grp & 1u) ? cntR : cntF;                      // pairs alternate strands and every step starts even
+
+    for (uint32_t w = tid; w < 2 * cnt_words; w += kPostThreads) s_mem[w] = 0;
+
+    for (uint64_t read = blockIdx.x; read < a.n_reads; read += gridDim.x) {
+        const uint64_t off = a.read_off[read];
+        const uint64_t len = a.read_off[read + 1] - off;
+        uint32_t flag = read_flag_of(len, k);
+        if (flag == 0 && CB == 8 && len - k + 1 > 255) flag = 3;         // longer than the caller's max_read_len promised
+        if (tid == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
+        __syncthreads();                                                   // counters are zero and visible
+
+        if (flag == 0) {
+            const uint32_t npos = (uint32_t)len - k + 1;
+            for (uint32_t cs = 0; cs < npos; cs += kPostPiece) {
+                const uint32_t cn = min((uint32_t)kPostPiece, npos - cs);
+                __syncthreads();
+                for (uint32_t i = tid; i < cn + k - 1; i += kPostThreads) s_dig[i] = (uint8_t)dna5(a.bases[off + cs + i]);
+                __syncthreads();
+                for (uint32_t j = tid; j < cn; j += kPostThreads) {
+                    uint32_t x = 0, bad = 0;
+                    for (uint32_t u = 0; u < k; ++u) {
+                        const uint32_t d = s_dig[j + u];
+                        x = (x << 2) | (d & 3u);
+                        bad |= d >> 2;
+                    }
+                    s_x[j] = bad ? ~0u : (x & kmask);
+                }
+                __syncthreads();
+                // every warp takes an equal, contiguous, even share of the (position, strand) pairs
+                const uint32_t n_pairs = 2 * cn;
+                const uint32_t share = 2u * ((cn + kPostWarps - 1) / kPostWarps);
+                const uint32_t q_end = min(n_pairs, (warp + 1) * share);
+                for (uint32_t qb = warp * share; qb < q_end; qb += NL * U) {
+                    uint32_t p0[U], n_u[U], hashed = 0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t q = qb + NL * u + grp;
+                        p0[u] = 0; n_u[u] = 0;
+                        if (q < q_end) {
+                            const uint32_t x = s_x[q >> 1];
+                            if (x == ~0u) hashed |= 1u << u;
+                            else {
+                                uint32_t idx = x;
+                                if (q & 1u) {                              // reverse strand: the list of revcomp(x)
+                                    uint32_t v = __brev(~x);
+                                    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+                                    idx = v >> (32 - kbits);
+                                }
+                                p0[u] = __ldg(ptr + idx);
+                                n_u[u] = __ldg(ptr + idx + 1) - p0[u];
+                            }
+                        }
+                    }
+                    uint4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        v[u] = make_uint4(0, 0, 0, 0);
+                        if (sub < n_u[u]) v[u] = __ldg(ids + p0[u] + sub);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (sub < n_u[u]) add_ids_skip<CB>(cnt, v[u], sentinel);
+                        for (uint32_t o = LG; o < n_u[u]; o += LG)       // lists of more than LG units: the group walks on
+                            if (o + sub < n_u[u]) add_ids_skip<CB>(cnt, __ldg(ids + p0[u] + o + sub), sentinel);
+                    }
+                    __syncwarp();
+                    // windows with a non-ACGT base: the whole warp evaluates the rows (rare)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t hm = __ballot_sync(0xffffffffu, (hashed >> u) & 1u);
+                        for (uint32_t g = 0; g < (uint32_t)NL; ++g)
+                            if ((hm >> (g * LG)) & 1u) {
+                                const uint32_t q = qb + NL * u + g;
+                                add_hashed<CB>(a.fv, s_dig + (q >> 1), q & 1u, (q & 1u) ? cntR : cntF, lane);
+                            }
                     }
                 }
             }
-            __syncthreads();
         }
-        // One pass over quads of counter words (LDS.128 / STS.128): every thread keeps the largest count it has seen and
-        // the first bin that had it (its bins ascend); a quad is unpacked only when the SWAR test says that one of its
-        // counters may beat that.  A maximum below every threshold of the read yields key 0 whatever it is, so the search
-        // starts at min(thr) - 1 and the unpacking is rare (random reads: never).
-        constexpr uint32_t LOW = CB == 8 ? 0x7F7F7F7Fu : 0x7FFF7FFFu, ONES = CB == 8 ? 0x01010101u : 0x00010001u;
-        constexpr uint32_t HALF = (CMASK + 1u) / 2u;                        // 128 or 32 768
-        uint32_t thr_min = CMASK + 1u;                                      // not classified: nothing to find
-        if (flag == 0)
-            for (uint32_t t = 0; t < a.n_lut; ++t) thr_min = min(thr_min, (uint32_t)__ldg(a.lut + (size_t)t * kLutSize + len));
-        uint32_t cur = min(thr_min, CMASK + 1u) - (thr_min ? 1u : 0u), cur_bin = 0;
-        // counter c > cur  =>  c >= HALF, or (c & LOW) + (HALF - 1 - cur) carries into the top bit (cur < HALF);
-        // for cur >= HALF only the first test is left: necessary, not sufficient -- the unpacking decides
-        uint32_t add = (HALF - 1u - min(cur, HALF - 1u)) * ONES;
-        uint4 *const qF = reinterpret_cast<uint4 *>(cntF), *const qR = reinterpret_cast<uint4 *>(cntR);
-        for (uint32_t qd = tid; qd < scan_quads; qd += kPostThreads) {
-            const uint4 f = qF[qd], r = qR[qd];
-            qF[qd] = make_uint4(0, 0, 0, 0); qR[qd] = make_uint4(0, 0, 0, 0);
-            const uint32_t gx = f.x | r.x, gy = f.y | r.y, gz = f.z | r.z, gw = f.w | r.w;
-            const uint32_t h = (((gx & LOW) + add) | gx) | (((gy & LOW) + add) | gy) | (((gz & LOW) + add) | gz) | (((gw & LOW) + add) | gw);
-            if (h & ~LOW) {
-                const uint32_t m[4] = {vmax<CB>(f.x, r.x), vmax<CB>(f.y, r.y), vmax<CB>(f.z, r.z), vmax<CB>(f.w, r.w)};
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-#pragma unroll
-                    for (int i = 0; i < PER; ++i) {
-                        const uint32_t v = (m[j] >> (i * CB)) & CMASK;
-                        if (v > cur) { cur = v; cur_bin = (4u * qd + j) * PER + i; }
-                    }
-                add = (HALF - 1u - min(cur, HALF - 1u)) * ONES;
-            }
-        }
-        // (count, lowest bin) as one key: larger count wins, then the smaller bin (bins < 65 535)
-        uint32_t best_key = __reduce_max_sync(0xffffffffu, (cur << 16) | (0xFFFFu - cur_bin));
-        if (lane == 0) s_red[warp] = best_key;
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < kPostWarps; ++i) best_key = max(best_key, s_red[i]);
-        const uint32_t M = best_key >> 16, best_bin = 0xFFFFu - (best_key & 0xFFFFu);
-        if (tid < (int)a.n_lut) {
-            uint64_t key = 0;
-            if (flag == 0) {
-                const uint32_t thr = (uint32_t)__ldg(a.lut + (size_t)tid * kLutSize + len);
-                if (M >= thr) key = pack_key(M, (uint32_t)(a.fv.bin_begin + best_bin));
-            }
-            uint64_t *const dst = a.keys + (size_t)tid * a.n_reads + read;
-            if (a.keys_shared) { if (key) key_max(dst, key, 1); }          // all bin shards fold into one array (NVLink peer atomics)
-            else *dst = key;
-        }
+        postings_epilogue<CB, kPostThreads>(a, read, len, flag, cntF, cntR, s_red);
     }
 }
 
@@ -1043,8 +1183,8 @@ int launch_count_slots(const CountArgs &a, const uint8_t *d_slots, uint32_t slot
 }
 
 // counter width by the longest read of the launch; returns launches, -1 on error, -2 if this launch cannot use postings
-int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint16_t *d_ids, uint32_t max_read_len, int sm_count,
-                          cudaStream_t st)
+int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint16_t *d_ids, uint32_t max_read_len, double mean_units,
+                          int sm_count, cudaStream_t st)
 {
     if (a.n_reads == 0) return 0;
     if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut) return -1;
@@ -1065,6 +1205,34 @@ int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint1
         const uint32_t gx = (uint32_t)(a.n_reads < cap ? a.n_reads : cap);
         kernel<<<gx, threads, smem, st>>>(a, d_ptr, ids, cnt_words);
     };
+    // lanes per list by the table's mean list length in 16-byte units: 8 lanes up to kSub8 units, 16 up to kSub16, else the
+    // whole warp (RB_POSTINGS_SUB = 0 / 8 / 16 forces one; measurements, tests)
+    int lg = mean_units > 0 && mean_units <= kSub8Units ? 8 : mean_units > 0 && mean_units <= kSub16Units ? 16 : 0;
+    if (const char *e = std::getenv("RB_POSTINGS_SUB")) { const int v = std::atoi(e); if (v == 0 || v == 8 || v == 16) lg = v; }
+    if (lg == 8) {
+        if (narrow) {
+            if (fit >= 3) launch(count_postings_sub_kernel<8, 256, 8>, 256);
+            else if (fit == 2) launch(count_postings_sub_kernel<8, 384, 8>, 384);
+            else launch(count_postings_sub_kernel<8, 768, 8>, 768);
+        } else {
+            if (fit >= 3) launch(count_postings_sub_kernel<16, 256, 8>, 256);
+            else if (fit == 2) launch(count_postings_sub_kernel<16, 384, 8>, 384);
+            else launch(count_postings_sub_kernel<16, 768, 8>, 768);
+        }
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
+    if (lg == 16) {
+        if (narrow) {
+            if (fit >= 3) launch(count_postings_sub_kernel<8, 256, 16>, 256);
+            else if (fit == 2) launch(count_postings_sub_kernel<8, 384, 16>, 384);
+            else launch(count_postings_sub_kernel<8, 768, 16>, 768);
+        } else {
+            if (fit >= 3) launch(count_postings_sub_kernel<16, 256, 16>, 256);
+            else if (fit == 2) launch(count_postings_sub_kernel<16, 384, 16>, 384);
+            else launch(count_postings_sub_kernel<16, 768, 16>, 768);
+        }
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     if (narrow) {
         if (fit >= 3) launch(count_postings_kernel<8, 256>, 256);
         else if (fit == 2) launch(count_postings_kernel<8, 384>, 384);

@@ -73,6 +73,7 @@ struct rb_ibf {
                                             // entries loaded by adjacent lanes (ibf_wtable.cu)
     mutable uint64_t table_bytes = 0;
     // wide filters: k-mer postings table (ibf_postings.cu) instead of the dense window table
+    mutable double post_mean_units = 0;     // postings lists: mean list length in 16-byte units (picks the lookup kernel)
     mutable int table_kind = 0;             // 0 none, 1 dense k-mer / window table, 2 postings, 4 k-mer table loaded by lane groups
     mutable uint32_t *d_post_ptr = nullptr;
     mutable uint16_t *d_post_ids = nullptr;
@@ -441,6 +442,7 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
         g_launches += (uint64_t)(1 + n1 + n2);
         f->d_post_ptr = d_ptr;
         f->d_post_ids = d_ids;
+        f->post_mean_units = (double)total_units / (double)n_kmers;
         f->table_kind = 2;
         f->table_span = 1;
         f->table_entries = n_kmers;
@@ -1550,7 +1552,7 @@ static int count_dev_impl(const rb_ibf *f, const uint8_t *d_bases, const uint64_
         table = nullptr;                          // -2: counters + rings of this launch's reads do not fit shared memory
     }
     if (table && f->table_kind == 2) {
-        int n = rb::launch_count_postings(a, f->d_post_ptr, f->d_post_ids, max_read_len, f->sm_count, (cudaStream_t)stream);
+        int n = rb::launch_count_postings(a, f->d_post_ptr, f->d_post_ids, max_read_len, f->post_mean_units, f->sm_count, (cudaStream_t)stream);
         if (n == -1) return fail(RB_ERR_COUNT_KMER, std::string("count launch failed: ") + cudaGetErrorString(cudaGetLastError()));
         if (n >= 0) { g_launches += (uint64_t)n; return RB_OK; }
         table = nullptr;                          // -2: this launch's reads need wider counters than shared memory holds

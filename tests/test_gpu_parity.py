@@ -178,9 +178,15 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
                 finally:
                     del os.environ["RB_POSTINGS_LAYOUT"], os.environ["RB_CTABLE"]
                 assert gf.kmer_table_kind() == kind and gf.kmer_table_bytes() > 4 ** k * 4
-                assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)          # long reads: 16-bit counters
-                assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)             # <= 255 positions: 8-bit counters
-                assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+                for sub in (("", "0", "8", "16") if layout == "lists" else ("",)):     # lanes per list of the lists kernel
+                    if sub:
+                        os.environ["RB_POSTINGS_SUB"] = sub
+                    try:
+                        assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)          # long reads: 16-bit counters
+                        assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)             # <= 255 positions: 8-bit counters
+                        assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+                    finally:
+                        os.environ.pop("RB_POSTINGS_SUB", None)
                 gf.disable_kmer_table()
                 assert gf.kmer_table_kind() == 0
             return
@@ -450,15 +456,18 @@ def test_postings_slots(n_blocks, order, slot_bytes, ring, monkeypatch):
     assert tb >= 0.95 * pairs * min(sbytes, 128) and reqs >= 0.95 * pairs and io > sb.size
 
 
+@pytest.mark.parametrize("sub", ["", "0", "8", "16"])
 @pytest.mark.parametrize("order", ["1", "0"])
 @pytest.mark.parametrize("n_blocks", [2600, 3700, 6000, 9000])
-def test_postings_long_lists(n_blocks, order, monkeypatch):
+def test_postings_long_lists(n_blocks, order, sub, monkeypatch):
     """Postings lists of ~610 / ~380 / ~160 / ~70 bins per k-mer (an over-full 1 100-bin filter: 56 % .. 6 % false positives
     per bin), so that the lookup kernel walks full rounds, further rounds and every tail width (ibf_postings_layout.cuh),
     with the ids dealt over the groups (default) and ascending (RB_POSTINGS_ORDER=0)."""
     monkeypatch.setenv("RB_POSTINGS_ORDER", order)
     monkeypatch.setenv("RB_POSTINGS_LAYOUT", "lists")
     monkeypatch.setenv("RB_CTABLE", "0")                    # 18 row words: the group-loaded k-mer table would come first
+    if sub:                                                 # lanes per list: 0 = the whole warp, 8 / 16 = the short-list kernel
+        monkeypatch.setenv("RB_POSTINGS_SUB", sub)          # ("" = chosen by the table's mean list length)
     k, n_hash = 11, 3
     ref = [synth.random_bases(1500, 300 + i) for i in range(1100)]
     plan = synth.build_plan(ref, 2000, k, n_hash=n_hash)
