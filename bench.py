@@ -52,8 +52,13 @@ WORKLOADS = {
                                cpu_build_frags=128),
     "w32_200Mb_2020bins": dict(lengths=[10_050_000] * 20, seed0=400, fragment=100_000, k=13, chunk=250, reads=262_144,
                                cpu_build_frags=128),
+    "w16_k15": dict(lengths=[10_050_000] * 10, seed0=400, fragment=100_000, k=15, chunk=250, reads=262_144, cpu_build_frags=128),
     "w64_400Mb_4040bins": dict(lengths=[10_050_000] * 40, seed0=400, fragment=100_000, k=13, chunk=250, reads=131_072,
                                cpu_build_frags=256),
+    "w128_800Mb_8080bins": dict(lengths=[10_050_000] * 80, seed0=400, fragment=100_000, k=13, chunk=250, reads=131_072,
+                                cpu_build_frags=256),
+    "w256_1.6Gb_16160bins": dict(lengths=[10_050_000] * 160, seed0=400, fragment=100_000, k=13, chunk=250, reads=65_536,
+                                 cpu_build_frags=256),
     "cfg3_3.1Gb_31kbins": dict(lengths=[129_166_666] * 24, seed0=300, fragment=100_000, k=13, chunk=250, reads=65_536,
                                cpu_build_frags=1024),
     "w1_50x4Mb_50bins": dict(lengths=[3_999_999] * 50, seed0=2, fragment=4_200_000, k=13, chunk=250, reads=1_000_000),

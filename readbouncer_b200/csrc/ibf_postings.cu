@@ -33,7 +33,7 @@ namespace {
 // Threads per CTA (template parameter of the lookup kernel) follow from how many CTAs of counters fit the shared memory
 // of an SM: 3 x 256, 2 x 384 or 1 x 768 -- always 24 warps per SM under the 85-register ceiling of 768 threads.
 constexpr int kPostPiece = 512;               // k-mer positions staged per pass over a read
-constexpr double kSub8Units = 8.0, kSub16Units = 16.0;   // mean list length (16-byte units) up to which 8 / 16 lanes own a list
+constexpr double kSub2Units = 3.5, kSub4Units = 7.5, kSub8Units = 16.0;   // mean list length (16-byte units) up to which 2 / 4 / 8 lanes own a list
 constexpr int kPostInFlight = 4;              // lists a warp loads before it counts them (even: strands alternate)
 
 // base-5 hashes of the forward and reverse-complement strand of the ACGT k-mer x (ranks, first base most significant)
@@ -465,9 +465,9 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
 // ------------------------------------------------------------------------------------------
 // The kernel above spends a warp-wide step on every list: right for the ~360 ids per list of a human-sized filter, wasteful
 // for a 4 000-bin one (46 ids = 6 units: most lanes idle, ~40 warp instructions and a dependent pair of requests per list,
-// four lists in flight per warp -- 13.6 M chunks/s with the DRAM a third busy, profiles/r2_x_*).  Here a group of LG = 8 or 16
-// lanes owns a list: lane s loads unit s (and s + LG, ... of a longer list), 4 or 2 lists per warp step, four steps' bounds
-// and then four steps' units requested before the first counter is touched (16 or 8 lists in flight per warp in 16
+// four lists in flight per warp -- 13.6 M chunks/s with the DRAM a third busy, profiles/r2_x_*).  Here a group of LG = 2, 4 or 8
+// lanes owns a list: lane s loads unit s (and s + LG, ... of a longer list), 16, 8 or 4 lists per warp step, four steps' bounds
+// and then four steps' units requested before the first counter is touched (64 .. 16 lists in flight per warp in 16
 // registers).  The order of the ids inside a list does not matter (counting is commutative), so the same table serves both
 // kernels; the launcher picks by the mean list length of the table.
 template <int CB>
@@ -563,7 +563,9 @@ count_postings_sub_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, c
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         if (sub < n_u[u]) add_ids_skip<CB>(cnt, v[u], sentinel);
-                        for (uint32_t o = LG; o < n_u[u]; o += LG)       // lists of more than LG units: the group walks on
+                        // lists of more than LG units: the group walks on.  (Loading a lane's second unit up front as well was
+                        // measured 10-25 % slower at every list length, profiles/r2_ab_postings_sub_sweep.jsonl.)
+                        for (uint32_t o = LG; o < n_u[u]; o += LG)
                             if (o + sub < n_u[u]) add_ids_skip<CB>(cnt, __ldg(ids + p0[u] + o + sub), sentinel);
                     }
                     __syncwarp();
@@ -1205,34 +1207,27 @@ int launch_count_postings(const CountArgs &a, const uint32_t *d_ptr, const uint1
         const uint32_t gx = (uint32_t)(a.n_reads < cap ? a.n_reads : cap);
         kernel<<<gx, threads, smem, st>>>(a, d_ptr, ids, cnt_words);
     };
-    // lanes per list by the table's mean list length in 16-byte units: 8 lanes up to kSub8 units, 16 up to kSub16, else the
-    // whole warp (RB_POSTINGS_SUB = 0 / 8 / 16 forces one; measurements, tests)
-    int lg = mean_units > 0 && mean_units <= kSub8Units ? 8 : mean_units > 0 && mean_units <= kSub16Units ? 16 : 0;
-    if (const char *e = std::getenv("RB_POSTINGS_SUB")) { const int v = std::atoi(e); if (v == 0 || v == 8 || v == 16) lg = v; }
-    if (lg == 8) {
-        if (narrow) {
-            if (fit >= 3) launch(count_postings_sub_kernel<8, 256, 8>, 256);
-            else if (fit == 2) launch(count_postings_sub_kernel<8, 384, 8>, 384);
-            else launch(count_postings_sub_kernel<8, 768, 8>, 768);
-        } else {
-            if (fit >= 3) launch(count_postings_sub_kernel<16, 256, 8>, 256);
-            else if (fit == 2) launch(count_postings_sub_kernel<16, 384, 8>, 384);
-            else launch(count_postings_sub_kernel<16, 768, 8>, 768);
-        }
-        return cudaGetLastError() == cudaSuccess ? 1 : -1;
-    }
-    if (lg == 16) {
-        if (narrow) {
-            if (fit >= 3) launch(count_postings_sub_kernel<8, 256, 16>, 256);
-            else if (fit == 2) launch(count_postings_sub_kernel<8, 384, 16>, 384);
-            else launch(count_postings_sub_kernel<8, 768, 16>, 768);
-        } else {
-            if (fit >= 3) launch(count_postings_sub_kernel<16, 256, 16>, 256);
-            else if (fit == 2) launch(count_postings_sub_kernel<16, 384, 16>, 384);
-            else launch(count_postings_sub_kernel<16, 768, 16>, 768);
-        }
-        return cudaGetLastError() == cudaSuccess ? 1 : -1;
-    }
+    // lanes per list by the table's mean list length in 16-byte units (profiles/r2_ab_postings_sub_sweep.jsonl: 8 lanes win up
+    // to ~12 units, the whole warp from ~23 on; 16 lanes per list lost everywhere); RB_POSTINGS_SUB = 0 / 2 / 4 / 8 forces one
+    int lg = mean_units <= 0 ? 0 : mean_units <= kSub2Units ? 2 : mean_units <= kSub4Units ? 4 : mean_units <= kSub8Units ? 8 : 0;
+    if (const char *e = std::getenv("RB_POSTINGS_SUB")) { const int v = std::atoi(e); if (v == 0 || v == 2 || v == 4 || v == 8) lg = v; }
+#define RB_SUB_LAUNCH(LG)                                                                                                     \
+    do {                                                                                                                      \
+        if (narrow) {                                                                                                         \
+            if (fit >= 3) launch(count_postings_sub_kernel<8, 256, LG>, 256);                                                 \
+            else if (fit == 2) launch(count_postings_sub_kernel<8, 384, LG>, 384);                                            \
+            else launch(count_postings_sub_kernel<8, 768, LG>, 768);                                                          \
+        } else {                                                                                                              \
+            if (fit >= 3) launch(count_postings_sub_kernel<16, 256, LG>, 256);                                                \
+            else if (fit == 2) launch(count_postings_sub_kernel<16, 384, LG>, 384);                                           \
+            else launch(count_postings_sub_kernel<16, 768, LG>, 768);                                                         \
+        }                                                                                                                     \
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;                                                                    \
+    } while (0)
+    if (lg == 2) RB_SUB_LAUNCH(2);
+    if (lg == 4) RB_SUB_LAUNCH(4);
+    if (lg == 8) RB_SUB_LAUNCH(8);
+#undef RB_SUB_LAUNCH
     if (narrow) {
         if (fit >= 3) launch(count_postings_kernel<8, 256>, 256);
         else if (fit == 2) launch(count_postings_kernel<8, 384>, 384);

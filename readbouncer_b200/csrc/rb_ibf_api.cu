@@ -281,12 +281,32 @@ constexpr uint64_t kTableMinReads = 1024;   // batches smaller than this never t
 // `lanes` slots of 2*col_words words per entry, loaded by adjacent lanes (ibf_wtable.cu, rows <= 2 words).
 // rows of 3..16 words: one k-mer per entry, the row padded to 4, 8 or 16 words, loaded by that many lanes (ibf_ctable.cu).
 // RB_CTABLE=0 turns the layout off (measurements: rows of 3-4 words fall back to ibf_table.cu, wider ones to postings).
-uint64_t ctable_bytes(const rb_ibf *f)
+// Rows of 17..32 words (512-byte entries, four lines per position) beat the short-list postings kernel only when the lists are
+// long: measured at 2 020 bins of 100 kb, 3.3 units per list, 32.7 M chunks/s (34 GB table) against 34.6 M (3.8 GB of lists),
+// while 8-unit lists run at ~20 M.  So that width takes the table only when a sample of the lists averages more than 4 units
+// (RB_CTABLE_WIDE=1 / 0 forces the answer: tests, measurements).
+uint64_t ctable_bytes(const rb_ibf *f, cudaStream_t st = nullptr)
 {
     const char *e = std::getenv("RB_CTABLE");
     const bool on = !(e && e[0] == '0');
     const int lanes = rb::ctable_lanes(f->col_words);
     if (!on || !lanes || f->k > 16) return 0;
+    if (lanes == 32) {
+        const char *w = std::getenv("RB_CTABLE_WIDE");
+        bool take = w && w[0] == '1';
+        if (!w && rb::postings_applicable(view_of(f))) {
+            const uint64_t n_kmers = 1ull << (2 * f->k);
+            const uint32_t n_sample = (uint32_t)std::min<uint64_t>(65536, n_kmers);
+            uint32_t *d_tmp = nullptr;
+            double mean_units = 0;
+            if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) == cudaSuccess) {
+                if (rb::postings_sample_units(view_of(f), d_tmp, n_sample, &mean_units, f->sm_count, st) >= 0) take = mean_units > 4.0;
+                cudaFree(d_tmp);
+            }
+            cudaGetLastError();
+        } else if (!w) take = true;                                      // no lists possible (k = 16): the table or nothing
+        if (!take) return 0;
+    }
     return (1ull << (2 * f->k)) * (uint64_t)lanes * 16;
 }
 
@@ -352,7 +372,7 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
     uint64_t cap = 80ull << 30;
     if (const char *gb = std::getenv("RB_KMER_TABLE_MAX_GB")) cap = (uint64_t)std::max(0, std::atoi(gb)) << 30;
     const uint64_t budget = f->table_budget ? f->table_budget : std::min<uint64_t>((uint64_t)(free_b * 0.6), cap);
-    if (const uint64_t need = ctable_bytes(f); need && need <= budget && need <= free_b) {
+    if (const uint64_t need = ctable_bytes(f, st); need && need <= budget && need <= free_b) {
         uint64_t *t = nullptr;
         if (cudaMalloc(&t, need) == cudaSuccess) {
             const uint64_t n_kmers = 1ull << (2 * f->k);
@@ -1380,7 +1400,7 @@ int rb_ibf_enable_kmer_tables(rb_ibf *const *filters, uint32_t n_filters, uint64
                 const uint64_t est = postings_estimate_bytes(f, (cudaStream_t)stream);
                 if (est) opts[i].push_back({est + est / 16, 0});  // the estimate comes from a sample: leave a margin
                 // rows of 5..16 words: the group-loaded k-mer table is the widening step after the postings lists
-                if (const uint64_t ct = ctable_bytes(f); ct && (opts[i].empty() || ct > opts[i][0].bytes)) opts[i].push_back({ct, 1});
+                if (const uint64_t ct = ctable_bytes(f, (cudaStream_t)stream); ct && (opts[i].empty() || ct > opts[i][0].bytes)) opts[i].push_back({ct, 1});
             } else {
                 for (int sp = 1; sp <= (f->col_words <= 2 ? 4 : 1); ++sp) {
                     const uint64_t ct = sp == 1 ? ctable_bytes(f) : 0;           // rows of 3-4 words: padded, group-loaded entries

@@ -162,7 +162,11 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
             sb[int(so[7]) + 100] = ord("U")
             sexp = of.count_batch(sb, so, lut, n_threads=4)
             if gf.bin_width <= 32:                       # rows of 5..32 words: the group-loaded k-mer table comes first
-                gf.enable_kmer_table(0)
+                os.environ["RB_CTABLE_WIDE"] = "1"       # (17..32 words: only for long lists unless forced)
+                try:
+                    gf.enable_kmer_table(0)
+                finally:
+                    del os.environ["RB_CTABLE_WIDE"]
                 lanes = 8 if gf.bin_width <= 8 else 16 if gf.bin_width <= 16 else 32
                 assert (gf.kmer_table_kind(), gf.kmer_table_bytes(), gf.kmer_table_span()) == (4, 4 ** k * lanes * 16, 1)
                 assert_same_results(gf.count_batch(bases, off, lut, dense=True), exp)
@@ -178,7 +182,7 @@ def test_count_matches_oracle(kernel, n_seqs, seq_len, frag, k):
                 finally:
                     del os.environ["RB_POSTINGS_LAYOUT"], os.environ["RB_CTABLE"]
                 assert gf.kmer_table_kind() == kind and gf.kmer_table_bytes() > 4 ** k * 4
-                for sub in (("", "0", "8", "16") if layout == "lists" else ("",)):     # lanes per list of the lists kernel
+                for sub in (("", "0", "2", "4", "8") if layout == "lists" else ("",)):     # lanes per list of the lists kernel
                     if sub:
                         os.environ["RB_POSTINGS_SUB"] = sub
                     try:
@@ -383,6 +387,12 @@ def test_medium_rows_group_loaded_table(n_bins, k, inflight, monkeypatch):
             monkeypatch.setenv("RB_CTABLE_U", inflight)
     plan, of, gf = make_filter_pair(n_bins, 1500, 2000, k)
     assert plan["n_bins"] == n_bins
+    if n_bins > 1024:
+        # 17..32 row words: by default the table is taken only when the sampled postings lists are long (> 4 units); these
+        # filters have ~1.5-unit lists, so the automatic choice is the short-list postings kernel
+        gf.enable_kmer_table(0)
+        assert gf.kmer_table_kind() == 2
+        monkeypatch.setenv("RB_CTABLE_WIDE", "1")
     gf.enable_kmer_table(0)
     lanes = 4 if n_bins <= 256 else 8 if n_bins <= 512 else 16 if n_bins <= 1024 else 32
     assert (gf.kmer_table_kind(), gf.kmer_table_span(), gf.kmer_table_bytes()) == (4, 1, 4 ** k * lanes * 16)
@@ -456,7 +466,7 @@ def test_postings_slots(n_blocks, order, slot_bytes, ring, monkeypatch):
     assert tb >= 0.95 * pairs * min(sbytes, 128) and reqs >= 0.95 * pairs and io > sb.size
 
 
-@pytest.mark.parametrize("sub", ["", "0", "8", "16"])
+@pytest.mark.parametrize("sub", ["", "0", "2", "4", "8"])
 @pytest.mark.parametrize("order", ["1", "0"])
 @pytest.mark.parametrize("n_blocks", [2600, 3700, 6000, 9000])
 def test_postings_long_lists(n_blocks, order, sub, monkeypatch):
@@ -466,7 +476,7 @@ def test_postings_long_lists(n_blocks, order, sub, monkeypatch):
     monkeypatch.setenv("RB_POSTINGS_ORDER", order)
     monkeypatch.setenv("RB_POSTINGS_LAYOUT", "lists")
     monkeypatch.setenv("RB_CTABLE", "0")                    # 18 row words: the group-loaded k-mer table would come first
-    if sub:                                                 # lanes per list: 0 = the whole warp, 8 / 16 = the short-list kernel
+    if sub:                                                 # lanes per list: 0 = the whole warp, 2 / 4 / 8 = the short-list kernel
         monkeypatch.setenv("RB_POSTINGS_SUB", sub)          # ("" = chosen by the table's mean list length)
     k, n_hash = 11, 3
     ref = [synth.random_bases(1500, 300 + i) for i in range(1100)]
