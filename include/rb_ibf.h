@@ -252,13 +252,15 @@ RB_API int rb_keys_combine_nccl(void *nccl_comm, uint64_t *d_keys, uint64_t n, r
  * table is possible (k = 16).
  * MEDIUM filters (rows of 3..32 words = 129..2048 bins, k <= 16) get the same one-k-mer table with the row padded to
  * 4 / 8 / 16 / 32 words: entries of 64..512 bytes, each loaded by 4..32 adjacent lanes in one instruction and counted in
- * bit-sliced registers (ibf_ctable.cu; 8.6 GB for 303 bins, 34 GB for 2020 bins at k = 13).  RB_CTABLE=0 turns this layout
+ * bit-sliced registers (ibf_ctable.cu; 8.6 GB for 303 bins, 17 GB for 1010 bins at k = 13; rows of 17..32 words only when
+ * their postings lists would average more than 4 units, RB_CTABLE_WIDE=1/0 forces that choice).  RB_CTABLE=0 turns this layout
  * off (rows of 3-4 words then use the unpadded lane-per-entry table, wider ones the postings below).
  * Wide filters (rows > 32 words, or > 4 words when that table does not fit; <= 65280 local bins, k <= 15) get a POSTINGS table instead: the AND of
  * the probed rows is ~1 % dense by the reference's own sizing, so the list of set bins of every
  * k-mer (2 bytes each, ~50 GB for a human-genome filter at k=13) replaces streaming 2*h rows of
  * thousands of bytes per position; same policy, budget and env switches.  Two layouts: pointer + lists
- * of 16-byte units read straight into registers (default), or (RB_POSTINGS_LAYOUT=slots) a fixed,
+ * of 16-byte units read straight into registers (default; lists averaging up to 16 units are walked by groups of 2 / 4 / 8
+ * lanes, longer ones by the whole warp -- RB_POSTINGS_SUB=0/2/4/8 forces one), or (RB_POSTINGS_LAYOUT=slots) a fixed,
  * 128-byte-aligned slot per k-mer (size chosen from the sampled list lengths; the few longer lists go to an
  * overflow area) fetched by one bulk copy into a shared-memory ring.
  *
