@@ -598,7 +598,13 @@ def run_workload(env, args, name, n_reads, steps, warmup, role):
     span = gf.kmer_table_span()
     kind = gf.kmer_table_kind()
     group_ok = span >= 2 and chunk - k + 1 <= 127 * span and chunk <= 545   # ibf_wtable.cu: wgroup_applicable
-    kernel_name = ("count_slots_kernel" if kind == 3 else "count_postings_kernel" if kind == 2 else "count_ctable_kernel" if kind == 4
+    tb_ = gf.kmer_table_bytes()
+    # the library picks the lookup kernel of a postings table by its geometry (ibf_postings.cu): slots of one or two lines and
+    # lists averaging up to 16 units are walked by groups of lanes, the rest by whole warps
+    slots_direct = kind == 3 and (tb_ // 4 ** k) // 128 * 128 <= 256 and os.environ.get("RB_SLOTS_SUB", "1") != "0"
+    lists_short = kind == 2 and (tb_ - 4 * (4 ** k + 1)) / 16 / 4 ** k <= 16.0 and os.environ.get("RB_POSTINGS_SUB", "") != "0"
+    kernel_name = ("count_slots_sub_kernel" if slots_direct else "count_slots_kernel" if kind == 3
+                   else "count_postings_sub_kernel" if lists_short else "count_postings_kernel" if kind == 2 else "count_ctable_kernel" if kind == 4
                    else "count_wgroup_kernel" if group_ok else "count_wtable_kernel" if span >= 2
                    else "count_table_kernel" if span == 1 else
                    "count_stream_kernel" if (gf.col_words > 4 or args.kernel == 2) else "count_tile_kernel")

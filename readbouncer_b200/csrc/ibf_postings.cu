@@ -481,6 +481,18 @@ __device__ __forceinline__ void add_ids_skip(uint32_t *cnt, const uint4 v, const
     }
 }
 
+// the same for slots: every id >= sentinel is a pad (slot_pad_id)
+template <int CB>
+__device__ __forceinline__ void add_ids_skip_ge(uint32_t *cnt, const uint4 v, const uint32_t sentinel)
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if ((w[i] & 0xFFFFu) < sentinel) bump<CB>(cnt, w[i]);
+        if ((w[i] >> 16) < sentinel) bump<CB>(cnt, w[i] >> 16);
+    }
+}
+
 template <int CB, int kPostThreads, int LG>
 __global__ void __launch_bounds__(kPostThreads, 768 / kPostThreads)
 count_postings_sub_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const uint4 *__restrict__ ids, const uint32_t cnt_words)
@@ -977,6 +989,120 @@ count_slots_kernel(const CountArgs a, const uint8_t *__restrict__ slots, const u
 }
 
 // counters: whole quads of bins + the 128 pad ids' words (+ slack to a quad)
+// ------------------------------------------------------------------------------------------
+// lookup in slots of 128 / 256 bytes: 8 / 16 lanes load one slot with ONE instruction
+// ------------------------------------------------------------------------------------------
+// Short lists again (count_postings_sub_kernel), without the pointer: the slot of a k-mer is found by a multiplication, so
+// a list costs ONE request of one or two lines instead of a dependent pair (a whole line for the 8 bytes of bounds, then
+// 1.5+ lines for a list that starts at a random 16-byte offset).  Lane s of a group takes piece s of the slot; the first 8
+// bytes are the header (n, or kSlotOverflow + the place of a list that did not fit), ids >= sentinel are pads.  Counters and
+// epilogue are those of the list kernels.
+template <int CB, int kPostThreads, int LG>
+__global__ void __launch_bounds__(kPostThreads, 768 / kPostThreads)
+count_slots_sub_kernel(const CountArgs a, const uint8_t *__restrict__ slots, const uint4 *__restrict__ ovf, const uint32_t cnt_words)
+{
+    constexpr int kPostWarps = kPostThreads / 32;
+    constexpr int NL = 32 / LG;                                          // slots per warp step
+    constexpr int U = 4;                                                 // steps in flight
+    constexpr uint32_t kSlotB = 16u * LG;
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint32_t *const cntF = s_mem, *const cntR = s_mem + cnt_words;
+    uint32_t *const s_x = s_mem + 2 * cnt_words;                         // [kPostPiece] packed k-mer or ~0u (not ACGT)
+    uint8_t *const s_dig = reinterpret_cast<uint8_t *>(s_x + kPostPiece); // [kPostPiece + 32] Dna5 ranks
+    __shared__ uint32_t s_red[kPostWarps];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t grp = (uint32_t)lane / LG, sub = (uint32_t)lane % LG;
+    const uint32_t k = a.fv.hp.k;
+    const uint32_t kbits = 2 * k;
+    const uint32_t kmask = kbits >= 32 ? ~0u : ((1u << kbits) - 1u);
+    const uint32_t sentinel = postings_sentinel(a.fv.n_bins_local);
+    uint32_t *const cnt = (grp & 1u) ? cntR : cntF;                      // pairs alternate strands and every step starts even
+
+    for (uint32_t w = tid; w < 2 * cnt_words; w += kPostThreads) s_mem[w] = 0;
+
+    for (uint64_t read = blockIdx.x; read < a.n_reads; read += gridDim.x) {
+        const uint64_t off = a.read_off[read];
+        const uint64_t len = a.read_off[read + 1] - off;
+        uint32_t flag = read_flag_of(len, k);
+        if (flag == 0 && CB == 8 && len - k + 1 > 255) flag = 3;         // longer than the caller's max_read_len promised
+        if (tid == 0 && a.read_flag) a.read_flag[read] = (uint8_t)flag;
+        __syncthreads();                                                   // counters are zero and visible
+
+        if (flag == 0) {
+            const uint32_t npos = (uint32_t)len - k + 1;
+            for (uint32_t cs = 0; cs < npos; cs += kPostPiece) {
+                const uint32_t cn = min((uint32_t)kPostPiece, npos - cs);
+                __syncthreads();
+                for (uint32_t i = tid; i < cn + k - 1; i += kPostThreads) s_dig[i] = (uint8_t)dna5(a.bases[off + cs + i]);
+                __syncthreads();
+                for (uint32_t j = tid; j < cn; j += kPostThreads) {
+                    uint32_t x = 0, bad = 0;
+                    for (uint32_t u = 0; u < k; ++u) {
+                        const uint32_t d = s_dig[j + u];
+                        x = (x << 2) | (d & 3u);
+                        bad |= d >> 2;
+                    }
+                    s_x[j] = bad ? ~0u : (x & kmask);
+                }
+                __syncthreads();
+                const uint32_t n_pairs = 2 * cn;
+                const uint32_t share = 2u * ((cn + kPostWarps - 1) / kPostWarps);
+                const uint32_t q_end = min(n_pairs, (warp + 1) * share);
+                for (uint32_t qb = warp * share; qb < q_end; qb += NL * U) {
+                    uint4 v[U];
+                    uint32_t hashed = 0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t q = qb + NL * u + grp;
+                        v[u] = make_uint4(0, 0, 0, 0);                     // header n = 0: nothing to count
+                        if (q < q_end) {
+                            const uint32_t x = s_x[q >> 1];
+                            if (x == ~0u) hashed |= 1u << u;
+                            else {
+                                uint32_t idx = x;
+                                if (q & 1u) {                              // reverse strand: the slot of revcomp(x)
+                                    uint32_t r = __brev(~x);
+                                    r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+                                    idx = r >> (32 - kbits);
+                                }
+                                v[u] = __ldg(reinterpret_cast<const uint4 *>(slots + (uint64_t)idx * kSlotB) + sub);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        // header words of the group's slot (piece 0)
+                        const uint32_t h0 = __shfl_sync(0xffffffffu, v[u].x, grp * LG), h1 = __shfl_sync(0xffffffffu, v[u].y, grp * LG);
+                        const uint32_t h2 = __shfl_sync(0xffffffffu, v[u].z, grp * LG);
+                        const uint32_t n = h0 & 0xFFFFu;
+                        if (n == kSlotOverflow) {                          // the list lives in the overflow area: h1 = first unit, h2 = units
+                            for (uint32_t o = sub; o < h2; o += LG) add_ids_skip_ge<CB>(cnt, __ldg(ovf + h1 + o), sentinel);
+                        } else if (n != 0) {
+                            uint4 w = v[u];
+                            if (sub == 0) { w.x = sentinel | (sentinel << 16); w.y = w.x; }     // the header is not ids
+                            add_ids_skip_ge<CB>(cnt, w, sentinel);
+                        }
+                    }
+                    __syncwarp();
+                    // windows with a non-ACGT base: the whole warp evaluates the rows (rare)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t hm = __ballot_sync(0xffffffffu, (hashed >> u) & 1u);
+                        for (uint32_t g = 0; g < (uint32_t)NL; ++g)
+                            if ((hm >> (g * LG)) & 1u) {
+                                const uint32_t q = qb + NL * u + g;
+                                add_hashed<CB>(a.fv, s_dig + (q >> 1), q & 1u, (q & 1u) ? cntR : cntF, lane);
+                            }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        postings_epilogue<CB, kPostThreads>(a, read, len, flag, cntF, cntR, s_red);
+    }
+}
+
 size_t slots_counter_words(uint64_t n_bins_local, int counter_bits)
 {
     const uint32_t per = 32 / counter_bits;
@@ -1139,6 +1265,41 @@ int launch_count_slots(const CountArgs &a, const uint8_t *d_slots, uint32_t slot
     if (a.n_lut == 0 || a.n_lut > (uint32_t)kMaxLut) return -1;
     const uint32_t k = a.fv.hp.k;
     const bool narrow = max_read_len != 0 && (max_read_len < k || max_read_len - k + 1 <= 255);
+    // slots of one or two lines: groups of 8 / 16 lanes load them straight into registers (RB_SLOTS_SUB=0: the ring kernel)
+    if (slot_bytes <= 256) {
+        const char *e = std::getenv("RB_SLOTS_SUB");
+        if (!(e && e[0] == '0')) {
+            uint32_t cw = 0;
+            const size_t smem = postings_smem_bytes(a.fv.n_bins_local, narrow ? 8 : 16, &cw);
+            if (smem > 220u * 1024u) return -2;
+            const int fit = (int)std::min<size_t>(3, (227u * 1024u) / (smem + 1024u));
+            const uint4 *ovf4 = reinterpret_cast<const uint4 *>(d_ovf);
+            auto launch = [&](auto kernel, int threads) {
+                cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                int occ = 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+                if (occ < 1) occ = 1;
+                const uint64_t capb = (uint64_t)sm_count * occ * grid_waves();
+                const uint32_t gx = (uint32_t)(a.n_reads < capb ? a.n_reads : capb);
+                kernel<<<gx, threads, smem, st>>>(a, d_slots, ovf4, cw);
+            };
+#define RB_SLOT_SUB_LAUNCH(LG)                                                                                                \
+    do {                                                                                                                      \
+        if (narrow) {                                                                                                         \
+            if (fit >= 3) launch(count_slots_sub_kernel<8, 256, LG>, 256);                                                    \
+            else if (fit == 2) launch(count_slots_sub_kernel<8, 384, LG>, 384);                                               \
+            else launch(count_slots_sub_kernel<8, 768, LG>, 768);                                                             \
+        } else {                                                                                                              \
+            if (fit >= 3) launch(count_slots_sub_kernel<16, 256, LG>, 256);                                                   \
+            else if (fit == 2) launch(count_slots_sub_kernel<16, 384, LG>, 384);                                              \
+            else launch(count_slots_sub_kernel<16, 768, LG>, 768);                                                            \
+        }                                                                                                                     \
+    } while (0)
+            if (slot_bytes == 128) RB_SLOT_SUB_LAUNCH(8); else RB_SLOT_SUB_LAUNCH(16);
+#undef RB_SLOT_SUB_LAUNCH
+            return cudaGetLastError() == cudaSuccess ? 1 : -1;
+        }
+    }
     const uint32_t cnt_words = (uint32_t)slots_counter_words(a.fv.n_bins_local, narrow ? 8 : 16);
     const size_t fixed = ((size_t)2 * cnt_words * 4 + kPostPiece * 8 + kPostPiece + 32 + 127) / 128 * 128;
     const size_t entry = 2 * (size_t)slot_bytes + 8;               // both strands' slots of one position + its mbarrier

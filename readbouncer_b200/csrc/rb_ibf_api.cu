@@ -320,6 +320,35 @@ uint64_t table_bytes_needed(const rb_ibf *f, int span)
     return n_entries * (uint64_t)lanes * 2 * f->col_words * 8;
 }
 
+// Mid-length lists -- 2.6 to 14 units on average, the 2 000..8 000-bin filters -- are faster in slots of one or two lines
+// read by groups of 8 / 16 lanes (count_slots_sub_kernel) than as pointer + lists: no dependent pointer fetch.  Measured
+// 38.6 / 30.2 / 21.1 M chunks/s against 34.8 / 25.4 / 16.7 M at 2 020 / 4 040 / 8 080 bins; shorter lists run faster through
+// the 2-lane list kernel, longer ones need slots of four lines and more, where the lists win
+// (profiles/r2_ah_slots_sub_sweep.jsonl).  Returns the slot size (128 or 256) or 0; RB_POSTINGS_LAYOUT overrides.
+uint32_t auto_slot_bytes(const std::vector<uint32_t> &lengths, uint32_t k, uint64_t budget, uint64_t *ovf_units, uint64_t *total)
+{
+    if (lengths.empty()) return 0;
+    double units = 0;
+    for (uint32_t n : lengths) units += (n + 7) / 8;
+    const double mean_units = units / (double)lengths.size();
+    if (mean_units < 2.6 || mean_units > 14.0) return 0;
+    const double n_kmers = (double)(1ull << (2 * k));
+    uint32_t best = 0;
+    double best_cost = 0;
+    for (uint32_t sb = 128; sb <= 256; sb += 128) {
+        const uint32_t cap = (sb - 8) / 2;
+        double over_units = 0, over_lines = 0;
+        for (uint32_t n : lengths)
+            if (n > cap) { over_units += (n + 7) / 8; over_lines += ((n + 7) / 8 * 16 + 127) / 128 + 1; }
+        const double cost = sb + 128.0 * over_lines / (double)lengths.size();
+        const uint64_t ou = (uint64_t)(2.0 * over_units / (double)lengths.size() * n_kmers) + (1u << 20);
+        const uint64_t bytes = (uint64_t)(n_kmers * sb) + ou * 16;
+        if (bytes > budget || ou > 0xFFFFFFF0ull) continue;
+        if (!best || cost < best_cost) { best = sb; best_cost = cost; *ovf_units = ou; *total = bytes; }
+    }
+    return best;
+}
+
 // Expected size of the postings table of a wide filter (0: not applicable), from a sample of 65 536 k-mers.
 uint64_t postings_estimate_bytes(const rb_ibf *f, cudaStream_t st)
 {
@@ -337,6 +366,15 @@ uint64_t postings_estimate_bytes(const rb_ibf *f, cudaStream_t st)
         uint64_t ou = 0, total = 0;
         if (r0 < 0 || !rb::slots_choose(lengths, (uint32_t)f->k, ~0ull, &sb, &ou, &total)) { cudaGetLastError(); return 0; }
         return total;
+    }
+    if (!lay && rb::slots_applicable(fv)) {                                // automatic: slots of one or two lines for mid-length lists
+        if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); return 0; }
+        std::vector<uint32_t> lengths;
+        const int r0 = rb::slots_sample_lengths(fv, d_tmp, n_sample, &lengths, f->sm_count, st);
+        cudaFree(d_tmp);
+        uint64_t ou = 0, total = 0;
+        if (r0 >= 0 && auto_slot_bytes(lengths, (uint32_t)f->k, ~0ull, &ou, &total)) return total;
+        cudaGetLastError();
     }
     if (!rb::postings_applicable(fv)) return 0;
     if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -395,20 +433,26 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
         // and no pointer chase, but the counting is bound by the shared-memory pipe (ATOMS wavefronts), and staging the lists
         // through shared memory adds a third to its load: measured 6.8 ms against 6.3 ms per 65 536 chunks on BASELINE
         // config #3 (profiles/r2_c_slots_cfg3_ncu.json), so it stays opt-in.
+        // Without RB_POSTINGS_LAYOUT: slots of one or two lines when the sampled lists are of middle length (auto_slot_bytes),
+        // else the lists; whatever goes wrong with automatic slots falls back to the lists.
         const char *lay = std::getenv("RB_POSTINGS_LAYOUT");
         const bool want_slots = lay && lay[0] == 's';
-        if (want_slots && rb::slots_applicable(fv)) {
+        const bool auto_slots = !lay;
+        if ((want_slots || auto_slots) && rb::slots_applicable(fv)) do {
             const uint64_t n_kmers = 1ull << (2 * f->k);
             const uint32_t n_sample = (uint32_t)std::min<uint64_t>(65536, n_kmers);
             uint32_t *d_tmp = nullptr;
-            if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            if (cudaMalloc(&d_tmp, (size_t)n_sample * 4) != cudaSuccess) { cudaGetLastError(); if (auto_slots) break; return nullptr; }
             std::vector<uint32_t> lengths;
             const int r0 = rb::slots_sample_lengths(fv, d_tmp, n_sample, &lengths, f->sm_count, st);
             cudaFree(d_tmp);
-            if (r0 < 0) { cudaGetLastError(); return nullptr; }
+            if (r0 < 0) { cudaGetLastError(); if (auto_slots) break; return nullptr; }
             uint32_t slot_bytes = 0;
             uint64_t ovf_units = 0, total = 0;
-            if (const char *sb = std::getenv("RB_SLOT_BYTES")) {          // tests / tuning: force the slot size
+            if (auto_slots) {
+                slot_bytes = auto_slot_bytes(lengths, (uint32_t)f->k, budget, &ovf_units, &total);
+                if (!slot_bytes) break;                                   // short or long lists, or no room: pointer + lists
+            } else if (const char *sb = std::getenv("RB_SLOT_BYTES")) {   // tests / tuning: force the slot size
                 std::vector<uint32_t> none;
                 slot_bytes = (uint32_t)std::max(128, std::min(4096, std::atoi(sb) / 128 * 128));
                 double over_units = 0;
@@ -417,11 +461,12 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
                 total = n_kmers * slot_bytes + ovf_units * 16;
                 if (total > budget || ovf_units > 0xFFFFFFF0ull) return nullptr;
             } else if (!rb::slots_choose(lengths, (uint32_t)f->k, budget, &slot_bytes, &ovf_units, &total)) return nullptr;
-            for (int attempt = 0; attempt < 2; ++attempt) {
+            bool give_up_slots = false;
+            for (int attempt = 0; attempt < 2 && !give_up_slots; ++attempt) {
                 uint8_t *d_slots = nullptr;
                 uint16_t *d_ovf = nullptr;
-                if (cudaMalloc(&d_slots, n_kmers * slot_bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-                if (cudaMalloc(&d_ovf, ovf_units * 16) != cudaSuccess) { cudaFree(d_slots); cudaGetLastError(); return nullptr; }
+                if (cudaMalloc(&d_slots, n_kmers * slot_bytes) != cudaSuccess) { cudaGetLastError(); if (auto_slots) { give_up_slots = true; break; } return nullptr; }
+                if (cudaMalloc(&d_ovf, ovf_units * 16) != cudaSuccess) { cudaFree(d_slots); cudaGetLastError(); if (auto_slots) { give_up_slots = true; break; } return nullptr; }
                 const int r1 = rb::slots_fill(fv, d_slots, slot_bytes, d_ovf, ovf_units, f->d_err + 2, f->sm_count, st);
                 if (r1 == 1) {
                     g_launches += 2;
@@ -431,12 +476,12 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
                     return reinterpret_cast<const uint64_t *>(d_slots);
                 }
                 cudaFree(d_slots); cudaFree(d_ovf); cudaGetLastError();
-                if (r1 != -3) return nullptr;
+                if (r1 != -3) { if (auto_slots) break; return nullptr; }
                 ovf_units *= 4;                                            // the sample underestimated the long lists: once more
-                if (n_kmers * slot_bytes + ovf_units * 16 > budget || ovf_units > 0xFFFFFFF0ull) return nullptr;
+                if (n_kmers * slot_bytes + ovf_units * 16 > budget || ovf_units > 0xFFFFFFF0ull) { if (auto_slots) break; return nullptr; }
             }
-            return nullptr;
-        }
+            if (!auto_slots) return nullptr;
+        } while (false);
         // pointer + lists.  Size known only after counting: sample first, then count everything, then fill.
         if (!rb::postings_applicable(fv)) return nullptr;
         const uint64_t n_kmers = 1ull << (2 * f->k);

@@ -452,11 +452,15 @@ def test_postings_slots(n_blocks, order, slot_bytes, ring, monkeypatch):
     short = [250] * 40 + [0, 1, k - 1, k, k + 1, 31, 64, 100, 249, 251, 254 + k]
     sb, so = synth.ragged_reads(plan["bases"], short, seed=21, frac_from_ref=0.7, n_frac=0.004, lower_frac=0.1)
     sexp = of.count_batch(sb, so, lut, n_threads=8)
-    assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)                 # 8-bit counters
-    assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
     longer = [250] * 8 + [255 + k, 400, 700, 1500]
     lb, lo = synth.ragged_reads(plan["bases"], longer, seed=22, frac_from_ref=0.7, n_frac=0.003, lower_frac=0.1)
-    assert_same_results(gf.count_batch(lb, lo, lut, dense=True), of.count_batch(lb, lo, lut, n_threads=8))   # 16-bit counters
+    lexp = of.count_batch(lb, lo, lut, n_threads=8)
+    # slots of 128 / 256 bytes: 8 / 16 lanes load a slot straight into registers (default), or the bulk-copy ring kernel
+    for direct in (("1", "0") if gf.kmer_table_bytes() < 4 ** k * 384 + (64 << 20) else ("1",)):
+        monkeypatch.setenv("RB_SLOTS_SUB", direct)
+        assert_same_results(gf.count_batch(sb, so, lut, dense=True), sexp)                 # 8-bit counters
+        assert_same_results(gf.count_batch(sb, so, lut, dense=False), sexp, dense=False)
+        assert_same_results(gf.count_batch(lb, lo, lut, dense=True), lexp)                 # 16-bit counters
     # the measured-geometry traffic of the roofline: a slot per (position, strand) + what overflowed
     import torch
     d_b, d_o = torch.from_numpy(sb).cuda(), torch.from_numpy(so.astype(np.int64)).cuda()

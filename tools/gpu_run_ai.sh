@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out
+timeout 600 python __graft_entry__.py smoke 2>&1 | tail -1
+timeout 2400 python -m pytest tests -q -m gpu -x 2>&1 | tail -5 > $O/ai_pytest.log
+cat $O/ai_pytest.log
+for w in w32_200Mb_2020bins w64_400Mb_4040bins w128_800Mb_8080bins w256_1.6Gb_16160bins w16_k15; do
+  timeout 600 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline > $O/ai_${w}.json 2>> $O/ai.err
+  python - <<P
+import json
+d=json.loads(open('gpurun_out/ai_${w}.json').read().strip().splitlines()[-1]); r=d['roofline']
+print("$w value %.4g e2e %.4g kernel %s kernel_ms %.3f frac %.3f kind %s table %.2f GB build %.0f ms parity %s"%(d['value'],d['e2e']['value'],r['kernel'],r['kernel_ms'],r['frac'],d['config'].get('kmer_table_kind'),d['config'].get('kmer_table_bytes',0)/1e9,d['config'].get('kmer_table_build_ms') or -1, 'oracle' in str(d.get('parity'))))
+P
+done
+tail -n 3 $O/ai.err
