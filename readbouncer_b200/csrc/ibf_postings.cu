@@ -470,26 +470,27 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
 // and then four steps' units requested before the first counter is touched (64 .. 16 lists in flight per warp in 16
 // registers).  The order of the ids inside a list does not matter (counting is commutative), so the same table serves both
 // kernels; the launcher picks by the mean list length of the table.
+// One increment unless the id is a pad (>= sentinel), as ONE predicated shared-memory reduction: written as `if (id <
+// sentinel) bump(...)` the compiler wraps every increment into a divergence region (BSSY / BRA / BSYNC were 28 % of the
+// instructions of the first version, profiles/r2_aj_slots_sub_w32_ncu.json).  cnt_s = shared-window address of the counters.
 template <int CB>
-__device__ __forceinline__ void add_ids_skip(uint32_t *cnt, const uint4 v, const uint32_t sentinel)
+__device__ __forceinline__ void bump_if_real(const uint32_t cnt_s, const uint32_t v, const uint32_t sentinel)
 {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if ((w[i] & 0xFFFFu) != sentinel) bump<CB>(cnt, w[i]);
-        if ((w[i] >> 16) != sentinel) bump<CB>(cnt, w[i] >> 16);
-    }
+    const uint32_t id = v & 0xFFFFu;
+    const uint32_t addr = cnt_s + (CB == 8 ? (v & 0xFFFCu) : ((v & 0xFFFEu) << 1));
+    const uint32_t inc = __funnelshift_l(0u, 1u, v << (CB == 8 ? 3 : 4));
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                 :: "r"(addr), "r"(inc), "r"(id), "r"(sentinel) : "memory");
 }
 
-// the same for slots: every id >= sentinel is a pad (slot_pad_id)
 template <int CB>
-__device__ __forceinline__ void add_ids_skip_ge(uint32_t *cnt, const uint4 v, const uint32_t sentinel)
+__device__ __forceinline__ void add_ids_real(const uint32_t cnt_s, const uint4 v, const uint32_t sentinel)
 {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        if ((w[i] & 0xFFFFu) < sentinel) bump<CB>(cnt, w[i]);
-        if ((w[i] >> 16) < sentinel) bump<CB>(cnt, w[i] >> 16);
+        bump_if_real<CB>(cnt_s, w[i], sentinel);
+        bump_if_real<CB>(cnt_s, w[i] >> 16, sentinel);
     }
 }
 
@@ -512,7 +513,8 @@ count_postings_sub_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, c
     const uint32_t kbits = 2 * k;
     const uint32_t kmask = kbits >= 32 ? ~0u : ((1u << kbits) - 1u);
     const uint32_t sentinel = postings_sentinel(a.fv.n_bins_local);
-    uint32_t *const cnt = (grp & 1u) ? cntR : cntF;                      // pairs alternate strands and every step starts even
+    // pairs alternate strands and every step starts even: a lane always counts into the same strand's counters
+    const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared((grp & 1u) ? cntR : cntF);
 
     for (uint32_t w = tid; w < 2 * cnt_words; w += kPostThreads) s_mem[w] = 0;
 
@@ -567,21 +569,22 @@ count_postings_sub_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, c
                         }
                     }
                     uint4 v[U];
+                    const uint32_t pads = sentinel | (sentinel << 16);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        v[u] = make_uint4(0, 0, 0, 0);
+                        v[u] = make_uint4(pads, pads, pads, pads);         // lanes past the end of the list count nothing
                         if (sub < n_u[u]) v[u] = __ldg(ids + p0[u] + sub);
                     }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (sub < n_u[u]) add_ids_skip<CB>(cnt, v[u], sentinel);
+                        add_ids_real<CB>(cnt_s, v[u], sentinel);
                         // lists of more than LG units: the group walks on.  (Loading a lane's second unit up front as well was
                         // measured 10-25 % slower at every list length, profiles/r2_ab_postings_sub_sweep.jsonl.)
                         for (uint32_t o = LG; o < n_u[u]; o += LG)
-                            if (o + sub < n_u[u]) add_ids_skip<CB>(cnt, __ldg(ids + p0[u] + o + sub), sentinel);
+                            if (o + sub < n_u[u]) add_ids_real<CB>(cnt_s, __ldg(ids + p0[u] + o + sub), sentinel);
                     }
-                    __syncwarp();
                     // windows with a non-ACGT base: the whole warp evaluates the rows (rare)
+                    if (__any_sync(0xffffffffu, hashed != 0))
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const uint32_t hm = __ballot_sync(0xffffffffu, (hashed >> u) & 1u);
@@ -1017,7 +1020,8 @@ count_slots_sub_kernel(const CountArgs a, const uint8_t *__restrict__ slots, con
     const uint32_t kbits = 2 * k;
     const uint32_t kmask = kbits >= 32 ? ~0u : ((1u << kbits) - 1u);
     const uint32_t sentinel = postings_sentinel(a.fv.n_bins_local);
-    uint32_t *const cnt = (grp & 1u) ? cntR : cntF;                      // pairs alternate strands and every step starts even
+    // pairs alternate strands and every step starts even: a lane always counts into the same strand's counters
+    const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared((grp & 1u) ? cntR : cntF);
 
     for (uint32_t w = tid; w < 2 * cnt_words; w += kPostThreads) s_mem[w] = 0;
 
@@ -1077,15 +1081,15 @@ count_slots_sub_kernel(const CountArgs a, const uint8_t *__restrict__ slots, con
                         const uint32_t h2 = __shfl_sync(0xffffffffu, v[u].z, grp * LG);
                         const uint32_t n = h0 & 0xFFFFu;
                         if (n == kSlotOverflow) {                          // the list lives in the overflow area: h1 = first unit, h2 = units
-                            for (uint32_t o = sub; o < h2; o += LG) add_ids_skip_ge<CB>(cnt, __ldg(ovf + h1 + o), sentinel);
+                            for (uint32_t o = sub; o < h2; o += LG) add_ids_real<CB>(cnt_s, __ldg(ovf + h1 + o), sentinel);
                         } else if (n != 0) {
                             uint4 w = v[u];
                             if (sub == 0) { w.x = sentinel | (sentinel << 16); w.y = w.x; }     // the header is not ids
-                            add_ids_skip_ge<CB>(cnt, w, sentinel);
+                            add_ids_real<CB>(cnt_s, w, sentinel);
                         }
                     }
-                    __syncwarp();
                     // windows with a non-ACGT base: the whole warp evaluates the rows (rare)
+                    if (__any_sync(0xffffffffu, hashed != 0))
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const uint32_t hm = __ballot_sync(0xffffffffu, (hashed >> u) & 1u);
