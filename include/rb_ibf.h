@@ -260,9 +260,11 @@ RB_API int rb_keys_combine_nccl(void *nccl_comm, uint64_t *d_keys, uint64_t n, r
  * k-mer (2 bytes each, ~50 GB for a human-genome filter at k=13) replaces streaming 2*h rows of
  * thousands of bytes per position; same policy, budget and env switches.  Two layouts: pointer + lists
  * of 16-byte units read straight into registers (default; lists averaging up to 16 units are walked by groups of 2 / 4 / 8
- * lanes, longer ones by the whole warp -- RB_POSTINGS_SUB=0/2/4/8 forces one), or (RB_POSTINGS_LAYOUT=slots) a fixed,
+ * lanes, longer ones by the whole warp -- RB_POSTINGS_SUB=0/2/4/8 forces one), or a fixed,
  * 128-byte-aligned slot per k-mer (size chosen from the sampled list lengths; the few longer lists go to an
- * overflow area) fetched by one bulk copy into a shared-memory ring.
+ * overflow area): slots of one or two lines are loaded by groups of 8 / 16 lanes and are chosen AUTOMATICALLY for lists
+ * averaging 2.6..14 units (2 000..8 000 bins); larger slots (RB_POSTINGS_LAYOUT=slots only) are fetched by one bulk copy
+ * into a shared-memory ring.  RB_POSTINGS_LAYOUT=lists / slots forces a layout.
  *
  * SUPPORTED ENVELOPE of the table paths (outside it results are the same, from the hashed / streaming kernels):
  *   rows <= 2 words (<= 128 bins): window tables for k + span - 1 <= 16, i.e. span 3 up to k = 14, span 2 up to k = 15,
