@@ -207,7 +207,9 @@ RB_API int rb_ibf_transfer_policy(const rb_ibf *f, int *choice, double *ns_per_b
 
 /* Device-pointer variant.  d_keys [n_lut][n_reads] (required) receives the packed summaries;
  * d_counts_* and d_read_flag may be NULL.  max_read_len (>= every read length, 0 = assume
- * 65535) only selects kernel variants.  Work is enqueued on `stream`; no host sync. */
+ * 65535) only selects kernel variants (narrower counters for short reads).  A read LONGER than a non-zero max_read_len
+ * promised is never miscounted: the kernels that rely on the promise give it read_flag 3 and key 0 (not classified);
+ * rb_ibf_count_batch computes the maximum itself, so flag 3 cannot occur there.  Work is enqueued on `stream`; no host sync. */
 RB_API int rb_ibf_count_batch_dev(const rb_ibf *f, const uint8_t *d_bases, const uint64_t *d_read_off,
                                   uint64_t n_reads, uint32_t max_read_len, const uint16_t *d_thr_lut,
                                   uint32_t n_lut, uint64_t *d_keys, uint16_t *d_counts_fwd,

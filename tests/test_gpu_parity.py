@@ -370,6 +370,40 @@ def test_packed_pieces_ship_the_bad_plane_only_when_needed(monkeypatch):
     assert some - clean < 5 * (1 << 20) / 8 + 4096          # four dirty pieces of 1 MB of bases: one more bit per base each
 
 
+@pytest.mark.parametrize("n_bins,k,layout", [(100, 11, ""), (60, 10, ""), (300, 10, ""), (1000, 10, ""), (1100, 11, "lists"),
+                                             (1100, 11, "slots")])
+def test_broken_max_read_len_promise_is_flagged(n_bins, k, layout, monkeypatch):
+    """rb_ibf_count_batch_dev: max_read_len selects narrow counters.  A read longer than promised must come back as read_flag 3
+    with key 0 (or, from kernels that do not rely on the promise, fully classified) -- never with wrapped counters -- and the
+    other reads of the batch must be unaffected.  Window table, group-loaded table, postings lists and slots."""
+    import torch
+    if layout:
+        monkeypatch.setenv("RB_POSTINGS_LAYOUT", layout)
+        monkeypatch.setenv("RB_CTABLE", "0")
+    plan, of, gf = make_filter_pair(n_bins, 1500, 2000, k)
+    gf.enable_kmer_table(0)
+    lengths = [250] * 20 + [1400, 250, 300, 249]                       # reads 20 and 22 break the promise of 250
+    bases, off = synth.ragged_reads(plan["bases"], lengths, seed=41, frac_from_ref=1.0, n_frac=0.0)
+    lut = rb.threshold_lut(0.1, k)
+    exp = of.count_batch(bases, off, lut, dense=False, n_threads=4)
+    n = len(lengths)
+    d_b, d_o = torch.from_numpy(bases).cuda(), torch.from_numpy(off.astype(np.int64)).cuda()
+    d_lut = torch.from_numpy(lut.view(np.int16)).cuda()
+    d_keys = torch.full((n,), -1, dtype=torch.int64, device="cuda")
+    d_flag = torch.full((n,), 77, dtype=torch.uint8, device="cuda")
+    gf.count_batch_dev(d_b, d_o, n, d_lut, 1, d_keys, max_read_len=250, d_read_flag=d_flag)
+    torch.cuda.synchronize()
+    flag = d_flag.cpu().numpy()
+    mx, hit, am = rb.keys_decode(d_keys.cpu().numpy().view(np.uint64))
+    for i in range(n):
+        if flag[i] == 3:
+            assert lengths[i] > 250 and (mx[i], hit[i]) == (0, 0), i
+        else:
+            assert flag[i] == exp["short_read"][i], i
+            assert (mx[i], hit[i], am[i]) == (exp["max_count"][i], exp["hit"][i], exp["argmax_bin"][i]), i
+    assert exp["hit"][20] == 1 and exp["max_count"][20] > 255           # the case that would wrap an 8-bit counter
+
+
 @pytest.mark.parametrize("inflight", ["", "atomic", "1", "8"])
 @pytest.mark.parametrize("n_bins,k", [(129, 11), (192, 10), (256, 11), (257, 11), (320, 10), (512, 11), (513, 10), (1000, 11), (1024, 10),
                                         (1025, 10), (1500, 11), (2048, 10)])
