@@ -67,7 +67,7 @@ __device__ __forceinline__ void bump_word(uint32_t *cnt, uint32_t w)
 }
 
 // the lane's two mask words of a window that is not in the table, from the original rows
-__device__ __noinline__ uint4 piece_hashed(const FilterView &fv, const uint8_t *dig, const bool rev, const uint32_t w0)
+__device__ __forceinline__ uint4 piece_hashed(const FilterView &fv, const uint8_t *dig, const bool rev, const uint32_t w0)
 {
     const HashParams &hp = fv.hp;
     uint64_t H = 0, pw = 1;
