@@ -250,7 +250,7 @@ __device__ __forceinline__ void count_list(const ListRegs &r, uint32_t *cnt, con
 
 // hashing path of one (position, strand): AND of the probed rows, one warp, counters by atomics
 template <int CB>
-__device__ __noinline__ void add_hashed(const FilterView &fv, const uint8_t *dig, uint32_t strand, uint32_t *cnt, int lane)
+__device__ __forceinline__ void add_hashed_inl(const FilterView &fv, const uint8_t *dig, uint32_t strand, uint32_t *cnt, int lane)
 {
     constexpr int PER = 32 / CB;
     constexpr int SH = (PER == 4) ? 2 : 1;
@@ -271,6 +271,15 @@ __device__ __noinline__ void add_hashed(const FilterView &fv, const uint8_t *dig
             atomicAdd(cnt + (id >> SH), 1u << ((id & (PER - 1)) * CB));
         }
     }
+}
+
+// Out of line for the lane-group kernels (inlined there it costs them 7-18 %: more registers in their hot loop); inlined into
+// the warp-per-list kernel, whose CTAs then need no stack frame: 6.5 -> 5.8 ms per batch on config #3
+// (profiles/r2_aq_add_hashed_inline.jsonl).
+template <int CB>
+__device__ __noinline__ void add_hashed(const FilterView &fv, const uint8_t *dig, uint32_t strand, uint32_t *cnt, int lane)
+{
+    add_hashed_inl<CB>(fv, dig, strand, cnt, lane);
 }
 
 template <int CB>
@@ -448,7 +457,7 @@ count_postings_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, const
                     if (any_hashed) {
                         for (uint32_t t = 0; t < n_here; ++t)
                             if ((any_hashed >> t) & 1u)
-                                add_hashed<CB>(a.fv, s_dig + ((q0 + t) >> 1), (q0 + t) & 1u, ((q0 + t) & 1u) ? cntR : cntF, lane);
+                                add_hashed_inl<CB>(a.fv, s_dig + ((q0 + t) >> 1), (q0 + t) & 1u, ((q0 + t) & 1u) ? cntR : cntF, lane);
                     }
                     p0 = np0; p1 = np1; hashed = nhashed;
                 }
