@@ -183,6 +183,9 @@ count_wtable_kernel(const CountArgs a, const uint64_t *__restrict__ table)
     constexpr int B = NWP;                  // mask bits owned by a lane after the fold
     constexpr int LPW = 32 / B;             // lanes per mask word
     constexpr int IT = Sh::IT, PPI = Sh::PPI;
+    __shared__ FilterView s_fv;             // for the out-of-line hashed path: one copy per CTA, no per-thread stack frame
+    if (threadIdx.x == 0) s_fv = a.fv;
+    __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t total_warps = (uint64_t)gridDim.x * kTileWarps;
@@ -272,7 +275,7 @@ count_wtable_kernel(const CountArgs a, const uint64_t *__restrict__ table)
                                     load_slot<WT>(table + (idx * G + t) * (2 * WT), m[u]);
                                     flip[u] = fl;
                                 } else {
-                                    const SlotWords<WT> hs = slot_hashed<WT>(a.fv, pb + pos);
+                                    const SlotWords<WT> hs = slot_hashed<WT>(s_fv, pb + pos);
 #pragma unroll
                                     for (int w = 0; w < NWP; ++w) m[u][w] = hs.v[w];
                                 }
@@ -516,6 +519,11 @@ count_wgroup_kernel(const CountArgs a, const uint64_t *__restrict__ table)
     constexpr int IB = kWgIB;
     static_assert(S * (IB - 1) + 16 <= 64 && S * (IB - 1) < 32, "a window block must fit the 64-bit stream piece");
     __shared__ __align__(16) uint16_t s_stream[kTileWarps][RPW][3][kWgRow];
+    // the out-of-line hashed path takes the filter by reference: one copy per CTA in shared memory instead of one per thread in
+    // local memory (a 304-byte stack frame written by every thread at kernel start)
+    __shared__ FilterView s_fv;
+    if (threadIdx.x == 0) s_fv = a.fv;
+    __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = (uint32_t)lane / G, t = (uint32_t)lane % G;
@@ -633,11 +641,11 @@ count_wgroup_kernel(const CountArgs a, const uint64_t *__restrict__ table)
                             } else {
                                 SlotWords<WT> hs;
                                 if constexpr (PACKED)
-                                    hs = slot_hashed_streams<WT>(a.fv, reinterpret_cast<const uint32_t *>(st_lo),
+                                    hs = slot_hashed_streams<WT>(s_fv, reinterpret_cast<const uint32_t *>(st_lo),
                                                                  reinterpret_cast<const uint32_t *>(st_hi),
                                                                  reinterpret_cast<const uint32_t *>(st_bad), sh + pos);
                                 else
-                                    hs = slot_hashed<WT>(a.fv, pr + pos);
+                                    hs = slot_hashed<WT>(s_fv, pr + pos);
 #pragma unroll
                                 for (int w = 0; w < NWP; ++w) m[u][w] = hs.v[w];
                             }
