@@ -276,7 +276,10 @@ __device__ __forceinline__ void add_hashed_inl(const FilterView &fv, const uint8
 // Out of line for the lane-group kernels (inlined there it costs them 7-18 %: more registers in their hot loop); inlined into
 // the warp-per-list kernel, whose CTAs then need no stack frame: 6.5 -> 5.8 ms per batch on config #3
 // (profiles/r2_aq_add_hashed_inline.jsonl).
-template <int CB>
+// TAG makes separate copies: ptxas gives a callee ONE register allocation, which all kernels that call it inherit -- called with
+// the shared-memory filter view of the list kernel it needs 72-80 registers, and the slot kernel, which shares nothing else with
+// that kernel, ran 17 % slower for it.
+template <int CB, int TAG = 0>
 __device__ __noinline__ void add_hashed(const FilterView &fv, const uint8_t *dig, uint32_t strand, uint32_t *cnt, int lane)
 {
     add_hashed_inl<CB>(fv, dig, strand, cnt, lane);
@@ -602,7 +605,7 @@ count_postings_sub_kernel(const CountArgs a, const uint32_t *__restrict__ ptr, c
                         for (uint32_t g = 0; g < (uint32_t)NL; ++g)
                             if ((hm >> (g * LG)) & 1u) {
                                 const uint32_t q = qb + NL * u + g;
-                                add_hashed<CB>(s_fv, s_dig + (q >> 1), q & 1u, (q & 1u) ? cntR : cntF, lane);
+                                add_hashed<CB, 1>(s_fv, s_dig + (q >> 1), q & 1u, (q & 1u) ? cntR : cntF, lane);
                             }
                     }
                 }
