@@ -404,6 +404,32 @@ def test_broken_max_read_len_promise_is_flagged(n_bins, k, layout, monkeypatch):
     assert exp["hit"][20] == 1 and exp["max_count"][20] > 255           # the case that would wrap an 8-bit counter
 
 
+@pytest.mark.parametrize("n_bins,k,env", [(300, 10, {}), (1000, 10, {}), (1100, 11, {"RB_CTABLE": "0", "RB_POSTINGS_LAYOUT": "lists"}),
+                                          (1100, 11, {"RB_CTABLE": "0", "RB_POSTINGS_LAYOUT": "slots", "RB_SLOT_BYTES": "128"})])
+def test_lane_group_kernels_edge_batches(n_bins, k, env, monkeypatch):
+    """Group-loaded table, 2-lane list kernel and slots read by lane groups on degenerate batches: four threshold tables in one
+    pass, a single read, reads that are empty / shorter than k / all N / all lower case, and a batch smaller than one CTA."""
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    plan, of, gf = make_filter_pair(n_bins, 1500, 2000, k)
+    gf.enable_kmer_table(0)
+    assert gf.kmer_table_kind() == (4 if not env else 2 if env["RB_POSTINGS_LAYOUT"] == "lists" else 3)
+    luts = np.stack([rb.threshold_lut(e, k) for e in (0.1, 0.08, 0.05, 0.15)])
+    bases, off = synth.ragged_reads(plan["bases"], [250, 0, k - 1, 250, 250, 300, 250], seed=5, frac_from_ref=1.0, n_frac=0.0)
+    bases[int(off[3]):int(off[4])] = ord("N")                                   # all N: every window takes the hashed path
+    lo, hi = int(off[4]), int(off[5])
+    bases[lo:hi] = np.frombuffer(bytes(bases[lo:hi]).lower(), np.uint8)          # all lower case
+    got = gf.count_batch(bases, off, luts)
+    for t in range(4):
+        exp = of.count_batch(bases, off, luts[t], dense=False, n_threads=4)
+        for key in ("max_count", "hit", "argmax_bin"):
+            assert np.array_equal(got[key][t], exp[key]), (t, key)
+    assert np.array_equal(got["read_flag"], exp["short_read"]) and got["hit"][0][4] == 1
+    # (the all-N read is one k-mer 241 times: whatever bins its three rows share, it "hits" them -- like the reference)
+    one_b, one_o = bases[:250].copy(), np.array([0, 250], np.uint64)             # a single read
+    assert_same_results(gf.count_batch(one_b, one_o, luts[0], dense=True), of.count_batch(one_b, one_o, luts[0], n_threads=1))
+
+
 @pytest.mark.parametrize("inflight", ["", "atomic", "1", "8"])
 @pytest.mark.parametrize("n_bins,k", [(129, 11), (192, 10), (256, 11), (257, 11), (320, 10), (512, 11), (513, 10), (1000, 11), (1024, 10),
                                         (1025, 10), (1500, 11), (2048, 10)])
