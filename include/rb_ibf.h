@@ -163,7 +163,7 @@ RB_API int rb_ibf_insert_batch_dev(rb_ibf *f, const uint8_t *d_bases, const uint
  * Replaces, per read, Read::count_matches / find_matches (src/IBF/IBFClassify.cpp:81-171):
  *   counts_fwd = seqan::count(filter, read), counts_rev = seqan::count(filter, revcomp(read)),
  *   thr = lut[len], hit = select_matches(...), max_count = max_matches(...).
- * n_lut thresholds tables (1 or 2; each uint16[65536]) are evaluated in the same pass so the
+ * n_lut threshold tables (1 to 4; each uint16[65536]) are evaluated in the same pass so the
  * error_rate-0.02 retry of check_unblock / classify_deplete_target needs no second launch.
  *
  * Outputs (any may be NULL): counts_* [n_reads][n_bins_local] dense per-bin counts;
