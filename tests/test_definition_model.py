@@ -1,0 +1,124 @@
+"""An INDEPENDENT second restatement of SURVEY Appendix A (A.1-A.6), written in plain Python integers straight from the
+specification text and sharing no code with oracle/ibf_oracle.c, compared with the C oracle bit for bit.
+
+Why: the reference's fixtures pin the oracle only for filters of 2 and 4 bins (binWidth 1).  Rows of several words
+(binWidth > 1, every benchmarked configuration), N / IUPAC bases inside k-mers, k other than 13 / 15 and a bin count that is
+not a multiple of 64 are "parity unpinned" corners.  Two implementations that were written independently from
+the same specification and agree on those corners do not replace a reference fixture, but they rule out a slip of one of
+them (word order inside a row, bit order inside a word, the reverse strand, the digit of N)."""
+import numpy as np
+import pytest
+
+import oracle
+
+SEED = 0x90B45D39FB6DA1FA       # A.1
+SHIFT = 27
+M64 = (1 << 64) - 1
+RANK = {c: r for r, cs in enumerate(("Aa", "Cc", "Gg", "Tt")) for c in cs}      # A.3: everything else -> 4
+COMP = {"A": "T", "C": "G", "G": "C", "T": "A", "a": "t", "c": "g", "g": "c", "t": "a"}
+
+
+class ModelIBF:
+    """The filter as a Python set of bit addresses."""
+
+    def __init__(self, n_bins, n_hash, k, n_bits):
+        self.n_bins, self.h, self.k, self.n_bits = n_bins, n_hash, k, n_bits
+        self.bin_width = -(-n_bins // 64)
+        self.block_bits = 64 * self.bin_width
+        self.n_blocks = n_bits // self.block_bits
+        self.pre = [i ^ ((k * SEED) & M64) for i in range(n_hash)]
+        self.bits = set()
+
+    def rows(self, kmer):
+        v = 0
+        for c in kmer:
+            v = (v * 5 + RANK.get(c, 4)) & M64
+        out = []
+        for p in self.pre:
+            x = (p * v) & M64
+            x ^= x >> SHIFT
+            out.append(x % self.n_blocks)
+        return out
+
+    def insert(self, text, b):
+        for j in range(len(text) - self.k + 1):
+            for r in self.rows(text[j:j + self.k]):
+                self.bits.add(r * self.block_bits + b)
+
+    def count(self, text):
+        counts = [0] * self.n_bins
+        for j in range(len(text) - self.k + 1):
+            rows = self.rows(text[j:j + self.k])
+            for b in range(self.n_bins):
+                if all(r * self.block_bits + b in self.bits for r in rows):
+                    counts[b] += 1
+        return counts
+
+    def words(self):
+        w = np.zeros(self.n_bits // 64, np.uint64)
+        for p in self.bits:
+            w[p >> 6] |= np.uint64(1) << np.uint64(p & 63)
+        return w
+
+
+def revcomp(s):
+    return "".join(COMP.get(c, "N") for c in reversed(s))
+
+
+def rand_text(rng, n, alphabet="ACGT"):
+    return "".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=n))
+
+
+@pytest.mark.parametrize("n_bins,k,rows", [(2, 13, 4001), (64, 13, 3001), (65, 13, 3001), (100, 13, 2003), (130, 11, 1999),
+                                           (200, 15, 1501), (70, 17, 2500), (257, 9, 997)])
+def test_c_oracle_equals_the_python_definition(n_bins, k, rows):
+    rng = np.random.default_rng(1000 * n_bins + k)
+    bin_width = -(-n_bins // 64)
+    n_bits = rows * 64 * bin_width
+    model = ModelIBF(n_bins, 3, k, n_bits)
+    orc = oracle.OracleIBF.create(n_bins, 3, k, n_bits)
+    texts = []
+    for b in range(n_bins):
+        t = rand_text(rng, int(rng.integers(k - 2, 70)))          # some texts shorter than k: nothing inserted (A.5)
+        if b % 7 == 3 and len(t) > k:                              # N, lower case and IUPAC inside k-mers
+            t = t[:5] + "N" + t[6:9].lower() + "R" + t[10:]
+        texts.append(t)
+        model.insert(t, b)
+        orc.insert(t.encode(), b)
+    # A.2 / A.5: the same bits at the same addresses
+    assert np.array_equal(orc.words()[:n_bits // 64], model.words())
+    # A.6 on both strands, reads made of inserted pieces (so that counts are not all zero), with errors and an N
+    for i in range(4):
+        pieces = [texts[int(rng.integers(n_bins))] for _ in range(4)]
+        read = "".join(pieces)[:150]
+        if i == 1:
+            read = read[:40] + "N" + read[41:]
+        if i == 2:
+            read = read.lower()
+        if len(read) < k:
+            continue
+        exp_f, exp_r = model.count(read), model.count(revcomp(read))
+        assert sum(exp_f) > 0
+        assert list(orc.count(read.encode())) == exp_f
+        assert list(orc.count(read.encode(), revcomp=True)) == exp_r
+
+
+def test_python_definition_reproduces_a_reference_fixture_count(golden_ibf_paths, known):
+    """The model itself is anchored to the reference: the 35-mer known answer of read.hpp:113,139-140 (23 per bin, 0 reverse)
+    against libIBFTests/data/test.ibf, evaluated with the model's hash / row / layout arithmetic on the file's words."""
+    f = oracle.OracleIBF.load(golden_ibf_paths["lib_test"])
+    words = f.words()
+    m = ModelIBF(2, 3, 13, 79121216)
+    read = "AAAAAAACCCCCCCCCGAGAGAGGAGAGAGGAGAG"
+
+    def count(text):
+        c = [0, 0]
+        for j in range(len(text) - 12):
+            rows = m.rows(text[j:j + 13])
+            for b in range(2):
+                if all((int(words[(r * m.block_bits + b) >> 6]) >> ((r * m.block_bits + b) & 63)) & 1 for r in rows):
+                    c[b] += 1
+        return c
+
+    assert count(read) == [23, 23]
+    assert count(revcomp(read)) == [0, 0]
