@@ -201,9 +201,9 @@ RB_API int rb_ibf_transfer_policy(const rb_ibf *f, int *choice, double *ns_per_b
  * key == 0 means no bin passed; keys are < 2^49, so signed and unsigned 64-bit MAX agree.  The
  * elementwise MAX of the keys of all bin shards is the key of the whole filter, which is what the
  * NCCL combine of the bin-sharded mode reduces. */
-#define RB_KEY_HIT(key) ((uint8_t)(((key) >> 48) & 1u))
-#define RB_KEY_MAX_COUNT(key) ((uint16_t)(((key) >> 32) & 0xFFFFu))
-#define RB_KEY_ARGMAX_BIN(key) ((key) ? ~(uint32_t)((key) & 0xFFFFFFFFu) : 0xFFFFFFFFu)
+#define RB_KEY_HIT(key) ((uint8_t)(((uint64_t)(key) >> 48) & 1u))
+#define RB_KEY_MAX_COUNT(key) ((uint16_t)(((uint64_t)(key) >> 32) & 0xFFFFu))
+#define RB_KEY_ARGMAX_BIN(key) ((key) ? ~(uint32_t)((uint64_t)(key) & 0xFFFFFFFFu) : 0xFFFFFFFFu)
 
 /* Device-pointer variant.  d_keys [n_lut][n_reads] (required) receives the packed summaries;
  * d_counts_* and d_read_flag may be NULL.  max_read_len (>= every read length, 0 = assume

@@ -121,6 +121,17 @@ def _compile(src, out, link=True):
     return out
 
 
+def test_plain_c_client_of_the_header(tmp_path):
+    """include/rb_ibf.h is valid, warning-free C99 and a pure C program (what cgo / JNI / N-API would bind) gets the
+    reference's known answers from the host-side entry points; on this GPU-less host the compute calls fail loudly."""
+    exe = str(tmp_path / "c_client")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + INCLUDE,
+                           os.path.join(ROOT, "tests", "c", "test_c_client.c"), "-L" + LIBDIR, "-lrb_ibf",
+                           "-Wl,-rpath," + LIBDIR, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "c client ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_fast_mod_exhaustive_edges(tmp_path):
     exe = _compile(os.path.join(ROOT, "tests", "cpp", "test_fastmod.cpp"), str(tmp_path / "test_fastmod"), link=False)
     out = subprocess.run([exe], capture_output=True, text=True)
