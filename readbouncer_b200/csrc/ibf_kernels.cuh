@@ -54,7 +54,7 @@ struct InsertArgs {
 // shares of the reads) leaves the SMs that finish early idle: memory channels are not equally far from every SM.  Several
 // waves of smaller shares let the block scheduler hand out work as SMs become free: measured on BASELINE config #2's shape
 // 2.38 -> 2.22 ms (k = 13), 6.90 -> 5.46 ms (k = 15), 8.34 -> 6.82 ms (k = 17) per batch with 16 waves
-// (profiles/r2_c_grid_waves.jsonl).  Default 16; RB_GRID_WAVES overrides (measurements).
+// (profiles/r2_d_grid_waves.jsonl).  Default 16; RB_GRID_WAVES overrides (measurements).
 int grid_waves();
 
 // which: 0 auto, 1 tile kernel, 2 streaming kernel.  Returns number of kernel launches or <0.

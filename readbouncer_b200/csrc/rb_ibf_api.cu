@@ -77,7 +77,7 @@ struct rb_ibf {
     mutable int table_kind = 0;             // 0 none, 1 dense k-mer / window table, 2 postings, 4 k-mer table loaded by lane groups
     mutable uint32_t *d_post_ptr = nullptr;
     mutable uint16_t *d_post_ids = nullptr;
-    // ... or, by default, the same lists as one fixed slot per k-mer + an overflow area (table_kind 3)
+    // ... or the same lists as one fixed slot per k-mer + an overflow area (table_kind 3: automatic for mid-length lists, else RB_POSTINGS_LAYOUT=slots)
     mutable uint8_t *d_slots = nullptr;
     mutable uint16_t *d_slot_ovf = nullptr;
     mutable uint32_t slot_bytes = 0;
@@ -432,7 +432,7 @@ const uint64_t *ensure_table(const rb_ibf *f, cudaStream_t st, bool force, uint6
         // RB_POSTINGS_LAYOUT=slots: one fixed slot per k-mer fetched by bulk copies into shared-memory rings -- fewer DRAM bytes
         // and no pointer chase, but the counting is bound by the shared-memory pipe (ATOMS wavefronts), and staging the lists
         // through shared memory adds a third to its load: measured 6.8 ms against 6.3 ms per 65 536 chunks on BASELINE
-        // config #3 (profiles/r2_c_slots_cfg3_ncu.json), so it stays opt-in.
+        // config #3 (profiles/r2_c_slots_v2_cfg3_ncu_full.json), so it stays opt-in.
         // Without RB_POSTINGS_LAYOUT: slots of one or two lines when the sampled lists are of middle length (auto_slot_bytes),
         // else the lists; whatever goes wrong with automatic slots falls back to the lists.
         const char *lay = std::getenv("RB_POSTINGS_LAYOUT");
