@@ -5,11 +5,15 @@ Why: the reference's fixtures pin the oracle only for filters of 2 and 4 bins (b
 (binWidth > 1, every benchmarked configuration), N / IUPAC bases inside k-mers, k other than 13 / 15 and a bin count that is
 not a multiple of 64 are "parity unpinned" corners.  Two implementations that were written independently from
 the same specification and agree on those corners do not replace a reference fixture, but they rule out a slip of one of
-them (word order inside a row, bit order inside a word, the reverse strand, the digit of N)."""
+them (word order inside a row, bit order inside a word, the reverse strand, the digit of N).
+
+The second half does the same for the build-side host logic: statement-level Python models of IBF::cutOutNNNs and of the fragment
+loop (IBFBuild.cpp:112-132, 165-202, quirks Q1-Q3) against the oracle AND the product's host entry points on random inputs."""
 import numpy as np
 import pytest
 
 import oracle
+import readbouncer_b200 as rb
 
 SEED = 0x90B45D39FB6DA1FA       # A.1
 SHIFT = 27
@@ -122,3 +126,64 @@ def test_python_definition_reproduces_a_reference_fixture_count(golden_ibf_paths
 
     assert count(read) == [23, 23]
     assert count(revcomp(read)) == [0, 0]
+
+
+# ---- build-side host logic: behaviour models of the reference's own loops --------------------------------------------------
+NPOS = 1 << 64
+
+
+def model_cut_out_nnns(seq):
+    """IBF::cutOutNNNs + the concatenation at IBFBuild.cpp:81-88, statement by statement with Python string methods
+    (std::string::find_first_not_of / find / substr semantics; npos = 2^64 - 1 compares greater than any length)."""
+    seqlen, pieces, end = len(seq), [], 0
+    while True:
+        start = next((i for i in range(end, seqlen) if seq[i] != "N"), NPOS)       # find_first_not_of("N", end)
+        if start == NPOS:
+            break
+        end = seq.find("N", start)
+        end = NPOS if end < 0 else end
+        if end > seqlen:
+            pieces.append(seq[start:start + max(0, seqlen - start - 1)])            # substr(start, seqlen - start - 1)
+            break
+        pieces.append(seq[start:end])
+    return "".join(pieces)
+
+
+def model_fragment_schedule(seqlen, F, k):
+    """The fragment loop of add_sequences_to_filter (IBFBuild.cpp:165-202) with its signed arithmetic; overlap_length = 1500
+    only makes the first start negative, which clamps to 0."""
+    out, idx = [], 0
+    start = max(0, idx * F - 1500 + 1)
+    while start < seqlen - 1:
+        end = min((idx + 1) * F, seqlen)
+        out.append((start, end))
+        idx += 1
+        start = idx * F - k + 1
+    return out
+
+
+def test_cut_out_nnns_equals_the_statement_level_model():
+    rng = np.random.default_rng(5)
+    cases = ["", "N", "NN", "A", "AN", "NA", "ANNA", "ACGT", "ACGTN", "NNACGTNN", "ACGTNNNACGT", "nACGTn", "ACGNnNT"]
+    for _ in range(400):
+        n = int(rng.integers(0, 40))
+        cases.append("".join("ACGTNNNn"[i] for i in rng.integers(0, 8, size=n)))
+    for s in cases:
+        exp = model_cut_out_nnns(s).encode()
+        assert oracle.cut_out_nnns(s) == exp, s
+        assert rb.cut_out_nnns(s) == exp, s
+
+
+def test_fragment_schedule_equals_the_statement_level_model():
+    rng = np.random.default_rng(6)
+    cases = [(0, 100, 13), (1, 100, 13), (2, 100, 13), (99, 100, 13), (100, 100, 13), (101, 100, 13), (188, 100, 13), (189, 100, 13),
+             (190, 100, 13), (199990, 100000, 13), (199989, 100000, 13), (299999, 100000, 13), (5000000, 100000, 13), (4999999, 100000, 13)]
+    for _ in range(600):
+        F = int(rng.integers(20, 500))
+        k = int(rng.integers(2, 19))
+        cases.append((int(rng.integers(0, 6 * F)), F, k))
+    for seqlen, F, k in cases:
+        exp = model_fragment_schedule(seqlen, F, k)
+        for impl in (oracle.fragment_schedule, rb.fragment_schedule):
+            b, e = impl(seqlen, F, k)
+            assert [(int(x), int(y)) for x, y in zip(b, e)] == exp, (impl.__module__, seqlen, F, k)
