@@ -8,7 +8,9 @@ the same specification and agree on those corners do not replace a reference fix
 them (word order inside a row, bit order inside a word, the reverse strand, the digit of N).
 
 The second half does the same for the build-side host logic: statement-level Python models of IBF::cutOutNNNs and of the fragment
-loop (IBFBuild.cpp:112-132, 165-202, quirks Q1-Q3) against the oracle AND the product's host entry points on random inputs."""
+loop (IBFBuild.cpp:112-132, 165-202, quirks Q1-Q3) against the oracle AND the product's host entry points on random inputs; the
+third restates calculateCI and the threshold wrap (IBF.hpp:268-338, IBFClassify.cpp:102-109) with Python's math module and checks
+both threshold tables for 48 (error rate, k) pairs."""
 import numpy as np
 import pytest
 
@@ -187,3 +189,54 @@ def test_fragment_schedule_equals_the_statement_level_model():
         for impl in (oracle.fragment_schedule, rb.fragment_schedule):
             b, e = impl(seqlen, F, k)
             assert [(int(x), int(y)) for x, y in zip(b, e)] == exp, (impl.__module__, seqlen, F, k)
+
+
+# ---- thresholds: calculateCI / NormalCDFInverse / the int16 -> uint16 wrap, restated with Python's math module ------------------
+def model_ci(r, kmer_size, readlen, confidence):
+    """interleave::calculateCI (IBF.hpp:320-338) with RationalApproximation / NormalCDFInverse (:268-308); kmer_size arrives as
+    uint8_t; the uint16_t casts take the low 16 bits of the truncated value (what x86-64 does for in-range doubles)."""
+    import math
+    k = float(kmer_size & 0xFF)
+    q = 1.0 - math.pow(1.0 - r, k)
+    L = float(readlen) - k + 1.0
+    var_n = (L * (1.0 - q) * (q * (2.0 * k + (2.0 / r) - 1.0) - 2.0 * k) + k * (k - 1.0) * math.pow(1.0 - q, 2.0)
+             + (2.0 * (1.0 - q) / math.pow(r, 2.0)) * ((1.0 + (k - 1.0) * (1.0 - q)) * r - q))
+    p = 1.0 - (1 - confidence) / 2.0
+    c, d = (2.515517, 0.802853, 0.010328), (1.432788, 0.189269, 0.001308)
+
+    def rational(t):
+        return t - ((c[2] * t + c[1]) * t + c[0]) / (((d[2] * t + d[1]) * t + d[0]) * t + 1.0)
+
+    z = -rational(math.sqrt(-2.0 * math.log(p))) if p < 0.5 else rational(math.sqrt(-2.0 * math.log(1.0 - p)))
+    if var_n < 0:
+        return None                                           # sqrt of a negative: NaN, cast undefined (reads shorter than ~k)
+    low = int(math.floor(L * q - z * math.sqrt(var_n))) & 0xFFFF
+    high = int(math.ceil(L * q + z * math.sqrt(var_n))) & 0xFFFF
+    return low, high
+
+
+def model_threshold(r, kmer_size, readlen, confidence=0.95):
+    """IBFClassify.cpp:102-109: uint16_t readlen; int16_t threshold = readlen - k + 1 - ci.second; passed on as uint16_t."""
+    ci = model_ci(r, kmer_size, readlen, confidence)
+    if ci is None:
+        return None
+    return ((readlen & 0xFFFF) - kmer_size + 1 - ci[1]) & 0xFFFF
+
+
+def test_thresholds_equal_the_python_restatement():
+    assert model_ci(0.1, 13, 35, 0.95) == (5, 30) and model_threshold(0.1, 13, 35) == 65529        # read.hpp:156-164
+    assert model_threshold(0.1, 13, 250) == 18 and model_threshold(0.08, 13, 250) == 34 and model_threshold(0.1, 15, 360) == 22
+    rng = np.random.default_rng(7)
+    for r in (0.03, 0.05, 0.08, 0.1, 0.12, 0.15, 0.2, 0.3):
+        for k in (9, 13, 15, 17, 20, 31):
+            lut_o, lut_p = oracle.threshold_lut(r, k), rb.threshold_lut(r, k)
+            lengths = list(range(k, 1200)) + [int(x) for x in rng.integers(1200, 65536, size=600)] + [65535]
+            for n in lengths:
+                exp = model_threshold(r, k, n)
+                if exp is None:
+                    continue
+                assert int(lut_o[n]) == exp and int(lut_p[n]) == exp, (r, k, n, exp, int(lut_o[n]), int(lut_p[n]))
+            for n in (k, 35, 250, 354, 1500, 40000):
+                ci = model_ci(r, k, n, 0.95)
+                if ci is not None:
+                    assert oracle.calculate_ci(r, k, n, 0.95) == ci and rb.calculate_ci(r, k, n, 0.95) == ci, (r, k, n)
