@@ -240,3 +240,30 @@ def test_thresholds_equal_the_python_restatement():
                 ci = model_ci(r, k, n, 0.95)
                 if ci is not None:
                     assert oracle.calculate_ci(r, k, n, 0.95) == ci and rb.calculate_ci(r, k, n, 0.95) == ci, (r, k, n)
+
+
+def test_filter_size_bits_equals_the_python_restatement():
+    """IBF::calculate_filter_size_bits (IBFBuild.cpp:404-413) and the bins-per-sequence rule (:90) with Python's math module."""
+    import math
+
+    def model(F, k, h, fp, bins):
+        max_kmers = F - k + 1
+        opt_bins = int(math.floor(bins / 64.0 + 1)) * 64
+        bin_bits = int(math.ceil(-1 / (math.pow(1 - math.pow(fp, 1.0 / h), 1.0 / float(h * max_kmers)) - 1)))
+        return bin_bits * opt_bins
+
+    assert model(100000, 13, 3, 0.01, 2) == 79121216                              # createfilter.hpp:148
+    rng = np.random.default_rng(8)
+    for _ in range(500):
+        F = int(rng.integers(50, 5_000_000))
+        k = int(rng.integers(5, 32))
+        h = int(rng.integers(1, 6))
+        fp = float(rng.choice([0.001, 0.01, 0.05, 0.1, 0.3]))
+        bins = int(rng.choice([1, 2, 63, 64, 65, 100, 127, 128, 129, 31008, 299520]))
+        if F <= k:
+            continue
+        exp = model(F, k, h, fp, bins)
+        assert oracle.filter_size_bits(F, k, h, fp, bins) == exp, (F, k, h, fp, bins)
+        assert rb.ibf_size_bits(F, k, h, fp, bins) == exp, (F, k, h, fp, bins)
+    for n in (0, 1, 99999, 100000, 100001, 4999999, 5000000):
+        assert oracle.bins_for_sequence(n, 100000) == n // 100000 + 1
